@@ -1,0 +1,72 @@
+"""ctypes binding of the C-ABI library (include/desenet_b200.h).
+
+The product has NO CPU fallback: if the CUDA library is missing or cannot be loaded, importing
+callers get a RuntimeError that says how to build it."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_uint64, c_void_p
+
+from . import build as _build
+
+_lib = None
+
+# name -> (restype, argtypes); mirrors include/desenet_b200.h one to one
+_FLOATPP = POINTER(c_void_p)
+SIGNATURES = {
+    "dsn_version": (c_int, []),
+    "dsn_error_string": (c_char_p, [c_int]),
+    "dsn_detect_decode": (c_int, [_FLOATPP, POINTER(c_int), POINTER(c_int), POINTER(c_float), POINTER(c_float),
+                                  c_int, c_int, c_int, c_int, c_void_p, _FLOATPP, c_void_p]),
+    "dsn_filter_levels": (c_int, [_FLOATPP, POINTER(c_int), POINTER(c_int), c_int, c_int, c_int, c_int, c_float, c_int,
+                                  POINTER(c_uint64), c_void_p, c_int64, c_void_p, c_void_p]),
+    "dsn_filter_z": (c_int, [c_void_p, c_int, c_int64, c_int, c_float, c_int, POINTER(c_uint64), c_void_p, c_int64,
+                             c_void_p, c_void_p]),
+    "dsn_nms_levels": (c_int, [_FLOATPP, POINTER(c_int), POINTER(c_int), POINTER(c_float), POINTER(c_float), c_int, c_int,
+                               c_int, c_int, c_void_p, c_int64, c_void_p, c_float, c_double, c_int, c_int, c_int, c_float,
+                               c_void_p, c_void_p, c_void_p]),
+    "dsn_nms_z": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int64, c_void_p, c_float, c_double, c_int, c_int,
+                          c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "dsn_seg_fused": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                              c_int, c_void_p, c_int, c_int, c_void_p]),
+    "dsn_seg_fullres": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                c_void_p, c_int, c_int, c_void_p]),
+    "dsn_upsample_bilinear_ac": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+}
+
+
+class DesenetCudaError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load (building first if the sources are newer and nvcc is present) the CUDA library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    try:
+        path = _build.build()
+    except Exception as e:  # no nvcc on this box: use the prebuilt .so that travelled with the repo
+        if not os.path.exists(path):
+            raise RuntimeError(
+                f"desenet_b200: CUDA library {path} is missing and could not be built ({e}). "
+                "Run `python -m desenet_b200.build` on a machine with nvcc; there is no CPU fallback.") from e
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = the .so is stale: rebuild
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().dsn_error_string(rc)
+        raise DesenetCudaError(f"{what} failed with code {rc}: {msg.decode() if msg else '?'}")

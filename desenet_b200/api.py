@@ -1,0 +1,282 @@
+"""Host-side mirror of the reference's interface for the post-network path: same names, argument
+meaning and error behaviour as splwany/DeSeNet, so these callables drop into the reference's
+``scripts/val.py`` / ``scripts/detect.py`` (see INTEGRATION.md and ``desenet_b200.patch``).
+
+Two ways in:
+  * strict — the reference's own tensors: ``non_max_suppression(prediction (bs,A,no), ...)``,
+    ``segoutput_to_target(full-res logits, size)``, ``batch_*(full-res logits, target)``;
+  * fused — hand the kernels what the network actually produced, before the reference materialises
+    anything: ``HeadOutputs`` (raw Detect conv outputs) instead of ``prediction`` and ``SegLogits``
+    (low-res logits before the final x8 Upsample) instead of full-res logits.  Same results, none of
+    the z / x_i / full-res-logit traffic.
+All arithmetic runs in the sm_100a kernels; there is no CPU fallback."""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+
+__all__ = [
+    "HeadOutputs", "SegLogits", "detect_forward", "non_max_suppression", "segoutput_to_target",
+    "batch_pix_accuracy", "batch_intersection_union", "seg_confusion_matrix", "seg_stats_from_cm",
+    "seg_validation", "xywh2xyxy",
+]
+
+
+class HeadOutputs:
+    """Raw outputs of the three ``Detect.m[i]`` convs (core/models/yolo.py:258) + the head's
+    ``anchor_grid`` / ``stride`` buffers.  ``.z`` / ``.x`` materialise what ``Detect.forward`` returns
+    (yolo.py:277) on demand; ``non_max_suppression`` accepts the object directly (fused path)."""
+
+    def __init__(self, levels: Sequence[torch.Tensor], anchor_grid, stride):
+        self.head = ops.Head(levels, anchor_grid, stride)
+        self._z = None
+        self._x = None
+
+    @property
+    def shape(self):
+        return (self.head.bs, self.head.A, self.head.no)
+
+    @property
+    def device(self):
+        return self.head.device
+
+    @property
+    def z(self) -> torch.Tensor:
+        if self._z is None:
+            self._z, _ = ops.detect_decode(self.head, want_z=True, want_x=False)
+        return self._z
+
+    @property
+    def x(self) -> List[torch.Tensor]:
+        if self._x is None:
+            _, self._x = ops.detect_decode(self.head, want_z=False, want_x=True)
+        return self._x
+
+
+class SegLogits:
+    """Low-res seg logits (bs, C, h, w) — the input of the head's final
+    ``nn.Upsample(scale_factor=8, mode='bilinear', align_corners=True)`` (core/models/yolo.py:183) —
+    plus the size that Upsample would produce.  ``.full()`` materialises the reference tensor."""
+
+    def __init__(self, low: torch.Tensor, scale_factor: int = 8, size: Optional[Tuple[int, int]] = None):
+        self.low = low
+        self.size = (int(low.shape[2]) * scale_factor, int(low.shape[3]) * scale_factor) if size is None else tuple(size)
+
+    @property
+    def shape(self):
+        return (int(self.low.shape[0]), int(self.low.shape[1])) + tuple(self.size)
+
+    @property
+    def device(self):
+        return self.low.device
+
+    def full(self) -> torch.Tensor:
+        return ops.upsample_bilinear_ac(self.low, self.size)
+
+
+# ------------------------------------------------------------------------------------------------
+# a1  Detect.forward, eval branch after the convs                      core/models/yolo.py:259-277
+# ------------------------------------------------------------------------------------------------
+def detect_forward(x: Sequence[torch.Tensor], anchor_grid, stride) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+    """``x[i]`` = output of ``Detect.m[i]`` (bs, na*no, ny, nx).  Returns ``(cat(z,1), x)`` exactly
+    as yolo.py:277: z (bs, A, no) decoded, x[i] (bs, na, ny, nx, no) permuted raw logits."""
+    head = ops.Head(x, anchor_grid, stride)
+    z, xs = ops.detect_decode(head, want_z=True, want_x=True)
+    return z, xs
+
+
+def xywh2xyxy(x: torch.Tensor) -> torch.Tensor:
+    """core/utils/general.py:523-530 (tiny host-side helper, kept for API completeness)."""
+    y = x.clone()
+    y[:, 0] = x[:, 0] - x[:, 2] / 2
+    y[:, 1] = x[:, 1] - x[:, 3] / 2
+    y[:, 2] = x[:, 0] + x[:, 2] / 2
+    y[:, 3] = x[:, 1] + x[:, 3] / 2
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
+# a2  non_max_suppression                                          core/utils/general.py:659-750
+# ------------------------------------------------------------------------------------------------
+def _append_label_rows(z: torch.Tensor, labels) -> torch.Tensor:
+    """general.py:690-696: a-priori label rows [cls, x, y, w, h] become extra prediction rows with
+    obj = 1 and a one-hot class; appended after the A anchor rows so candidate order is unchanged."""
+    bs, A, no = z.shape
+    L = max(len(l) for l in labels)
+    if L == 0:
+        return z
+    extra = torch.zeros((bs, L, no), dtype=z.dtype, device=z.device)
+    for i, l in enumerate(labels):
+        if len(l):
+            l = torch.as_tensor(l, dtype=z.dtype, device=z.device)
+            n = l.shape[0]
+            extra[i, :n, :4] = l[:, 1:5]
+            extra[i, :n, 4] = 1.0
+            extra[i, torch.arange(n, device=z.device), l[:, 0].long() + 5] = 1.0
+    return torch.cat((z, extra), 1)
+
+
+def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False,
+                        multi_label=False, labels=(), max_det=300) -> List[torch.Tensor]:
+    """Same signature and result as the reference (general.py:659-750): list of (n_i, 6) tensors
+    [x1, y1, x2, y2, conf, cls] per image, sorted by confidence, on ``prediction.device``.
+    ``prediction`` is the decoded (bs, A, no) tensor, or a ``HeadOutputs`` (fused path).
+    Differences, both documented in DESIGN.md: no 10 s wall-clock ``break`` (general.py:746-748), and
+    among equal confidences beyond 30 000 candidates the order is canonical (stable) where the
+    reference's non-stable argsort (general.py:729) leaves it implementation-defined."""
+    assert 0 <= conf_thres <= 1, f'Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0'
+    assert 0 <= iou_thres <= 1, f'Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0'
+    has_labels = bool(labels) and any(len(l) for l in labels)
+    if isinstance(prediction, HeadOutputs) and not has_labels:
+        head = prediction.head
+        keys, counts = ops.filter_levels(head, conf_thres, multi_label, classes)
+        det, det_count = ops.nms_levels(head, keys, counts, conf_thres, iou_thres, agnostic, int(max_det))
+    else:
+        z = prediction.z if isinstance(prediction, HeadOutputs) else prediction
+        if has_labels:
+            z = _append_label_rows(z, labels)
+        if z.shape[0] == 0:
+            return []
+        keys, counts = ops.filter_z(z, conf_thres, multi_label, classes)
+        det, det_count = ops.nms_z(z, keys, counts, conf_thres, iou_thres, agnostic, int(max_det))
+    n = det_count.cpu().tolist()                       # the single host sync of the call
+    if any(v < 0 for v in n):
+        raise RuntimeError("desenet_b200: candidate buffer overflow (internal capacity error)")
+    return [det[i, :n[i]] for i in range(len(n))]      # views of a per-call buffer: caller-owned
+
+
+# ------------------------------------------------------------------------------------------------
+# a6  segoutput_to_target                                              core/utils/plots.py:222-229
+# ------------------------------------------------------------------------------------------------
+def segoutput_to_target(output, size=None) -> torch.Tensor:
+    """argmax over classes -> float -> nearest resize to ``size`` -> (bs, size[0], size[1]) float32.
+    ``output``: full-res logits (bs, C, H, W) as in the reference, or ``SegLogits`` (fused path)."""
+    if isinstance(output, SegLogits):
+        full = output.size
+        msize = full if size is None else tuple(int(v) for v in size)[-2:]
+        mask, _ = ops.seg_fused(output.low, full, mask_dtype=torch.float32, mask_size=msize)
+        return mask
+    H, W = int(output.shape[2]), int(output.shape[3])
+    msize = (H, W) if size is None else tuple(int(v) for v in size)[-2:]
+    mask, _ = ops.seg_fullres(output, mask_dtype=torch.float32, mask_size=msize)
+    return mask
+
+
+# ------------------------------------------------------------------------------------------------
+# a7 / a8  seg metrics                                               core/utils/metrics.py:350-388
+# ------------------------------------------------------------------------------------------------
+def seg_confusion_matrix(output, target: torch.Tensor, nclass: int, cm: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Target-clamped confusion matrix CM[r][p] (device int64, shape (slots, rows, C); sum over
+    slots) of argmax(output) against ``target`` — the sufficient statistic of metrics.py:350-388."""
+    C = int(output.shape[1])
+    rows = ops.cm_rows_for(C, nclass)
+    if isinstance(output, SegLogits):
+        _, cm = ops.seg_fused(output.low, output.size, target=target, cm=cm, cm_rows=rows)
+    else:
+        _, cm = ops.seg_fullres(output, target=target, cm=cm, cm_rows=rows)
+    return cm
+
+
+def seg_stats_from_cm(cm: np.ndarray, nclass: int):
+    """(pixel_correct, pixel_labeled, area_inter[nclass-1], area_union[nclass-1]) from CM[r][p].
+
+    Closed form of metrics.py:350-388: labeled = target > 0 (metrics.py:361); correct = predict ==
+    target among labeled (:362); the three np.histogram(bins=nclass-1, range=(1, nclass)) calls
+    (:383-385) put value k in bin min(k, nclass-1)-1 for 1 <= k <= nclass (last bin right-closed) and
+    drop everything else; predictions are < C, exact target rows are 0..rows-2, the last row holds
+    every larger target (labeled, never a class, never equal to a prediction)."""
+    cm = np.asarray(cm, dtype=np.int64)
+    if cm.ndim == 3:
+        cm = cm.sum(0)
+    rows, C = cm.shape
+    exact = rows - 1                      # rows 0..exact-1 are exact target values
+    labeled = np.int64(cm[1:].sum())
+    correct = np.int64(sum(cm[k, k] for k in range(1, min(exact, C))))
+    nb = nclass - 1
+    inter = np.zeros(nb, np.int64)
+    pred = np.zeros(nb, np.int64)
+    lab = np.zeros(nb, np.int64)
+    for k in range(1, nclass + 1):
+        b = min(k, nclass - 1) - 1
+        if k < C:
+            pred[b] += cm[:, k].sum()
+            if k < exact:
+                inter[b] += cm[k, k]
+        if k < exact:
+            lab[b] += cm[k].sum()
+    return correct, labeled, inter, pred + lab - inter
+
+
+def batch_pix_accuracy(output, target):
+    """metrics.py:350-365: returns (pixel_correct, pixel_labeled) as numpy int64 scalars."""
+    C = int(output.shape[1])
+    cm = seg_confusion_matrix(output, target, max(C - 1, 2)).sum(0).cpu().numpy()
+    correct, labeled, _, _ = seg_stats_from_cm(cm, max(C - 1, 2))
+    assert correct <= labeled, "Correct area should be smaller than Labeled"
+    return correct, labeled
+
+
+def batch_intersection_union(output, target, nclass):
+    """metrics.py:368-388: returns (area_inter, area_union), int64 arrays of length nclass-1."""
+    cm = seg_confusion_matrix(output, target, nclass).sum(0).cpu().numpy()
+    _, _, inter, union = seg_stats_from_cm(cm, nclass)
+    assert (inter <= union).all(), "Intersection area should be smaller than Union area"
+    return inter, union
+
+
+# ------------------------------------------------------------------------------------------------
+# a9  seg_validation                                                      scripts/val.py:42-76
+# ------------------------------------------------------------------------------------------------
+def seg_validation(model, n_segcls, valloader, half_precision=True, device=None, progress=None):
+    """Same contract as scripts/val.py:42-76: loops the loader, accumulates pixel / IoU statistics,
+    returns mIoU.  The statistics are accumulated ON DEVICE in one int64 confusion matrix (one
+    D2H at the end instead of four full-resolution maps per batch); pixAcc / IoU / mIoU are then
+    formed exactly as val.py:71-73 (float64, ``np.spacing(1)`` eps).  ``model(image)[1]`` may return
+    full-res logits (reference model) or ``SegLogits`` (patched head).  fp16 logits
+    (``half_precision``) are upcast to fp32 on load."""
+    import torch.nn.functional as F
+
+    first = next(iter(model.parameters()), None) if hasattr(model, "parameters") else None
+    if device is None:
+        device = first.device if first is not None else torch.device("cuda")
+    half = half_precision and device.type != "cpu" and first is not None
+    if half:
+        model.half()                                                              # val.py:54-56
+    if hasattr(model, "eval"):
+        model.eval()
+    cm = None
+    rows = None
+    it = valloader if progress is None else progress(valloader)
+    with torch.no_grad():
+        for image, _, target, *_ in it:                                            # val.py:61
+            image = image.to(device, non_blocking=True)
+            image = image.half() if half else image.float()
+            image = image / 255.0                                                  # val.py:64
+            target = target.to(device, non_blocking=True)
+            pred = model(image)[1]                                                 # val.py:45
+            if isinstance(pred, SegLogits):
+                if tuple(pred.size) != tuple(target.shape[1:]):
+                    pred = pred.full()
+                elif pred.low.dtype != torch.float32:
+                    pred = SegLogits(pred.low.float(), size=pred.size)
+            if not isinstance(pred, SegLogits):
+                pred = pred.float()
+                if tuple(pred.shape[2:]) != tuple(target.shape[1:]):               # val.py:47
+                    pred = F.interpolate(pred, tuple(target.shape[1:]), mode="bilinear", align_corners=False)
+            C = int(pred.shape[1])
+            if cm is None:
+                rows = ops.cm_rows_for(C, n_segcls)
+                cm = torch.zeros((64, rows, C), dtype=torch.int64, device=target.device)
+            seg_confusion_matrix(pred, target.long(), n_segcls, cm=cm)             # val.py:48-49
+    if cm is None:
+        return 0.0
+    correct, labeled, inter, union = seg_stats_from_cm(cm.sum(0).cpu().numpy(), n_segcls)
+    pix_acc = 1.0 * correct / (np.spacing(1) + labeled)                            # val.py:71
+    iou = 1.0 * inter / (np.spacing(1) + union)                                    # val.py:72
+    miou = iou.mean()                                                              # val.py:73
+    seg_validation.last = dict(pixAcc=float(pix_acc), mIoU=float(miou), cm=cm.sum(0))
+    return float(miou)

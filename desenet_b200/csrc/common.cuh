@@ -1,0 +1,77 @@
+// Shared device helpers for the DeSeNet post-process kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/desenet_b200.h"
+
+#define DSN_CHECK_LAUNCH()                         \
+    do {                                           \
+        cudaError_t e__ = cudaGetLastError();      \
+        if (e__ != cudaSuccess) return (int)e__;   \
+    } while (0)
+
+#define DSN_CUDA(expr)                             \
+    do {                                           \
+        cudaError_t e__ = (expr);                  \
+        if (e__ != cudaSuccess) return (int)e__;   \
+    } while (0)
+
+namespace dsn {
+
+// Streaming 128-bit loads that do not pollute L1 (inputs are read exactly once).
+__device__ __forceinline__ float4 ldg_stream_f4(const float *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ldg_stream_f1(const float *p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ longlong2 ldg_stream_ll2(const long long *p) {
+    longlong2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.s64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+    return r;
+}
+// Streaming stores (outputs are never re-read by the producing kernel).
+__device__ __forceinline__ void stg_stream_f4(float *p, float4 v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+// sigmoid as the reference computes it (torch.sigmoid, core/models/yolo.py:266): 1/(1+exp(-x)).
+// expf / IEEE division (no fast-math): within a few ulp of ATen's CPU kernel; the north-star
+// tolerance for decoded boxes and scores is 1e-5 relative.
+__device__ __forceinline__ float sigmoidf_ref(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+// monotone key of a confidence: larger conf -> smaller key.  conf > 0 always (it passed
+// `conf > conf_thres >= 0`), so the raw IEEE bits are already ordered.
+__device__ __forceinline__ uint32_t conf_key(float conf) { return ~__float_as_uint(conf); }
+__device__ __forceinline__ float key_conf(uint64_t key) { return __uint_as_float(~(uint32_t)(key >> 32)); }
+
+// ATen align_corners=True source index + lambdas, in fp32 (see oracle/c/oracle.c: coeffs()).
+struct Lerp {
+    int i0;
+    float l0, l1;
+};
+__device__ __forceinline__ Lerp lerp_coeff(float scale, int dst, int n_in) {
+    float src = __fmul_rn(scale, (float)dst);
+    int a = (int)src;
+    a = a > n_in - 1 ? n_in - 1 : a;
+    Lerp r;
+    r.i0 = a;
+    r.l1 = __fsub_rn(src, (float)a);
+    r.l0 = __fsub_rn(1.0f, r.l1);
+    return r;
+}
+
+// argmax update, torch semantics: first maximum wins, NaN counts as maximal (first NaN wins).
+__device__ __forceinline__ bool argmax_better(float cur, float best) {
+    return !(cur <= best) && (best == best);
+}
+
+}  // namespace dsn

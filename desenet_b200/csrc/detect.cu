@@ -1,0 +1,316 @@
+// Detection head tail: Detect.forward's post-conv decode (core/models/yolo.py:259-277) and the
+// candidate filter of non_max_suppression (core/utils/general.py:668-718), as
+//   * dsn_detect_decode  — strict drop-in: materialises z (bs,A,no) and the permuted raw logits
+//   * dsn_filter_levels  — fused: raw NCHW head outputs -> 64-bit candidate keys, nothing else
+//   * dsn_filter_z       — the same filter on an already decoded prediction
+// All three are HBM-bound streaming kernels: plane-major 16 B loads (threadIdx.x runs along the
+// cell index, the contiguous dimension of every channel plane), no shared-memory reuse needed
+// except the decode transposition.
+#include <algorithm>
+
+#include "common.cuh"
+#include "geom.cuh"
+
+namespace dsn {
+
+// =============================================================================================
+// Strict decode: z + xperm                                                 yolo.py:259-277
+// One CTA = one (image, level, anchor) x a run of `cells` cells; the no x cells input tile is read
+// plane-major (coalesced along cells), decoded, transposed through shared memory and written as
+// ONE contiguous run of cells*no floats of z (rows of one anchor plane are adjacent in z) and of
+// xperm.
+// =============================================================================================
+__global__ void __launch_bounds__(256) detect_decode_kernel(const HeadGeom g, float *__restrict__ z, XpermPtrs xp, int cells) {
+    extern __shared__ float sm[];
+    const int no = g.no;
+    float *sz = sm;                       // [cells][no] decoded
+    float *sx = sm + (size_t)cells * no;  // [cells][no] raw
+    // blockIdx.x enumerates (level, anchor, tile) for one image
+    int t = blockIdx.x, l = 0;
+    while (l + 1 < g.nl && t >= g.tile_off[l + 1]) ++l;
+    t -= g.tile_off[l];
+    const int plane = g.plane[l];
+    const int tiles_per_plane = (plane + cells - 1) / cells;
+    const int a = t / tiles_per_plane;
+    const int c0 = (t % tiles_per_plane) * cells;
+    const int n = min(cells, plane - c0);
+    const int b = blockIdx.y;
+    const float *src = g.raw[l] + ((size_t)(b * g.na + a) * no) * plane + c0;
+    const float stride = g.stride[l], aw = g.anchor_w[l][a], ah = g.anchor_h[l][a];
+    const int nx = g.nx[l];
+    for (int i = threadIdx.x; i < no * n; i += blockDim.x) {
+        const int o = i / n, c = i - o * n;
+        const float v = ldg_stream_f1(src + (size_t)o * plane + c);
+        float r;
+        const int cell = c0 + c;
+        if (o == 0) r = decode_xy(v, cell % nx, stride);                     // yolo.py:268
+        else if (o == 1) r = decode_xy(v, cell / nx, stride);
+        else if (o < 4) r = decode_wh(v, o == 2 ? aw : ah);                  // yolo.py:269
+        else r = sigmoidf_ref(v);                                            // yolo.py:266
+        sz[c * no + o] = r;
+        sx[c * no + o] = v;
+    }
+    __syncthreads();
+    const size_t row0 = (size_t)g.row_off[l] + (size_t)a * plane + c0;
+    if (z) {
+        float *dst = z + ((size_t)b * g.A + row0) * no;                        // yolo.py:275,277
+        for (int i = threadIdx.x; i < no * n; i += blockDim.x) dst[i] = sz[i];
+    }
+    if (xp.p[l]) {
+        float *dst = xp.p[l] + (((size_t)(b * g.na + a)) * plane + c0) * no;   // yolo.py:260
+        for (int i = threadIdx.x; i < no * n; i += blockDim.x) dst[i] = sx[i];
+    }
+}
+
+// =============================================================================================
+// Candidate filter
+// =============================================================================================
+struct FilterOut {
+    unsigned long long *keys;
+    long long cap;
+    int *counts;
+    float conf_thres;
+    int multi_label;
+    unsigned long long cmask[4];
+    int use_cmask;
+};
+
+__device__ __forceinline__ bool class_allowed(const FilterOut &f, int cls) {
+    return !f.use_cmask || ((f.cmask[(cls >> 6) & 3] >> (cls & 63)) & 1ull);
+}
+
+// Warp-aggregated slot allocation: every lane passes its emission count; returns the lane's first
+// slot inside keys[b][*].  One global atomic per warp (ballot-style compaction of survivors).
+__device__ __forceinline__ int warp_alloc(int *counter, int n_mine) {
+    const int lane = threadIdx.x & 31;
+    int incl = n_mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += up;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(counter, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    return base + incl - n_mine;
+}
+
+constexpr int kClsChunk = 8;
+
+// V consecutive rows per lane.  `Cls` loads the V class confidences of class c (already a
+// probability): cls(c, out[V]).  obj[k] is the objectness probability of row (row0+k); lanes with
+// no passing row (or !valid) skip every class load.  Must be called by all 32 lanes.
+template <int V, class Cls>
+__device__ __forceinline__ void filter_emit(const FilterOut &f, int b, unsigned int row0, int nc, const float (&obj)[V],
+                                            bool valid, Cls cls) {
+    unsigned int pass = 0;
+    if (valid) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) pass |= (obj[k] > f.conf_thres) ? (1u << k) : 0u;      // general.py:668,687
+    }
+    if (!__any_sync(0xffffffffu, pass != 0)) return;
+    unsigned long long *kout = f.keys + (size_t)b * f.cap;
+    int *counter = f.counts + b;
+    if (!f.multi_label) {
+        // best class, first maximum wins                                   general.py:713-714
+        float best[V];
+        int bcls[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) { best[k] = 0.f; bcls[k] = 0; }
+        if (pass) {
+            for (int c = 0; c < nc; ++c) {
+                float cv[V];
+                cls(c, cv);
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    const float conf = __fmul_rn(cv[k], obj[k]);                            // general.py:703
+                    if (c == 0 || argmax_better(conf, best[k])) { best[k] = conf; bcls[k] = c; }
+                }
+            }
+        }
+        unsigned int emit = 0;
+#pragma unroll
+        for (int k = 0; k < V; ++k)
+            if (((pass >> k) & 1u) && best[k] > f.conf_thres && class_allowed(f, bcls[k])) emit |= 1u << k;   // :714,:717
+        int slot = warp_alloc(counter, __popc(emit));
+#pragma unroll
+        for (int k = 0; k < V; ++k)
+            if ((emit >> k) & 1u) {
+                if (slot < f.cap)
+                    kout[slot] = ((unsigned long long)conf_key(best[k]) << 32) | (unsigned long long)((row0 + k) * (unsigned)nc + bcls[k]);
+                ++slot;
+            }
+    } else {
+        // every (row, class) with conf > thres                               general.py:710-711
+        for (int c0 = 0; c0 < nc; c0 += kClsChunk) {
+            float cf[kClsChunk][V];
+            unsigned int emit = 0;   // bit (ci*V + k)
+            if (pass) {
+#pragma unroll
+                for (int ci = 0; ci < kClsChunk; ++ci) {
+                    const int c = c0 + ci;
+                    if (c < nc) {
+                        float cv[V];
+                        cls(c, cv);
+                        const bool ok = class_allowed(f, c);
+#pragma unroll
+                        for (int k = 0; k < V; ++k) {
+                            cf[ci][k] = __fmul_rn(cv[k], obj[k]);
+                            if (ok && ((pass >> k) & 1u) && cf[ci][k] > f.conf_thres) emit |= 1u << (ci * V + k);
+                        }
+                    }
+                }
+            }
+            if (!__any_sync(0xffffffffu, emit != 0)) continue;
+            int slot = warp_alloc(counter, __popc(emit));
+#pragma unroll
+            for (int ci = 0; ci < kClsChunk; ++ci)
+#pragma unroll
+                for (int k = 0; k < V; ++k)
+                    if ((emit >> (ci * V + k)) & 1u) {
+                        if (slot < f.cap)
+                            kout[slot] = ((unsigned long long)conf_key(cf[ci][k]) << 32) |
+                                         (unsigned long long)((row0 + k) * (unsigned)nc + (c0 + ci));
+                        ++slot;
+                    }
+        }
+    }
+}
+
+// ---- from the raw levels: thread = V consecutive cells of one (image, level, anchor) plane --------
+template <int V>
+__global__ void __launch_bounds__(256) filter_levels_kernel(const HeadGeom g, const FilterOut f) {
+    const int b = blockIdx.y;
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;          // unit index inside the image
+    const bool valid = u < g.unit_off[g.nl];
+    int l = 0;
+    if (valid)
+        while (l + 1 < g.nl && u >= g.unit_off[l + 1]) ++l;
+    const int plane = g.plane[l];
+    const int upp = plane / V;                                    // units per plane
+    const int ul = valid ? u - g.unit_off[l] : 0;
+    const int a = ul / upp;
+    const int cell = (ul - a * upp) * V;
+    const float *base = g.raw[l] + ((size_t)(b * g.na + a) * g.no) * plane + cell;
+    float obj[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) obj[k] = 0.f;
+    if (valid) {
+        if constexpr (V == 4) {
+            const float4 t = ldg_stream_f4(base + (size_t)4 * plane);
+            obj[0] = sigmoidf_ref(t.x); obj[1] = sigmoidf_ref(t.y); obj[2] = sigmoidf_ref(t.z); obj[3] = sigmoidf_ref(t.w);
+        } else {
+            obj[0] = sigmoidf_ref(ldg_stream_f1(base + (size_t)4 * plane));
+        }
+    }
+    const unsigned int row0 = (unsigned)(g.row_off[l] + a * plane + cell);
+    auto cls = [&](int c, float (&out)[V]) {
+        const float *pc = base + (size_t)(5 + c) * plane;
+        if constexpr (V == 4) {
+            const float4 t = ldg_stream_f4(pc);
+            out[0] = sigmoidf_ref(t.x); out[1] = sigmoidf_ref(t.y); out[2] = sigmoidf_ref(t.z); out[3] = sigmoidf_ref(t.w);
+        } else {
+            out[0] = sigmoidf_ref(ldg_stream_f1(pc));
+        }
+    };
+    filter_emit<V>(f, b, row0, g.no - 5, obj, valid, cls);
+}
+
+// ---- from a decoded prediction (bs, A, no): lane = one row ---------------------------------------
+__global__ void __launch_bounds__(256) filter_z_kernel(const float *__restrict__ z, long long A, int no, const FilterOut f) {
+    const int b = blockIdx.y;
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = row < A;
+    const float *r = z + ((size_t)b * A + (valid ? row : 0)) * no;
+    float obj[1] = {valid ? __ldg(r + 4) : 0.f};
+    auto cls = [&](int c, float (&out)[1]) { out[0] = __ldg(r + 5 + c); };
+    filter_emit<1>(f, b, (unsigned)row, no - 5, obj, valid, cls);
+}
+
+static int make_filter_out(FilterOut &f, float conf_thres, int multi_label, int nc, const uint64_t *class_mask,
+                           uint64_t *keys, int64_t cap, int *counts) {
+    if (!keys || !counts || cap < 1) return DSN_E_INVALID;
+    if (!(conf_thres >= 0.f && conf_thres <= 1.f)) return DSN_E_INVALID;     // general.py:671
+    if (class_mask && nc > 256) return DSN_E_UNSUPPORTED;
+    f.keys = (unsigned long long *)keys;
+    f.cap = cap;
+    f.counts = counts;
+    f.conf_thres = conf_thres;
+    f.multi_label = (multi_label && nc > 1) ? 1 : 0;                          // general.py:679
+    f.use_cmask = class_mask != nullptr;
+    for (int i = 0; i < 4; ++i) f.cmask[i] = class_mask ? class_mask[i] : ~0ull;
+    return DSN_OK;
+}
+
+}  // namespace dsn
+
+using namespace dsn;
+
+extern "C" __attribute__((visibility("default"))) int dsn_detect_decode(const float *const *raw, const int *ny, const int *nx, const float *stride,
+                                 const float *anchor_grid, int nl, int bs, int na, int no, float *z,
+                                 float *const *xperm, void *stream) {
+    HeadGeom g;
+    int rc = make_geom(g, raw, ny, nx, stride, anchor_grid, nl, bs, na, no);
+    if (rc) return rc;
+    if (bs == 0 || (!z && !xperm)) return DSN_OK;
+    const int cells = no <= 32 ? 128 : 32;
+    XpermPtrs xp{};
+    for (int l = 0; l < nl; ++l) xp.p[l] = xperm ? xperm[l] : nullptr;
+    int tiles = 0;
+    for (int l = 0; l < nl; ++l) {
+        g.tile_off[l] = tiles;
+        tiles += na * ((g.plane[l] + cells - 1) / cells);
+    }
+    g.tile_off[nl] = tiles;
+    const size_t smem = (size_t)2 * cells * no * sizeof(float);
+    if (smem > 200 * 1024) return DSN_E_UNSUPPORTED;
+    if (smem > 48 * 1024) DSN_CUDA(cudaFuncSetAttribute(detect_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    detect_decode_kernel<<<dim3(tiles, bs), 256, smem, (cudaStream_t)stream>>>(g, z, xp, cells);
+    DSN_CHECK_LAUNCH();
+    return DSN_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int dsn_filter_levels(const float *const *raw, const int *ny, const int *nx, int nl, int bs, int na, int no,
+                                 float conf_thres, int multi_label, const uint64_t *class_mask, uint64_t *keys,
+                                 int64_t cap, int *counts, void *stream) {
+    HeadGeom g;
+    int rc = make_geom(g, raw, ny, nx, nullptr, nullptr, nl, bs, na, no);
+    if (rc) return rc;
+    FilterOut f;
+    rc = make_filter_out(f, conf_thres, multi_label, no - 5, class_mask, keys, cap, counts);
+    if (rc) return rc;
+    if (bs == 0) return DSN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DSN_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)bs, st));
+    bool vec = true;
+    for (int l = 0; l < nl; ++l) vec = vec && (g.plane[l] % 4 == 0) && (((uintptr_t)raw[l] & 15) == 0);
+    const int V = vec ? 4 : 1;
+    int units = 0;
+    for (int l = 0; l < nl; ++l) {
+        g.unit_off[l] = units;
+        units += na * (g.plane[l] / V);
+    }
+    g.unit_off[nl] = units;
+    dim3 grid((units + 255) / 256, bs);
+    if (vec) filter_levels_kernel<4><<<grid, 256, 0, st>>>(g, f);
+    else filter_levels_kernel<1><<<grid, 256, 0, st>>>(g, f);
+    DSN_CHECK_LAUNCH();
+    return DSN_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int dsn_filter_z(const float *z, int bs, int64_t A, int no, float conf_thres, int multi_label,
+                            const uint64_t *class_mask, uint64_t *keys, int64_t cap, int *counts, void *stream) {
+    if (!z || bs < 0 || A < 1 || no < 6) return DSN_E_INVALID;
+    if (bs > 65535 || (unsigned long long)A * (unsigned long long)(no - 5) >= (1ull << 32)) return DSN_E_UNSUPPORTED;
+    FilterOut f;
+    int rc = make_filter_out(f, conf_thres, multi_label, no - 5, class_mask, keys, cap, counts);
+    if (rc) return rc;
+    if (bs == 0) return DSN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DSN_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)bs, st));
+    dim3 grid((unsigned)((A + 255) / 256), bs);
+    filter_z_kernel<<<grid, 256, 0, st>>>(z, A, no, f);
+    DSN_CHECK_LAUNCH();
+    return DSN_OK;
+}

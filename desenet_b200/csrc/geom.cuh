@@ -1,0 +1,69 @@
+// Detection-head geometry passed by value to the kernels (fits the 4 KB kernel-parameter space).
+#pragma once
+#include "common.cuh"
+
+namespace dsn {
+
+struct HeadGeom {
+    const float *raw[DSN_MAX_LEVELS];   // (bs, na*no, ny, nx) per level
+    int ny[DSN_MAX_LEVELS], nx[DSN_MAX_LEVELS], plane[DSN_MAX_LEVELS];
+    int row_off[DSN_MAX_LEVELS + 1];    // first row of the level inside z (per image); [nl] = A
+    int unit_off[DSN_MAX_LEVELS + 1];   // filter kernel: first work unit of the level
+    int tile_off[DSN_MAX_LEVELS + 1];   // decode kernel: first tile of the level
+    float stride[DSN_MAX_LEVELS];
+    float anchor_w[DSN_MAX_LEVELS][DSN_MAX_ANCHORS], anchor_h[DSN_MAX_LEVELS][DSN_MAX_ANCHORS];
+    int nl, na, no, bs, A;
+};
+
+struct XpermPtrs {
+    float *p[DSN_MAX_LEVELS];
+};
+
+// stride / anchor_grid may be NULL for kernels that never decode boxes (the key-only filter).
+static inline int make_geom(HeadGeom &g, const float *const *raw, const int *ny, const int *nx, const float *stride,
+                            const float *anchor_grid, int nl, int bs, int na, int no) {
+    if (!raw || !ny || !nx || nl < 1 || bs < 0 || na < 1 || no < 6) return DSN_E_INVALID;
+    if (nl > DSN_MAX_LEVELS || na > DSN_MAX_ANCHORS || bs > 65535) return DSN_E_UNSUPPORTED;
+    g = HeadGeom{};
+    g.nl = nl; g.na = na; g.no = no; g.bs = bs;
+    long long rows = 0;
+    for (int l = 0; l < nl; ++l) {
+        if (!raw[l] || ny[l] < 1 || nx[l] < 1) return DSN_E_INVALID;
+        if (((uintptr_t)raw[l] & 3) != 0) return DSN_E_ALIGN;
+        g.raw[l] = raw[l];
+        g.ny[l] = ny[l]; g.nx[l] = nx[l];
+        const long long plane = (long long)ny[l] * nx[l];
+        if (plane > (1 << 28)) return DSN_E_UNSUPPORTED;
+        g.plane[l] = (int)plane;
+        g.row_off[l] = (int)rows;
+        rows += (long long)na * plane;
+        g.stride[l] = stride ? stride[l] : 0.f;
+        for (int a = 0; a < na; ++a) {
+            g.anchor_w[l][a] = anchor_grid ? anchor_grid[((size_t)l * na + a) * 2 + 0] : 0.f;
+            g.anchor_h[l][a] = anchor_grid ? anchor_grid[((size_t)l * na + a) * 2 + 1] : 0.f;
+        }
+    }
+    // candidate keys carry row*nc + cls in 32 bits
+    if ((unsigned long long)rows * (unsigned long long)(no - 5) >= (1ull << 32)) return DSN_E_UNSUPPORTED;
+    g.row_off[nl] = (int)rows;
+    g.A = (int)rows;
+    return DSN_OK;
+}
+
+// Box decode of one anchor row from the raw level planes (core/models/yolo.py:266-269), every op
+// rounded separately so dsn_detect_decode and the NMS box fetch agree bit-for-bit.
+__device__ __forceinline__ float decode_xy(float logit, int g, float stride) {
+    const float two = __fmul_rn(sigmoidf_ref(logit), 2.0f);
+    return __fmul_rn(__fadd_rn(__fsub_rn(two, 0.5f), (float)g), stride);
+}
+__device__ __forceinline__ float decode_wh(float logit, float anchor) {
+    const float two = __fmul_rn(sigmoidf_ref(logit), 2.0f);
+    return __fmul_rn(__fmul_rn(two, two), anchor);
+}
+// xywh2xyxy (core/utils/general.py:523-530)
+__device__ __forceinline__ float4 xywh2xyxy(float x, float y, float w, float h) {
+    const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
+    return make_float4(__fsub_rn(x, hw), __fsub_rn(y, hh), __fadd_rn(x, hw), __fadd_rn(y, hh));
+}
+
+}  // namespace dsn

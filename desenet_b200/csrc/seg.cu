@@ -1,0 +1,456 @@
+// Segmentation tail: x8 bilinear upsample (align_corners=True) + per-pixel argmax + mask write +
+// confusion-matrix accumulation, fused (core/models/yolo.py:183, core/utils/plots.py:222-229,
+// core/utils/metrics.py:350-388 of the reference).  HBM-bound streaming kernels: the low-res
+// logits (bs*C*h*w*4 B) stay in L1/L2, the int64 target is read once with 16 B no-allocate
+// loads, the fp32 mask is written once with 16 B streaming stores.  The upsampled logits are
+// never materialised, yet every upsampled value is rounded exactly as ATen's CPU kernel rounds
+// it (horizontal lerps first, each lerp = fma(l0, a, l1*b)), so argmax ties break identically.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace dsn {
+
+struct SegParams {
+    const float *logits;
+    int bs, C, h, w, H, W;
+    const long long *target;
+    float *mask_f32;
+    uint8_t *mask_u8;
+    int mask_h, mask_w;
+    unsigned long long *cm;
+    int cm_slots, cm_rows;
+    float sy, sx;      // (h-1)/(H-1), (w-1)/(W-1) in fp32 (0 when the output extent is 1)
+    float my, mx;      // nearest scales float(H)/float(mask_h), float(W)/float(mask_w)
+};
+
+constexpr int kTileRows = 8;        // output rows per CTA in the fast path
+constexpr int kMaxPackedC = 4;      // template instantiations of the fast path
+
+// ---- packed confusion-matrix counters ------------------------------------------------------
+// Per thread: one uint64 per predicted class, eight 8-bit fields = target rows 0..7.  A thread
+// adds at most 32..64 pixels between flushes, far below 255.  Flush: widen to 16-bit fields,
+// REDUX-add across the warp (32 lanes * 64 px < 65536), one shared-memory atomic per
+// (row, class) per warp, one global atomic per (row, class) per CTA.
+template <int C>
+__device__ __forceinline__ void cm_flush_warp(unsigned long long (&acc)[C], unsigned int *cm_smem, int rows) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const unsigned long long even = acc[c] & 0x00FF00FF00FF00FFull;         // rows 0,2,4,6
+        const unsigned long long odd = (acc[c] >> 8) & 0x00FF00FF00FF00FFull;   // rows 1,3,5,7
+        unsigned int wsum[4];
+        wsum[0] = __reduce_add_sync(0xffffffffu, (unsigned int)even);           // rows 0,2
+        wsum[1] = __reduce_add_sync(0xffffffffu, (unsigned int)(even >> 32));   // rows 4,6
+        wsum[2] = __reduce_add_sync(0xffffffffu, (unsigned int)odd);            // rows 1,3
+        wsum[3] = __reduce_add_sync(0xffffffffu, (unsigned int)(odd >> 32));    // rows 5,7
+        if (lane < rows) {
+            const int f = lane >> 1;   // field inside the even/odd word pair
+            unsigned int word = (lane & 1) ? ((f >> 1) ? wsum[3] : wsum[2]) : ((f >> 1) ? wsum[1] : wsum[0]);
+            unsigned int cnt = (word >> (16 * (f & 1))) & 0xFFFFu;
+            if (cnt) atomicAdd(&cm_smem[lane * C + c], cnt);
+        }
+        acc[c] = 0ull;
+    }
+}
+
+__device__ __forceinline__ int clamp_target_row(long long t, int rows) {
+    // metrics.py:359,380 wrap the int64 target to int32 (`astype('int32')`); negatives are neither
+    // "labeled" (target > 0) nor inside any histogram range -> same statistics as row 0.
+    int v = (int)(unsigned int)(unsigned long long)t;
+    v = v < 0 ? 0 : v;
+    return v > rows - 1 ? rows - 1 : v;
+}
+
+// ---- fast path: scale >= 8, W % 4 == 0, mask (if any) at full resolution, C in 2..4 -------------
+// One CTA = 8 output rows x full width of one image; one thread = a 4-pixel column group.
+// 8 output rows touch at most 2 distinct source rows y0 (8*sy < 1) and 4 pixels at most 2 distinct
+// source columns, so a thread needs a 3x3 clamped source patch per class.
+template <int C, bool HAS_TGT, bool HAS_MASK>
+__global__ void __launch_bounds__(512) seg_fused_tile_kernel(const SegParams p) {
+    __shared__ unsigned int cm_smem[DSN_MAX_CM_ROWS * kMaxPackedC];
+    const int b = blockIdx.y;
+    const int Y0 = blockIdx.x * kTileRows;
+    const int G = p.W >> 2;
+    if (HAS_TGT) {
+        if (threadIdx.x < DSN_MAX_CM_ROWS * kMaxPackedC) cm_smem[threadIdx.x] = 0u;
+        __syncthreads();
+    }
+    const float *img = p.logits + (size_t)b * C * p.h * p.w;
+    const Lerp ly_first = lerp_coeff(p.sy, Y0, p.h);
+    const int ya = ly_first.i0;
+    const int r0 = ya * p.w;
+    const int r1 = min(ya + 1, p.h - 1) * p.w;
+    const int r2 = min(ya + 2, p.h - 1) * p.w;
+    unsigned long long acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0ull;
+
+    for (int g0 = 0; g0 < G; g0 += blockDim.x) {
+        const int g = g0 + threadIdx.x;
+        if (g < G) {
+            const int X = g << 2;
+            Lerp lx[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) lx[k] = lerp_coeff(p.sx, X + k, p.w);
+            const int xa = lx[0].i0;
+            const int c0 = xa, c1 = min(xa + 1, p.w - 1), c2 = min(xa + 2, p.w - 1);
+            // horizontal lerps of the three candidate source rows            (yolo.py:183)
+            float hz[C][3][4];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float *pl = img + (size_t)c * p.h * p.w;
+                float v[3][3];
+                v[0][0] = __ldg(pl + r0 + c0); v[0][1] = __ldg(pl + r0 + c1); v[0][2] = __ldg(pl + r0 + c2);
+                v[1][0] = __ldg(pl + r1 + c0); v[1][1] = __ldg(pl + r1 + c1); v[1][2] = __ldg(pl + r1 + c2);
+                v[2][0] = __ldg(pl + r2 + c0); v[2][1] = __ldg(pl + r2 + c1); v[2][2] = __ldg(pl + r2 + c2);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool sh = lx[k].i0 != xa;   // source column advanced by one
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        const float a = sh ? v[r][1] : v[r][0];
+                        const float bb = sh ? v[r][2] : v[r][1];
+                        hz[c][r][k] = __fmaf_rn(lx[k].l0, a, __fmul_rn(lx[k].l1, bb));
+                    }
+                }
+            }
+#pragma unroll
+            for (int dy = 0; dy < kTileRows; ++dy) {
+                const int Y = Y0 + dy;
+                if (Y < p.H) {
+                    const Lerp ly = lerp_coeff(p.sy, Y, p.h);
+                    const bool sh = ly.i0 != ya;       // uniform across the CTA
+                    int pred[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float best = 0.f;
+                        int bi = 0;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            const float t = sh ? hz[c][1][k] : hz[c][0][k];
+                            const float bt = sh ? hz[c][2][k] : hz[c][1][k];
+                            const float val = __fmaf_rn(ly.l0, t, __fmul_rn(ly.l1, bt));
+                            if (c == 0) {
+                                best = val;
+                            } else if (argmax_better(val, best)) {
+                                best = val;
+                                bi = c;
+                            }
+                        }
+                        pred[k] = bi;
+                    }
+                    const size_t pix = ((size_t)b * p.H + Y) * p.W + X;
+                    if (HAS_MASK) {
+                        if (p.mask_f32)
+                            stg_stream_f4(p.mask_f32 + pix, make_float4((float)pred[0], (float)pred[1], (float)pred[2], (float)pred[3]));
+                        if (p.mask_u8)
+                            *reinterpret_cast<uint32_t *>(p.mask_u8 + pix) =
+                                (uint32_t)pred[0] | ((uint32_t)pred[1] << 8) | ((uint32_t)pred[2] << 16) | ((uint32_t)pred[3] << 24);
+                    }
+                    if (HAS_TGT) {
+                        const longlong2 ta = ldg_stream_ll2(p.target + pix);
+                        const longlong2 tb = ldg_stream_ll2(p.target + pix + 2);
+                        const long long tv[4] = {ta.x, ta.y, tb.x, tb.y};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const unsigned long long inc = 1ull << (8 * clamp_target_row(tv[k], p.cm_rows));
+#pragma unroll
+                            for (int c = 0; c < C; ++c) acc[c] += (pred[k] == c) ? inc : 0ull;
+                        }
+                    }
+                }
+            }
+        }
+        if (HAS_TGT) cm_flush_warp<C>(acc, cm_smem, p.cm_rows);   // <= 32 px per thread per pass
+    }
+    if (HAS_TGT) {
+        __syncthreads();
+        const int nb = p.cm_rows * C;
+        if (threadIdx.x < nb) {
+            const unsigned int r = threadIdx.x / C, c = threadIdx.x % C;
+            const unsigned int cnt = cm_smem[r * C + c];
+            if (cnt) atomicAdd(p.cm + ((size_t)(b % p.cm_slots) * p.cm_rows + r) * C + c, (unsigned long long)cnt);
+        }
+    }
+}
+
+// ---- general path: any C, any scale, any mask size, any cm_rows -------------------------------
+__device__ __forceinline__ int pred_bilinear(const float *img, int C, int h, int w, float sy, float sx, int Y, int X) {
+    const Lerp ly = lerp_coeff(sy, Y, h);
+    const Lerp lx = lerp_coeff(sx, X, w);
+    const int y1 = ly.i0 + (ly.i0 < h - 1), x1 = lx.i0 + (lx.i0 < w - 1);
+    float best = 0.f;
+    int bi = 0;
+    for (int c = 0; c < C; ++c) {
+        const float *pl = img + (size_t)c * h * w;
+        const float t = __fmaf_rn(lx.l0, __ldg(pl + ly.i0 * w + lx.i0), __fmul_rn(lx.l1, __ldg(pl + ly.i0 * w + x1)));
+        const float bt = __fmaf_rn(lx.l0, __ldg(pl + y1 * w + lx.i0), __fmul_rn(lx.l1, __ldg(pl + y1 * w + x1)));
+        const float val = __fmaf_rn(ly.l0, t, __fmul_rn(ly.l1, bt));
+        if (c == 0) {
+            best = val;
+        } else if (argmax_better(val, best)) {
+            best = val;
+            bi = c;
+        }
+    }
+    return bi;
+}
+
+__device__ __forceinline__ int pred_fullres(const float *img, int C, size_t plane, size_t off) {
+    float best = __ldg(img + off);
+    int bi = 0;
+    for (int c = 1; c < C; ++c) {
+        const float val = __ldg(img + (size_t)c * plane + off);
+        if (argmax_better(val, best)) {
+            best = val;
+            bi = c;
+        }
+    }
+    return bi;
+}
+
+// ATen legacy 'nearest' source index (plots.py:229): min(floor(dst * float(in/out)), in-1)
+__device__ __forceinline__ int nearest_src(int dst, float scale, int n_in) {
+    const int s = (int)floorf(__fmul_rn((float)dst, scale));
+    return s < n_in - 1 ? s : n_in - 1;
+}
+
+// warp-aggregated shared-memory histogram update for an arbitrary number of bins
+__device__ __forceinline__ void cm_add_match(unsigned int *cm_smem, int bin, bool valid) {
+    const unsigned int act = __ballot_sync(0xffffffffu, valid);
+    if (!valid) return;
+    const unsigned int peers = __match_any_sync(act, bin);
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&cm_smem[bin], (unsigned int)__popc(peers));
+}
+
+template <bool FULLRES>
+__global__ void __launch_bounds__(256) seg_general_kernel(const SegParams p) {
+    extern __shared__ unsigned int cm_dyn[];
+    const int b = blockIdx.y;
+    const int nb = p.cm_rows * p.C;
+    const size_t plane_lo = (size_t)p.h * p.w;
+    const size_t plane_hi = (size_t)p.H * p.W;
+    const float *img = p.logits + (size_t)b * p.C * (FULLRES ? plane_hi : plane_lo);
+    if (p.target) {
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) cm_dyn[i] = 0u;
+        __syncthreads();
+        const size_t npx = plane_hi;
+        const size_t per = ((npx + gridDim.x - 1) / gridDim.x + 31) / 32 * 32;
+        const size_t lo = per * blockIdx.x, hi = min(lo + per, npx);
+        for (size_t i0 = lo; i0 < hi; i0 += blockDim.x) {
+            const size_t i = i0 + threadIdx.x;
+            const bool valid = i < hi;
+            int bin = 0;
+            if (valid) {
+                const int Y = (int)(i / p.W), X = (int)(i % p.W);
+                const int pr = FULLRES ? pred_fullres(img, p.C, plane_hi, i) : pred_bilinear(img, p.C, p.h, p.w, p.sy, p.sx, Y, X);
+                bin = clamp_target_row(p.target[(size_t)b * npx + i], p.cm_rows) * p.C + pr;
+            }
+            cm_add_match(cm_dyn, bin, valid);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb; i += blockDim.x)
+            if (cm_dyn[i]) atomicAdd(p.cm + (size_t)(b % p.cm_slots) * nb + i, (unsigned long long)cm_dyn[i]);
+    }
+    if (p.mask_f32 || p.mask_u8) {
+        const size_t npx = (size_t)p.mask_h * p.mask_w;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (size_t)gridDim.x * blockDim.x) {
+            const int Y = nearest_src((int)(i / p.mask_w), p.my, p.H);
+            const int X = nearest_src((int)(i % p.mask_w), p.mx, p.W);
+            const int pr = FULLRES ? pred_fullres(img, p.C, plane_hi, (size_t)Y * p.W + X)
+                                   : pred_bilinear(img, p.C, p.h, p.w, p.sy, p.sx, Y, X);
+            if (p.mask_f32) p.mask_f32[(size_t)b * npx + i] = (float)pr;
+            if (p.mask_u8) p.mask_u8[(size_t)b * npx + i] = (uint8_t)pr;
+        }
+    }
+}
+
+// ---- full-resolution logits, vectorised: W*H % 4 == 0, mask (if any) at full resolution --------
+// One thread = 4 consecutive pixels x kQuadsPerThread strided quads; C planes read with 16 B
+// streaming loads (each logit is read exactly once).
+constexpr int kQuadsPerThread = 8;
+template <bool HAS_TGT, bool HAS_MASK>
+__global__ void __launch_bounds__(256) seg_fullres_vec_kernel(const SegParams p) {
+    __shared__ unsigned int cm_smem[DSN_MAX_CM_ROWS * 32];
+    const int b = blockIdx.y;
+    const size_t plane = (size_t)p.H * p.W;
+    const size_t nquads = plane >> 2;
+    const float *img = p.logits + (size_t)b * p.C * plane;
+    const int nb = p.cm_rows * p.C;
+    if (HAS_TGT) {
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) cm_smem[i] = 0u;
+        __syncthreads();
+    }
+    const size_t q0 = (size_t)blockIdx.x * blockDim.x * kQuadsPerThread;
+#pragma unroll 2
+    for (int j = 0; j < kQuadsPerThread; ++j) {
+        const size_t q = q0 + (size_t)j * blockDim.x + threadIdx.x;
+        const bool valid = q < nquads;
+        int pred[4] = {0, 0, 0, 0};
+        if (valid) {
+            float4 best = ldg_stream_f4(img + 4 * q);
+            for (int c = 1; c < p.C; ++c) {
+                const float4 v = ldg_stream_f4(img + (size_t)c * plane + 4 * q);
+                if (argmax_better(v.x, best.x)) { best.x = v.x; pred[0] = c; }
+                if (argmax_better(v.y, best.y)) { best.y = v.y; pred[1] = c; }
+                if (argmax_better(v.z, best.z)) { best.z = v.z; pred[2] = c; }
+                if (argmax_better(v.w, best.w)) { best.w = v.w; pred[3] = c; }
+            }
+            const size_t pix = (size_t)b * plane + 4 * q;
+            if (HAS_MASK) {
+                if (p.mask_f32)
+                    stg_stream_f4(p.mask_f32 + pix, make_float4((float)pred[0], (float)pred[1], (float)pred[2], (float)pred[3]));
+                if (p.mask_u8)
+                    *reinterpret_cast<uint32_t *>(p.mask_u8 + pix) =
+                        (uint32_t)pred[0] | ((uint32_t)pred[1] << 8) | ((uint32_t)pred[2] << 16) | ((uint32_t)pred[3] << 24);
+            }
+        }
+        if (HAS_TGT) {
+            long long tv[4] = {0, 0, 0, 0};
+            if (valid) {
+                const size_t pix = (size_t)b * plane + 4 * q;
+                const longlong2 ta = ldg_stream_ll2(p.target + pix);
+                const longlong2 tb = ldg_stream_ll2(p.target + pix + 2);
+                tv[0] = ta.x; tv[1] = ta.y; tv[2] = tb.x; tv[3] = tb.y;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                cm_add_match(cm_smem, clamp_target_row(tv[k], p.cm_rows) * p.C + pred[k], valid);
+        }
+    }
+    if (HAS_TGT) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb; i += blockDim.x)
+            if (cm_smem[i]) atomicAdd(p.cm + (size_t)(b % p.cm_slots) * nb + i, (unsigned long long)cm_smem[i]);
+    }
+}
+
+// ---- plain upsample (strict drop-in for nn.Upsample, yolo.py:183) ------------------------------
+__global__ void __launch_bounds__(256) upsample_bilinear_ac_kernel(const float *__restrict__ in, long long planes, int h, int w,
+                                                                   int H, int W, float sy, float sx, float *__restrict__ out) {
+    const size_t total = (size_t)planes * H * W;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int X = (int)(i % W);
+        const size_t t = i / W;
+        const int Y = (int)(t % H);
+        const float *pl = in + (t / H) * (size_t)h * w;
+        const Lerp ly = lerp_coeff(sy, Y, h);
+        const Lerp lx = lerp_coeff(sx, X, w);
+        const int y1 = ly.i0 + (ly.i0 < h - 1), x1 = lx.i0 + (lx.i0 < w - 1);
+        const float tp = __fmaf_rn(lx.l0, __ldg(pl + ly.i0 * w + lx.i0), __fmul_rn(lx.l1, __ldg(pl + ly.i0 * w + x1)));
+        const float bt = __fmaf_rn(lx.l0, __ldg(pl + y1 * w + lx.i0), __fmul_rn(lx.l1, __ldg(pl + y1 * w + x1)));
+        out[i] = __fmaf_rn(ly.l0, tp, __fmul_rn(ly.l1, bt));
+    }
+}
+
+static inline float ac_scale(int n_in, int n_out) { return n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.0f; }
+
+static int check_seg_args(const float *logits, int bs, int C, int H, int W, const int64_t *target, float *mask_f32,
+                          uint8_t *mask_u8, int mask_h, int mask_w, unsigned long long *cm, int cm_slots, int cm_rows) {
+    if (!logits || bs < 0 || C < 1 || H < 1 || W < 1) return DSN_E_INVALID;
+    if ((target != nullptr) != (cm != nullptr)) return DSN_E_INVALID;
+    if (target && (cm_slots < 1 || cm_rows < 1)) return DSN_E_INVALID;
+    if ((mask_f32 || mask_u8) && (mask_h < 1 || mask_w < 1)) return DSN_E_INVALID;
+    if (bs > 65535) return DSN_E_UNSUPPORTED;
+    if ((long long)cm_rows * C > 12288) return DSN_E_UNSUPPORTED;   // 48 KB of shared-memory bins
+    return DSN_OK;
+}
+
+template <bool FULLRES>
+static int launch_general(const SegParams &p, cudaStream_t st) {
+    const size_t px = std::max((size_t)p.H * p.W, (size_t)p.mask_h * p.mask_w);
+    int gx = (int)std::min<size_t>((px + 256 * 16 - 1) / (256 * 16), 4096);
+    gx = std::max(gx, 1);
+    const size_t smem = p.target ? (size_t)p.cm_rows * p.C * sizeof(unsigned int) : 0;
+    seg_general_kernel<FULLRES><<<dim3(gx, p.bs), 256, smem, st>>>(p);
+    DSN_CHECK_LAUNCH();
+    return DSN_OK;
+}
+
+template <int C>
+static int launch_tile(const SegParams &p, cudaStream_t st) {
+    const int G = p.W / 4;
+    int threads = std::min(512, (G + 31) / 32 * 32);
+    dim3 grid((p.H + kTileRows - 1) / kTileRows, p.bs);
+    const bool tgt = p.target != nullptr, mask = p.mask_f32 || p.mask_u8;
+    if (tgt && mask) seg_fused_tile_kernel<C, true, true><<<grid, threads, 0, st>>>(p);
+    else if (tgt) seg_fused_tile_kernel<C, true, false><<<grid, threads, 0, st>>>(p);
+    else seg_fused_tile_kernel<C, false, true><<<grid, threads, 0, st>>>(p);
+    DSN_CHECK_LAUNCH();
+    return DSN_OK;
+}
+
+}  // namespace dsn
+
+using namespace dsn;
+
+extern "C" __attribute__((visibility("default"))) int dsn_seg_fused(const float *logits, int bs, int C, int h, int w, int H, int W, const int64_t *target,
+                             float *mask_f32, uint8_t *mask_u8, int mask_h, int mask_w, unsigned long long *cm,
+                             int cm_slots, int cm_rows, void *stream) {
+    int rc = check_seg_args(logits, bs, C, H, W, target, mask_f32, mask_u8, mask_h, mask_w, cm, cm_slots, cm_rows);
+    if (rc) return rc;
+    if (h < 1 || w < 1) return DSN_E_INVALID;
+    const bool has_mask = mask_f32 || mask_u8;
+    if (bs == 0 || (!target && !has_mask)) return DSN_OK;
+    SegParams p{};
+    p.logits = logits; p.bs = bs; p.C = C; p.h = h; p.w = w; p.H = H; p.W = W;
+    p.target = (const long long *)target; p.mask_f32 = mask_f32; p.mask_u8 = mask_u8;
+    p.mask_h = has_mask ? mask_h : 0; p.mask_w = has_mask ? mask_w : 0;
+    p.cm = cm; p.cm_slots = cm_slots; p.cm_rows = cm_rows;
+    p.sy = ac_scale(h, H); p.sx = ac_scale(w, W);
+    p.my = has_mask ? (float)H / (float)mask_h : 1.f;
+    p.mx = has_mask ? (float)W / (float)mask_w : 1.f;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool fast = C >= 2 && C <= kMaxPackedC && (W % 4 == 0) && (H - 1) >= 8 * (h - 1) && (W - 1) >= 8 * (w - 1) &&
+                      (!has_mask || (mask_h == H && mask_w == W)) && (!target || cm_rows <= DSN_MAX_CM_ROWS) &&
+                      (((uintptr_t)mask_f32 & 15) == 0) && (((uintptr_t)mask_u8 & 3) == 0) && (((uintptr_t)target & 15) == 0);
+    if (!fast) return launch_general<false>(p, st);
+    switch (C) {
+        case 2: return launch_tile<2>(p, st);
+        case 3: return launch_tile<3>(p, st);
+        default: return launch_tile<4>(p, st);
+    }
+}
+
+extern "C" __attribute__((visibility("default"))) int dsn_seg_fullres(const float *logits, int bs, int C, int H, int W, const int64_t *target, float *mask_f32,
+                               uint8_t *mask_u8, int mask_h, int mask_w, unsigned long long *cm, int cm_slots,
+                               int cm_rows, void *stream) {
+    int rc = check_seg_args(logits, bs, C, H, W, target, mask_f32, mask_u8, mask_h, mask_w, cm, cm_slots, cm_rows);
+    if (rc) return rc;
+    const bool has_mask = mask_f32 || mask_u8;
+    if (bs == 0 || (!target && !has_mask)) return DSN_OK;
+    SegParams p{};
+    p.logits = logits; p.bs = bs; p.C = C; p.h = H; p.w = W; p.H = H; p.W = W;
+    p.target = (const long long *)target; p.mask_f32 = mask_f32; p.mask_u8 = mask_u8;
+    p.mask_h = has_mask ? mask_h : 0; p.mask_w = has_mask ? mask_w : 0;
+    p.cm = cm; p.cm_slots = cm_slots; p.cm_rows = cm_rows;
+    p.sy = 1.f; p.sx = 1.f;
+    p.my = has_mask ? (float)H / (float)mask_h : 1.f;
+    p.mx = has_mask ? (float)W / (float)mask_w : 1.f;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t plane = (size_t)H * W;
+    const bool fast = (plane % 4 == 0) && (!has_mask || (mask_h == H && mask_w == W)) &&
+                      (!target || cm_rows * C <= DSN_MAX_CM_ROWS * 32) && (((uintptr_t)logits & 15) == 0) &&
+                      (((uintptr_t)mask_f32 & 15) == 0) && (((uintptr_t)mask_u8 & 3) == 0) && (((uintptr_t)target & 15) == 0);
+    if (!fast) return launch_general<true>(p, st);
+    const size_t nquads = plane / 4;
+    dim3 grid((unsigned)((nquads + 256 * kQuadsPerThread - 1) / (256 * kQuadsPerThread)), bs);
+    const bool tgt = target != nullptr;
+    if (tgt && has_mask) seg_fullres_vec_kernel<true, true><<<grid, 256, 0, st>>>(p);
+    else if (tgt) seg_fullres_vec_kernel<true, false><<<grid, 256, 0, st>>>(p);
+    else seg_fullres_vec_kernel<false, true><<<grid, 256, 0, st>>>(p);
+    DSN_CHECK_LAUNCH();
+    return DSN_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int dsn_upsample_bilinear_ac(const float *in, int64_t planes, int h, int w, int H, int W, float *out,
+                                        void *stream) {
+    if (!in || !out || planes < 0 || h < 1 || w < 1 || H < 1 || W < 1) return DSN_E_INVALID;
+    if (planes == 0) return DSN_OK;
+    const size_t total = (size_t)planes * H * W;
+    const int grid = (int)std::min<size_t>((total + 256 * 8 - 1) / (256 * 8), 148 * 32);
+    upsample_bilinear_ac_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, planes, h, w, H, W, ac_scale(h, H), ac_scale(w, W), out);
+    DSN_CHECK_LAUNCH();
+    return DSN_OK;
+}

@@ -1,0 +1,257 @@
+"""Tensor-level wrappers of the C-ABI kernels.  PyTorch is used for device memory and streams only;
+all arithmetic happens in the hand-written sm_100a kernels behind ``include/desenet_b200.h``.
+Every function enqueues on the current CUDA stream of the input's device and does not synchronise."""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_float, c_int, c_uint64, c_void_p
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+MAX_WH = 4096.0      # core/utils/general.py:675
+MAX_NMS = 30000      # core/utils/general.py:676
+
+
+def _require_cuda(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"desenet_b200: {name} must live on a CUDA device (got {t.device}); "
+                           "this package has no CPU path")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _stream(device) -> c_void_p:
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> c_void_p:
+    return c_void_p(t.data_ptr() if t is not None else 0)
+
+
+def class_mask(classes, nc: int):
+    """general.py:717-718 `classes` filter as the 4 x uint64 bitmask of the C ABI (None = all)."""
+    if classes is None:
+        return None
+    if isinstance(classes, torch.Tensor):
+        classes = classes.tolist()
+    m = [0, 0, 0, 0]
+    for c in classes:
+        c = int(c)
+        if 0 <= c < min(nc, 256):
+            m[c >> 6] |= 1 << (c & 63)
+    return (c_uint64 * 4)(*m)
+
+
+class Head:
+    """Raw Detect head outputs + geometry (the arguments of the ``*_levels`` entry points)."""
+
+    def __init__(self, levels: Sequence[torch.Tensor], anchor_grid, stride):
+        if len(levels) == 0:
+            raise ValueError("no detection levels")
+        self.levels: List[torch.Tensor] = [_require_cuda(l, f"levels[{i}]") for i, l in enumerate(levels)]
+        self.device = self.levels[0].device
+        self.nl = len(self.levels)
+        self.bs = int(self.levels[0].shape[0])
+        ag = torch.as_tensor(anchor_grid, dtype=torch.float32).detach().cpu().reshape(self.nl, -1, 2)
+        self.na = int(ag.shape[1])
+        ch = int(self.levels[0].shape[1])
+        if ch % self.na:
+            raise ValueError(f"channels {ch} not divisible by na={self.na}")
+        self.no = ch // self.na
+        self.nc = self.no - 5
+        for l in self.levels:
+            if l.dim() != 4 or int(l.shape[0]) != self.bs or int(l.shape[1]) != ch or l.device != self.device:
+                raise ValueError("levels must be (bs, na*no, ny, nx) tensors on one device")
+        st = torch.as_tensor(stride, dtype=torch.float32).detach().cpu().reshape(-1)
+        if st.numel() != self.nl:
+            raise ValueError("one stride per level expected")
+        self.ny = [int(l.shape[2]) for l in self.levels]
+        self.nx = [int(l.shape[3]) for l in self.levels]
+        self.A = self.na * sum(y * x for y, x in zip(self.ny, self.nx))
+        self.anchor_grid = ag
+        self.stride = st
+        # ctypes views (host arrays of the C ABI)
+        self.c_raw = (c_void_p * self.nl)(*[l.data_ptr() for l in self.levels])
+        self.c_ny = (c_int * self.nl)(*self.ny)
+        self.c_nx = (c_int * self.nl)(*self.nx)
+        self.c_stride = (c_float * self.nl)(*st.tolist())
+        self.c_anchor = (c_float * (self.nl * self.na * 2))(*ag.reshape(-1).tolist())
+
+
+def detect_decode(head: Head, want_z: bool = True, want_x: bool = True):
+    """Detect.forward eval branch after the convs (core/models/yolo.py:259-277): ``(z, [x_i])``."""
+    lib = _lib.load()
+    with torch.cuda.device(head.device):
+        z = torch.empty((head.bs, head.A, head.no), dtype=torch.float32, device=head.device) if want_z else None
+        xs = [torch.empty((head.bs, head.na, ny, nx, head.no), dtype=torch.float32, device=head.device)
+              for ny, nx in zip(head.ny, head.nx)] if want_x else None
+        c_x = (c_void_p * head.nl)(*[x.data_ptr() for x in xs]) if xs is not None else None
+        rc = lib.dsn_detect_decode(head.c_raw, head.c_ny, head.c_nx, head.c_stride, head.c_anchor, head.nl, head.bs,
+                                   head.na, head.no, _ptr(z), c_x, _stream(head.device))
+    _lib.check(rc, "dsn_detect_decode")
+    return z, xs
+
+
+def filter_levels(head: Head, conf_thres: float, multi_label: bool, classes=None, cap: Optional[int] = None,
+                  keys: Optional[torch.Tensor] = None, counts: Optional[torch.Tensor] = None):
+    """Fused decode + candidate filter (yolo.py:259-277 + general.py:668-718) -> (keys, counts)."""
+    lib = _lib.load()
+    ml = bool(multi_label) and head.nc > 1
+    if cap is None:
+        cap = head.A * (head.nc if ml else 1)
+    with torch.cuda.device(head.device):
+        if keys is None:
+            keys = torch.empty((head.bs, cap), dtype=torch.int64, device=head.device)
+        if counts is None:
+            counts = torch.empty((head.bs,), dtype=torch.int32, device=head.device)
+        rc = lib.dsn_filter_levels(head.c_raw, head.c_ny, head.c_nx, head.nl, head.bs, head.na, head.no,
+                                   float(conf_thres), int(ml), class_mask(classes, head.nc), _ptr(keys), cap,
+                                   _ptr(counts), _stream(head.device))
+    _lib.check(rc, "dsn_filter_levels")
+    return keys, counts
+
+
+def filter_z(z: torch.Tensor, conf_thres: float, multi_label: bool, classes=None, cap: Optional[int] = None):
+    """Candidate filter on a decoded prediction (bs, A, no) (general.py:668-718) -> (keys, counts)."""
+    lib = _lib.load()
+    z = _require_cuda(z, "prediction")
+    bs, A, no = (int(v) for v in z.shape)
+    nc = no - 5
+    ml = bool(multi_label) and nc > 1
+    if cap is None:
+        cap = max(A * (nc if ml else 1), 1)
+    with torch.cuda.device(z.device):
+        keys = torch.empty((bs, cap), dtype=torch.int64, device=z.device)
+        counts = torch.empty((bs,), dtype=torch.int32, device=z.device)
+        rc = lib.dsn_filter_z(_ptr(z), bs, A, no, float(conf_thres), int(ml), class_mask(classes, nc), _ptr(keys), cap,
+                              _ptr(counts), _stream(z.device))
+    _lib.check(rc, "dsn_filter_z")
+    return keys, counts
+
+
+def nms_levels(head: Head, keys: torch.Tensor, counts: torch.Tensor, conf_thres: float, iou_thres: float,
+               agnostic: bool, max_det: int, max_nms: int = MAX_NMS, max_wh: float = MAX_WH,
+               det: Optional[torch.Tensor] = None, det_count: Optional[torch.Tensor] = None):
+    lib = _lib.load()
+    with torch.cuda.device(head.device):
+        if det is None:
+            det = torch.empty((head.bs, max(max_det, 0), 6), dtype=torch.float32, device=head.device)
+        if det_count is None:
+            det_count = torch.empty((head.bs,), dtype=torch.int32, device=head.device)
+        rc = lib.dsn_nms_levels(head.c_raw, head.c_ny, head.c_nx, head.c_stride, head.c_anchor, head.nl, head.bs,
+                                head.na, head.no, _ptr(keys), int(keys.shape[1]), _ptr(counts), float(conf_thres),
+                                float(iou_thres), int(bool(agnostic)), int(max_nms), int(max_det), float(max_wh),
+                                _ptr(det), _ptr(det_count), _stream(head.device))
+    _lib.check(rc, "dsn_nms_levels")
+    return det, det_count
+
+
+def nms_z(z: torch.Tensor, keys: torch.Tensor, counts: torch.Tensor, conf_thres: float, iou_thres: float,
+          agnostic: bool, max_det: int, max_nms: int = MAX_NMS, max_wh: float = MAX_WH):
+    lib = _lib.load()
+    z = _require_cuda(z, "prediction")
+    bs, A, no = (int(v) for v in z.shape)
+    with torch.cuda.device(z.device):
+        det = torch.empty((bs, max(max_det, 0), 6), dtype=torch.float32, device=z.device)
+        det_count = torch.empty((bs,), dtype=torch.int32, device=z.device)
+        rc = lib.dsn_nms_z(_ptr(z), bs, A, no, _ptr(keys), int(keys.shape[1]), _ptr(counts), float(conf_thres),
+                           float(iou_thres), int(bool(agnostic)), int(max_nms), int(max_det), float(max_wh),
+                           _ptr(det), _ptr(det_count), _stream(z.device))
+    _lib.check(rc, "dsn_nms_z")
+    return det, det_count
+
+
+def cm_rows_for(n_channels: int, nclass: int) -> int:
+    """Rows of the target-clamped confusion matrix: exact target values 0..max(nclass, C-1) plus one
+    overflow row for everything larger (labeled, but never a class nor equal to a prediction)."""
+    return max(int(nclass), int(n_channels) - 1) + 2
+
+
+def _seg_call(fn_name: str, logits: torch.Tensor, lowres_hw, size, target, mask_dtype, mask_size, cm, cm_rows,
+              mask_out=None):
+    lib = _lib.load()
+    logits = _require_cuda(logits, "logits")
+    if logits.dim() != 4:
+        raise ValueError("logits must be (bs, C, h, w)")
+    bs, C = int(logits.shape[0]), int(logits.shape[1])
+    H, W = int(size[0]), int(size[1])
+    dev = logits.device
+    with torch.cuda.device(dev):
+        m32 = m8 = None
+        mh, mw = (int(mask_size[0]), int(mask_size[1])) if mask_size is not None else (H, W)
+        if mask_out is not None:
+            if mask_out.dtype == torch.float32:
+                m32 = mask_out
+            elif mask_out.dtype == torch.uint8:
+                m8 = mask_out
+            else:
+                raise TypeError("mask_out must be float32 or uint8")
+            if tuple(mask_out.shape) != (bs, mh, mw) or not mask_out.is_contiguous() or mask_out.device != dev:
+                raise ValueError("mask_out must be a contiguous (bs, mask_h, mask_w) tensor on the logits' device")
+        elif mask_dtype is not None:
+            if mask_dtype == torch.float32:
+                m32 = torch.empty((bs, mh, mw), dtype=torch.float32, device=dev)
+            elif mask_dtype == torch.uint8:
+                m8 = torch.empty((bs, mh, mw), dtype=torch.uint8, device=dev)
+            else:
+                raise TypeError("mask dtype must be torch.float32 or torch.uint8")
+        slots = 0
+        if target is not None:
+            target = _require_cuda(target, "target", torch.int64)
+            if tuple(target.shape) != (bs, H, W):
+                raise ValueError(f"target must be {(bs, H, W)}, got {tuple(target.shape)}")
+            if cm is None:
+                cm = torch.zeros((min(max(bs, 1), 64), cm_rows, C), dtype=torch.int64, device=dev)
+            slots = int(cm.shape[0])
+            if cm.dtype != torch.int64 or tuple(cm.shape[1:]) != (cm_rows, C) or not cm.is_contiguous():
+                raise ValueError("cm must be a contiguous int64 (slots, cm_rows, C) tensor")
+        else:
+            cm = None
+        if fn_name == "dsn_seg_fused":
+            h, w = lowres_hw
+            rc = lib.dsn_seg_fused(_ptr(logits), bs, C, h, w, H, W, _ptr(target), _ptr(m32), _ptr(m8), mh, mw, _ptr(cm),
+                                   slots, int(cm_rows), _stream(dev))
+        else:
+            rc = lib.dsn_seg_fullres(_ptr(logits), bs, C, H, W, _ptr(target), _ptr(m32), _ptr(m8), mh, mw, _ptr(cm),
+                                     slots, int(cm_rows), _stream(dev))
+    _lib.check(rc, fn_name)
+    return (m32 if m32 is not None else m8), cm
+
+
+def seg_fused(logits_low: torch.Tensor, size: Tuple[int, int], target: Optional[torch.Tensor] = None,
+              mask_dtype=None, mask_size=None, cm: Optional[torch.Tensor] = None, cm_rows: int = 4, mask_out=None):
+    """Fused upsample(align_corners=True) + argmax (+ mask, + confusion matrix) from LOW-RES logits
+    (yolo.py:183 + plots.py:222-229 + metrics.py:350-388).  Returns ``(mask | None, cm | None)``; cm is
+    (slots, cm_rows, C) int64, accumulate with ``cm.sum(0)``."""
+    return _seg_call("dsn_seg_fused", logits_low, (int(logits_low.shape[2]), int(logits_low.shape[3])), size, target,
+                     mask_dtype, mask_size, cm, cm_rows, mask_out)
+
+
+def seg_fullres(logits: torch.Tensor, target: Optional[torch.Tensor] = None, mask_dtype=None, mask_size=None,
+                cm: Optional[torch.Tensor] = None, cm_rows: int = 4, mask_out=None):
+    """argmax (+ mask, + confusion matrix) from FULL-RES logits (plots.py:222-229, metrics.py:350-388)."""
+    return _seg_call("dsn_seg_fullres", logits, None, (int(logits.shape[2]), int(logits.shape[3])), target, mask_dtype,
+                     mask_size, cm, cm_rows, mask_out)
+
+
+def upsample_bilinear_ac(x: torch.Tensor, size: Tuple[int, int]) -> torch.Tensor:
+    """nn.Upsample(bilinear, align_corners=True) (yolo.py:183), bit-identical to ATen's CPU kernel."""
+    lib = _lib.load()
+    x = _require_cuda(x, "input")
+    H, W = int(size[0]), int(size[1])
+    lead = tuple(int(v) for v in x.shape[:-2])
+    planes = 1
+    for v in lead:
+        planes *= v
+    with torch.cuda.device(x.device):
+        out = torch.empty(lead + (H, W), dtype=torch.float32, device=x.device)
+        rc = lib.dsn_upsample_bilinear_ac(_ptr(x), planes, int(x.shape[-2]), int(x.shape[-1]), H, W, _ptr(out),
+                                          _stream(x.device))
+    _lib.check(rc, "dsn_upsample_bilinear_ac")
+    return out

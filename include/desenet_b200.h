@@ -1,0 +1,143 @@
+/*
+ * desenet_b200.h — C ABI of the B200-native (sm_100a) DeSeNet post-network inference path.
+ *
+ * The reference (splwany/DeSeNet) exposes no FFI/plugin layer for this path: its boundary is a
+ * set of Python callables.  This header is the boundary a binding would bind:
+ * plain pointers and sizes, no torch types.  Every entry point
+ *   - returns int: 0 = ok, >0 = a cudaError_t raised while enqueueing, <0 = argument error
+ *     (DSN_E_*), never throws;
+ *   - only ENQUEUES work on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *     stream) and never synchronises the device;
+ *   - owns no caller-visible memory: every buffer is allocated by the caller (device memory
+ *     unless the parameter says "host").
+ *
+ * Reference file:line each entry point replaces is given at its declaration
+ * (paths are into the reference tree).
+ */
+#ifndef DESENET_B200_H_
+#define DESENET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSN_VERSION 100          /* major*10000 + minor*100 + patch */
+#define DSN_MAX_LEVELS 8         /* detection levels (reference: nl = 3, core/models/yolo.py:244) */
+#define DSN_MAX_ANCHORS 16       /* anchors per level (reference: na = 3, yolo.py:245) */
+#define DSN_MAX_CM_ROWS 8        /* confusion-matrix rows handled by the packed-counter path */
+
+/* argument-error codes (negative); positive return values are cudaError_t */
+#define DSN_OK 0
+#define DSN_E_INVALID (-1)       /* null pointer / non-positive size / out-of-range value */
+#define DSN_E_UNSUPPORTED (-2)   /* shape outside what the kernels implement */
+#define DSN_E_ALIGN (-3)         /* pointer not aligned as documented */
+
+int dsn_version(void);
+/* Static string for a return code of any function below (cudaGetErrorString for codes > 0). */
+const char *dsn_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------
+ * Detection head geometry, shared by the calls below.
+ *   raw[l]      device pointer, level l conv output, NCHW fp32 (bs, na*no, ny[l], nx[l]);
+ *               channel = a*no + o                                  (core/models/yolo.py:258-260)
+ *   stride[l]   host, pixels per cell (8,16,32)                      (yolo.py:315)
+ *   anchor_grid host, nl*na*2 floats, PIXEL anchors (w,h) = the `anchor_grid` buffer (yolo.py:251)
+ *   no = nc + 5; rows of the decoded prediction are ordered level-major, then anchor, gy, gx
+ *   (yolo.py:275-277), A = sum_l na*ny[l]*nx[l].
+ * ------------------------------------------------------------------------------------------ */
+
+/* Detect.forward, eval branch, everything after the 1x1 convs (core/models/yolo.py:259-277).
+ * z      (bs, A, no) fp32 or NULL:  sigmoid + grid/anchor xywh decode, levels concatenated.
+ * xperm  host array of nl device pointers or NULL: xperm[l] (bs, na, ny, nx, no) = the permuted
+ *        raw logits the reference also returns (yolo.py:260). */
+int dsn_detect_decode(const float *const *raw, const int *ny, const int *nx, const float *stride,
+                      const float *anchor_grid, int nl, int bs, int na, int no,
+                      float *z, float *const *xperm, void *stream);
+
+/* Candidate keys.  A candidate is one (row, class) pair that passes non_max_suppression's
+ * filters (core/utils/general.py:668,687,703,710-718).  It is emitted as ONE 64-bit key
+ *     key = (~float_bits(conf) << 32) | (row * nc + cls)
+ * so ascending key order == descending confidence, ties by reference candidate order
+ * (general.py:710-714 row-major) — the order torchvision's stable sort sees (general.py:734).
+ * keys    (bs, cap) uint64, written in arbitrary order within an image
+ * counts  (bs) int32: total candidates of the image (may exceed cap: then only the first cap
+ *         arrivals were stored and the caller must retry with a larger cap)
+ * class_mask host, 4 x uint64 bitmask of allowed classes (general.py:717-718) or NULL = all.
+ */
+
+/* Fused decode + filter straight from the raw head outputs: sigmoid(obj) > conf_thres,
+ * conf = obj*cls, multi-label / best-class selection, class filter, warp-aggregated compaction.
+ * Replaces yolo.py:259-277 + general.py:668-718 without materialising z. */
+int dsn_filter_levels(const float *const *raw, const int *ny, const int *nx, int nl, int bs, int na,
+                      int no, float conf_thres, int multi_label, const uint64_t *class_mask,
+                      uint64_t *keys, int64_t cap, int *counts, void *stream);
+
+/* Same filter on an already decoded prediction (bs, A, no) — the input of the reference's
+ * non_max_suppression(prediction, ...) (general.py:659). */
+int dsn_filter_z(const float *z, int bs, int64_t A, int no, float conf_thres, int multi_label,
+                 const uint64_t *class_mask, uint64_t *keys, int64_t cap, int *counts, void *stream);
+
+/* Per-image NMS over the candidate keys: lazy descending-score selection (histogram select +
+ * in-shared-memory sort of the next chunk), top-max_nms cut (general.py:728-729), class-offset
+ * boxes (general.py:732-733), greedy IoU suppression with torchvision's CPU arithmetic
+ * (call site general.py:734), stop at max_det (general.py:735-736), write rows
+ * [x1,y1,x2,y2,conf,cls] (general.py:745).
+ *   conf_thres the threshold the keys were produced with (dsn_filter_*): every key then satisfies
+ *              conf > conf_thres, which bounds the key range the selection histogram covers
+ *   iou_thres  compared as torchvision does: (double)iou_fp32 > iou_thres
+ *   max_wh     class offset in pixels (4096, general.py:675); agnostic != 0 => offset 0
+ *   det        (bs, max_det, 6) fp32, rows >= det_count[i] are left untouched
+ *   det_count  (bs) int32; -1 when counts[i] > cap (keys were dropped: retry with a larger cap)
+ * Box source is either the raw levels (dsn_nms_levels: decode on the fly, yolo.py:266-269 +
+ * general.py:523-530) or a decoded prediction (dsn_nms_z). */
+int dsn_nms_levels(const float *const *raw, const int *ny, const int *nx, const float *stride,
+                   const float *anchor_grid, int nl, int bs, int na, int no,
+                   const uint64_t *keys, int64_t cap, const int *counts, float conf_thres,
+                   double iou_thres, int agnostic, int max_nms, int max_det, float max_wh,
+                   float *det, int *det_count, void *stream);
+
+int dsn_nms_z(const float *z, int bs, int64_t A, int no,
+              const uint64_t *keys, int64_t cap, const int *counts, float conf_thres,
+              double iou_thres, int agnostic, int max_nms, int max_det, float max_wh,
+              float *det, int *det_count, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Segmentation tail.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Fused  nn.Upsample(bilinear, align_corners=True) (core/models/yolo.py:183)
+ *      + argmax over classes, lowest index on ties (core/utils/plots.py:228,
+ *        core/utils/metrics.py:356,375)
+ *      + optional mask write, nearest-resized to (mask_h, mask_w) (plots.py:229)
+ *      + optional confusion-matrix accumulation against an int64 target
+ *        (closed form of metrics.py:350-388).
+ * logits   (bs, C, h, w) fp32 LOW-RES head output (input of the final Upsample)
+ * H, W     full-resolution size the reference would upsample to (8h, 8w)
+ * target   (bs, H, W) int64 or NULL.  Values are wrapped to int32 as metrics.py:359,380 do,
+ *          then clamped into [0, cm_rows-1] (negatives -> 0: neither labeled nor a class).
+ * mask_f32 (bs, mask_h, mask_w) fp32 or NULL;  mask_u8 same shape uint8 or NULL
+ * cm       (cm_slots, cm_rows, C) uint64 or NULL, ACCUMULATED into (caller zeroes once);
+ *          image b adds into slot b % cm_slots; the confusion matrix is the sum over slots.
+ *          cm[r][p] = #pixels with clamped target r and predicted class p.
+ */
+int dsn_seg_fused(const float *logits, int bs, int C, int h, int w, int H, int W,
+                  const int64_t *target, float *mask_f32, uint8_t *mask_u8, int mask_h, int mask_w,
+                  unsigned long long *cm, int cm_slots, int cm_rows, void *stream);
+
+/* Same outputs from FULL-RES logits (bs, C, H, W) — the tensor the reference's
+ * segoutput_to_target / batch_pix_accuracy / batch_intersection_union receive. */
+int dsn_seg_fullres(const float *logits, int bs, int C, int H, int W,
+                    const int64_t *target, float *mask_f32, uint8_t *mask_u8, int mask_h, int mask_w,
+                    unsigned long long *cm, int cm_slots, int cm_rows, void *stream);
+
+/* nn.Upsample(bilinear, align_corners=True) alone (core/models/yolo.py:183): (planes,h,w) ->
+ * (planes,H,W), bit-identical to ATen's CPU kernel (fma(l0,a,l1*b) lerps, horizontal first). */
+int dsn_upsample_bilinear_ac(const float *in, int64_t planes, int h, int w, int H, int W,
+                             float *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DESENET_B200_H_ */

@@ -115,11 +115,11 @@ void orc_argmax_first(const float *logits, int64_t bs, int C, int64_t hw, int32_
 
 /* ---- target-clamped confusion matrix: closed form behind batch_pix_accuracy /
  *      batch_intersection_union (core/utils/metrics.py:350-388).  Targets are wrapped to int32
- *      first, as metrics.py:359,380 (`astype('int32')`).  rows: see oracle/port.py:cm_rows. ---- */
+ *      first, as metrics.py:359,380 (`astype('int32')`).  rows: see oracle/port.py:cm_rows (clamp into [0, rows-1], negatives -> 0). ---- */
 void orc_confusion_matrix(const int32_t *pred, const int64_t *target, int64_t n, int C, int rows, int64_t *cm) {
     for (int64_t i = 0; i < n; ++i) {
         int32_t t = (int32_t)(uint32_t)(uint64_t)target[i];
-        int r = t < 0 ? rows - 2 : (t >= rows - 2 ? rows - 1 : t);
+        int r = t < 0 ? 0 : (t > rows - 1 ? rows - 1 : t);
         cm[(int64_t)r * C + pred[i]] += 1;
     }
 }

@@ -312,18 +312,18 @@ def batch_intersection_union(output: torch.Tensor, target: torch.Tensor, nclass:
 
 
 def cm_rows(n_channels: int, nclass: int) -> int:
-    """Row count of the target-clamped confusion matrix used by the CUDA path: rows
-    0..R-3 are exact target values, row R-2 collects negative targets, row R-1 collects
-    targets >= R-2 (which exceed both ``nclass`` and every predictable class)."""
-    return max(nclass + 1, n_channels) + 2
+    """Row count of the target-clamped confusion matrix used by the CUDA path: rows 0..R-2 are
+    exact target values 0..max(nclass, C-1) (negatives fold into row 0: neither labeled nor a
+    class), row R-1 collects every larger target (labeled, never a class nor a prediction)."""
+    return max(nclass, n_channels - 1) + 2
 
 
 def confusion_matrix(predict: np.ndarray, target: np.ndarray, n_channels: int, rows: int) -> np.ndarray:
     """CM[row(t)][p] over all pixels, int64; ``target`` is first wrapped to int32 exactly as
-    metrics.py:359,380 do (``astype('int32')``)."""
+    metrics.py:359,380 do (``astype('int32')``), then clamped into [0, rows-1]."""
     t = np.asarray(target).astype("int32").astype(np.int64).reshape(-1)
     p = np.asarray(predict).astype(np.int64).reshape(-1)
-    r = np.where(t < 0, rows - 2, np.where(t >= rows - 2, rows - 1, t))
+    r = np.clip(t, 0, rows - 1)
     cm = np.zeros((rows, n_channels), np.int64)
     np.add.at(cm, (r, p), 1)
     return cm
@@ -334,8 +334,8 @@ def seg_stats_from_cm(cm: np.ndarray, nclass: int):
     of metrics.py:350-388 incl. np.histogram's right-closed last bin (value==nclass folds into
     the last bin; class 0 and values > nclass are never counted)."""
     rows, C = cm.shape
-    exact = rows - 2
-    labeled = int(cm[1:exact].sum() + cm[rows - 1].sum())
+    exact = rows - 1
+    labeled = int(cm[1:].sum())
     correct = int(sum(cm[k, k] for k in range(1, min(exact, C))))
     nb = nclass - 1
     inter = np.zeros(nb, np.int64)

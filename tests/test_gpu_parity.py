@@ -1,0 +1,407 @@
+"""GPU (-m gpu): parity of the CUDA path (through the C ABI) against the golden fixtures generated
+from the real reference and against the oracle on seeded inputs.
+
+Bars (BASELINE.json north_star): decoded boxes/scores within 1e-5 relative (fp32; only sigmoid's
+expf differs CPU<->GPU); NMS outputs bit-exact given identical decoded rows; argmax masks and
+confusion matrices bit-exact (the fused kernel reproduces ATen's CPU upsample bit-for-bit, so no
+"given identical upsampled logits" caveat is needed)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cport, port
+from tests.nms_param_sets import NMS_PARAM_SETS
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5        # north_star tolerance for decoded boxes and scores
+
+
+@pytest.fixture(scope="module")
+def dsn():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import desenet_b200
+    from desenet_b200 import ops
+    desenet_b200.ops = ops
+    return desenet_b200
+
+
+def dev(a, dtype=None):
+    t = torch.as_tensor(a)
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def levels_of(g):
+    return [dev(g[f"raw{i}"]) for i in range(3)]
+
+
+def assert_dets_equal(got, want, msg=""):
+    assert len(got) == len(want), msg
+    for i, (a, b) in enumerate(zip(got, want)):
+        a = a.cpu().numpy()
+        b = np.asarray(b)
+        assert a.shape == b.shape, f"{msg} image {i}: {a.shape} vs {b.shape}"
+        assert np.array_equal(a, b), f"{msg} image {i}: max |diff| {np.abs(a - b).max() if a.size else 0}"
+
+
+# ------------------------------------------------------------------------------------------------
+# a1  Detect decode
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["synthT_s160_nc6.npz", "synthT_s64_nc80.npz", "real_desenet_s128.npz"])
+def test_decode_matches_reference(dsn, golden, name):
+    g = golden(name)
+    ag = g["anchor_grid"] if "anchor_grid" in g else port.DEFAULT_ANCHORS
+    st = g["stride"] if "stride" in g else port.DEFAULT_STRIDES
+    z, xs = dsn.detect_forward(levels_of(g), ag, st)
+    zr = g["z"]
+    assert z.shape == zr.shape
+    rel = np.abs(z.cpu().numpy() - zr) / np.maximum(np.abs(zr), 1e-30)
+    assert rel.max() <= REL_TOL, rel.max()
+    if "xperm0" in g:
+        for i, x in enumerate(xs):
+            assert np.array_equal(x.cpu().numpy(), g[f"xperm{i}"])          # pure permutation: bit-exact
+    else:
+        _, xr = port.decode_levels([torch.from_numpy(g[f"raw{i}"]) for i in range(3)], ag, st, int(g["nc"]))
+        for x, r in zip(xs, xr):
+            assert torch.equal(x.cpu(), r)
+
+
+def test_decode_lazy_head_outputs(dsn, golden):
+    g = golden("synthT_s160_nc6.npz")
+    ho = dsn.HeadOutputs(levels_of(g), port.DEFAULT_ANCHORS, port.DEFAULT_STRIDES)
+    z, xs = dsn.detect_forward(levels_of(g), port.DEFAULT_ANCHORS, port.DEFAULT_STRIDES)
+    assert torch.equal(ho.z, z) and all(torch.equal(a, b) for a, b in zip(ho.x, xs))
+    assert ho.shape == tuple(z.shape)
+
+
+# ------------------------------------------------------------------------------------------------
+# a2-a4  non_max_suppression: strict path on the reference's own decoded rows -> bit-exact
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["synthT_s160_nc6.npz", "synthT_s64_nc80.npz"])
+@pytest.mark.parametrize("k", range(len(NMS_PARAM_SETS)))
+def test_nms_strict_bit_exact_vs_reference_fixture(dsn, golden, name, k):
+    g = golden(name)
+    out = dsn.non_max_suppression(dev(g["z"]), **NMS_PARAM_SETS[k])
+    assert_dets_equal(out, [g[f"nms{k}_{i}"] for i in range(len(out))], f"{name} set {k}")
+
+
+def test_nms_real_model_fixture(dsn, golden):
+    g = golden("real_desenet_s128.npz")
+    z = dev(g["z"])
+    out = dsn.non_max_suppression(z, 0.001, 0.6, multi_label=True, max_det=300)
+    assert_dets_equal(out, [g[f"nms_val_{i}"] for i in range(2)])
+    out = dsn.non_max_suppression(z, 0.25, 0.45)
+    for o in out:
+        assert tuple(o.shape) == (0, 6)                # KAT 8: random-init model has no dets at 0.25
+
+
+def test_nms_over_30000_candidates_fixture(dsn, golden):
+    g = golden("over30k_s160_nc80.npz")
+    z, _ = port.decode_levels([torch.from_numpy(g[f"raw{i}"]) for i in range(3)], port.DEFAULT_ANCHORS,
+                              port.DEFAULT_STRIDES, 80)
+    out = dsn.non_max_suppression(z.cuda(), 0.001, 0.6, multi_label=True, max_det=300)
+    assert_dets_equal(out, [g["nms0_0"]])
+
+
+@pytest.mark.parametrize("name", ["synthT_s160_nc6.npz", "synthT_s64_nc80.npz", "over30k_s160_nc80.npz"])
+def test_nms_fused_equals_strict_and_oracle(dsn, golden, name):
+    """Fused path (raw head outputs -> keys -> NMS with on-the-fly box decode) == strict path on the
+    kernel's own z == oracle on that z (bit-exact), for every parameter set."""
+    g = golden(name)
+    lv = levels_of(g)
+    ho = dsn.HeadOutputs(lv, port.DEFAULT_ANCHORS, port.DEFAULT_STRIDES)
+    z = ho.z
+    sets = NMS_PARAM_SETS if "over30k" not in name else [NMS_PARAM_SETS[1], dict(conf_thres=0.3, iou_thres=0.5, max_det=50)]
+    for kw in sets:
+        fused = dsn.non_max_suppression(ho, **kw)
+        strict = dsn.non_max_suppression(z, **kw)
+        want = port.non_max_suppression(z.cpu(), nms_impl="c", **kw)
+        assert_dets_equal(strict, [w.numpy() for w in want], f"{name} strict {kw}")
+        assert_dets_equal(fused, [w.numpy() for w in want], f"{name} fused {kw}")
+
+
+def test_nms_fused_close_to_reference_fixture(dsn, golden):
+    """End to end from the raw logits against the REFERENCE's detections: same detections, boxes and
+    scores within 1e-5 relative (candidates within an ulp of a threshold may legitimately differ)."""
+    g = golden("synthT_s160_nc6.npz")
+    ho = dsn.HeadOutputs(levels_of(g), port.DEFAULT_ANCHORS, port.DEFAULT_STRIDES)
+    for k, kw in enumerate(NMS_PARAM_SETS):
+        out = dsn.non_max_suppression(ho, **kw)
+        for i, o in enumerate(out):
+            want = g[f"nms{k}_{i}"]
+            o = o.cpu().numpy()
+            if o.shape == want.shape and np.array_equal(o[:, 5], want[:, 5]):
+                rel = np.abs(o - want) / np.maximum(np.abs(want), 1.0)
+                assert rel.max() <= REL_TOL if o.size else True
+            else:   # a borderline candidate flipped: sizes may differ by a few rows at most
+                assert abs(o.shape[0] - want.shape[0]) <= 2, (k, i, o.shape, want.shape)
+
+
+def _z_from_boxes(boxes_xyxy, scores, cls, nc):
+    """Prediction rows whose xywh2xyxy gives back exactly the given corner boxes (power-of-two
+    friendly values) with obj = 1 and conf = score on class cls."""
+    b = np.asarray(boxes_xyxy, np.float32)
+    n = b.shape[0]
+    z = np.zeros((1, n, nc + 5), np.float32)
+    z[0, :, 2] = b[:, 2] - b[:, 0]
+    z[0, :, 3] = b[:, 3] - b[:, 1]
+    z[0, :, 0] = b[:, 0] + z[0, :, 2] / 2
+    z[0, :, 1] = b[:, 1] + z[0, :, 3] / 2
+    z[0, :, 4] = 1.0
+    z[0, np.arange(n), 5 + np.asarray(cls)] = np.asarray(scores, np.float32)
+    return z
+
+
+def test_nms_known_answers(dsn):
+    def run(boxes, scores, thr):
+        z = _z_from_boxes(boxes, scores, [0] * len(boxes), 2)
+        got = dsn.non_max_suppression(dev(z), 0.01, thr)[0].cpu().numpy()
+        want = port.non_max_suppression(torch.from_numpy(z), 0.01, thr, nms_impl="c")[0].numpy()
+        assert np.array_equal(got, want)
+        return got[:, :4].tolist()
+
+    assert run([[0, 0, 10, 10]] * 2, [0.5, 0.5], 0.5) == [[0, 0, 10, 10]]                        # (1) tie -> lower index
+    assert len(run([[0, 0, 1, 1], [0, 0, 1, 0.5]], [0.9, 0.8], 0.5)) == 2                         # (2) IoU == thr kept
+    assert len(run([[5, 5, 5, 5]] * 2, [0.9, 0.8], 0.5)) == 2                                     # (3) zero-area NaN
+    assert len(run([[0, 0, 1, 2.7293658], [0, 0, 1, 1.6376196]], [0.9, 0.8], 0.6)) == 1           # (4) double compare
+    assert len(run([[0, 0, 1, 1], [2, 2, 3, 3], [0, 0, 1, 1]], [0.1, 0.9, 0.1], 0.5)) == 2
+
+
+def _clustered_prediction(bs, n, nc, seed, n_centres=40, score_levels=None, S=640.0):
+    """Decoded rows with heavily overlapping boxes (suppression chains), optional score ties."""
+    g = torch.Generator().manual_seed(seed)
+    centres = torch.rand(bs, n_centres, 2, generator=g) * S
+    which = torch.randint(0, n_centres, (bs, n), generator=g)
+    xy = torch.gather(centres, 1, which[..., None].expand(-1, -1, 2)) + torch.randn(bs, n, 2, generator=g) * 6
+    wh = 40 + torch.rand(bs, n, 2, generator=g) * 60
+    obj = torch.rand(bs, n, 1, generator=g) * 0.9 + 0.1
+    cls = torch.rand(bs, n, nc, generator=g)
+    if score_levels:
+        obj = torch.ones_like(obj)
+        cls = torch.randint(1, score_levels + 1, (bs, n, nc), generator=g).float() / score_levels
+    return torch.cat((xy, wh, obj, cls), 2).contiguous()
+
+
+@pytest.mark.parametrize("case", [
+    dict(n=700, nc=3, kw=dict(conf_thres=0.2, iou_thres=0.45, max_det=300)),
+    dict(n=6000, nc=4, kw=dict(conf_thres=0.05, iou_thres=0.6, multi_label=True, max_det=300)),      # many chunks
+    dict(n=6000, nc=4, kw=dict(conf_thres=0.05, iou_thres=0.6, multi_label=True, max_det=5000)),     # kept > smem cache
+    dict(n=9000, nc=2, kw=dict(conf_thres=0.1, iou_thres=0.5, agnostic=True, max_det=1000)),
+    dict(n=5000, nc=3, levels=7, kw=dict(conf_thres=0.1, iou_thres=0.5, multi_label=True, max_det=2000)),  # huge tie groups
+    dict(n=3000, nc=5, kw=dict(conf_thres=0.3, iou_thres=0.3, classes=[1, 3], max_det=100)),
+    dict(n=40, nc=1, kw=dict(conf_thres=0.3, iou_thres=0.5, multi_label=True)),                       # nc == 1
+])
+def test_nms_stress_bit_exact_vs_oracle(dsn, case):
+    z = _clustered_prediction(2, case["n"], case["nc"], seed=case["n"], score_levels=case.get("levels"))
+    got = dsn.non_max_suppression(z.cuda(), **case["kw"])
+    want = port.non_max_suppression(z, nms_impl="c", **case["kw"])
+    assert_dets_equal(got, [w.numpy() for w in want], str(case["kw"]))
+    assert sum(w.shape[0] for w in want) > 0
+
+
+def test_nms_scores_above_one_and_labels(dsn):
+    z = _clustered_prediction(2, 500, 3, seed=5)
+    z[:, :50, 4] = 1.5                       # generic input: conf > 1 (keys below the conf<=1 hint)
+    labels = [torch.tensor([[1.0, 100, 100, 50, 50], [0.0, 300, 300, 80, 40]]), torch.zeros(0, 5)]
+    kw = dict(conf_thres=0.25, iou_thres=0.45, multi_label=True, max_det=300)
+    got = dsn.non_max_suppression(z.cuda(), labels=[l.cuda() for l in labels], **kw)
+    want = port.non_max_suppression(z, labels=labels, nms_impl="c", **kw)
+    assert_dets_equal(got, [w.numpy() for w in want])
+
+
+def test_nms_empty_and_ragged(dsn):
+    z = _clustered_prediction(3, 64, 2, seed=9)
+    z[1, :, 4] = 0.0                          # image 1 has no candidates
+    got = dsn.non_max_suppression(z.cuda(), 0.25, 0.45)
+    want = port.non_max_suppression(z, 0.25, 0.45, nms_impl="c")
+    assert tuple(got[1].shape) == (0, 6)
+    assert_dets_equal(got, [w.numpy() for w in want])
+    assert dsn.non_max_suppression(torch.zeros(0, 64, 7).cuda()) == []
+    got = dsn.non_max_suppression(z.cuda(), 0.25, 0.45, max_det=0)
+    assert all(tuple(o.shape) == (0, 6) for o in got)
+
+
+def test_nms_full_size_properties(dsn):
+    """BASELINE config 2 size (640x640, bs 64, nc 6, conf .25/iou .45, max_det 1000): fused path vs
+    oracle on a subset of images + size-independent properties on all of them."""
+    levels, _, _ = port.synth_head_outputs(64, 640, 6, seed=0, with_target=False)
+    ho = dsn.HeadOutputs([l.cuda() for l in levels], port.DEFAULT_ANCHORS, port.DEFAULT_STRIDES)
+    kw = dict(conf_thres=0.25, iou_thres=0.45, max_det=1000)
+    out = dsn.non_max_suppression(ho, **kw)
+    assert len(out) == 64
+    z = ho.z.cpu()
+    want = port.non_max_suppression(z[:6], nms_impl="c", **kw)
+    assert_dets_equal(out[:6], [w.numpy() for w in want])
+    for o in out:
+        o = o.cpu()
+        assert o.shape[0] > 0 and o.shape[0] <= 1000
+        assert (o[:-1, 4] >= o[1:, 4]).all()                              # sorted by confidence
+        assert (o[:, 4] > 0.25).all() and (o[:, 2] >= o[:, 0]).all() and (o[:, 3] >= o[:, 1]).all()
+    # idempotence: NMS of the survivors (as a decoded prediction) keeps all of them
+    o = out[0].cpu()
+    zz = torch.zeros(1, o.shape[0], 11)
+    zz[0, :, 2] = o[:, 2] - o[:, 0]
+    zz[0, :, 3] = o[:, 3] - o[:, 1]
+    zz[0, :, 0] = o[:, 0] + zz[0, :, 2] / 2
+    zz[0, :, 1] = o[:, 1] + zz[0, :, 3] / 2
+    zz[0, :, 4] = 1.0
+    zz[0, torch.arange(o.shape[0]), 5 + o[:, 5].long()] = o[:, 4]
+    again = dsn.non_max_suppression(zz.cuda(), **kw)[0]
+    assert again.shape[0] >= o.shape[0] - 2      # re-rounded corners may flip a borderline pair
+
+
+def test_nms_eval_setting_multilabel_full_size(dsn):
+    """BASELINE config 3 setting on 4 images: conf .001 / iou .6 / multi_label / max_det 300 -> ~95 k
+    candidates per image (> max_nms): lazy selection + top-30000 cut vs the oracle."""
+    levels, _, _ = port.synth_head_outputs(4, 640, 6, seed=1, with_target=False)
+    ho = dsn.HeadOutputs([l.cuda() for l in levels], port.DEFAULT_ANCHORS, port.DEFAULT_STRIDES)
+    kw = dict(conf_thres=0.001, iou_thres=0.6, multi_label=True, max_det=300)
+    out = dsn.non_max_suppression(ho, **kw)
+    want = port.non_max_suppression(ho.z.cpu()[:2], nms_impl="c", **kw)
+    assert_dets_equal(out[:2], [w.numpy() for w in want])
+    assert all(o.shape[0] == 300 for o in out)
+
+
+# ------------------------------------------------------------------------------------------------
+# a5-a8  segmentation tail
+# ------------------------------------------------------------------------------------------------
+def test_seg_fixture_cases_bit_exact(dsn, golden):
+    g = golden("seg_cases.npz")
+    for k in range(int(g["n_cases"])):
+        low, full, tgt = g[f"low{k}"], g[f"full{k}"], g[f"target{k}"]
+        C = low.shape[1]
+        H, W = full.shape[-2:]
+        up = dsn.ops.upsample_bilinear_ac(dev(low), (H, W)).cpu().numpy()
+        assert np.array_equal(up, cport.upsample_bilinear_ac(low, H, W))          # == the C oracle, always
+        if H * W > 4096:
+            assert np.array_equal(up, full)                                         # == ATen (reference)
+        sl = dsn.SegLogits(dev(low))
+        size = tuple(int(v) for v in g[f"resized_size{k}"])
+        # from the reference's full-res logits: always bit-exact
+        assert np.array_equal(dsn.segoutput_to_target(dev(full)).cpu().numpy(), g[f"mask{k}"])
+        m = dsn.segoutput_to_target(dev(full), size)
+        assert m.dtype == torch.float32 and np.array_equal(m.cpu().numpy(), g[f"mask{k}_resized"])
+        # fused from the low-res logits: bit-exact wherever ATen's upsample is the fma kernel (see
+        # tests/test_oracle_golden.py: out_h*out_w <= 4096 takes a differently-rounded ATen path)
+        if H * W > 4096:
+            assert np.array_equal(dsn.segoutput_to_target(sl).cpu().numpy(), g[f"mask{k}"])
+            assert np.array_equal(dsn.segoutput_to_target(sl, size).cpu().numpy(), g[f"mask{k}_resized"])
+        else:
+            want = port.segoutput_to_target_np(cport.upsample_bilinear_ac(low, H, W), size)
+            assert np.array_equal(dsn.segoutput_to_target(sl, size).cpu().numpy(), want)
+        # metrics from the full-res reference logits: bit-exact counts
+        t = dev(tgt)
+        c, l = dsn.batch_pix_accuracy(dev(full), t)
+        assert [int(c), int(l)] == list(g[f"pix{k}"])
+        for nclass in (2, 3, 4):
+            i_, u_ = dsn.batch_intersection_union(dev(full), t, nclass)
+            assert np.array_equal(i_, g[f"inter{k}_{nclass}"]) and np.array_equal(u_, g[f"union{k}_{nclass}"])
+            if H * W > 4096:
+                i2, u2 = dsn.batch_intersection_union(sl, t, nclass)
+                assert np.array_equal(i2, i_) and np.array_equal(u2, u_)
+
+
+def test_seg_real_model_fixture(dsn, golden):
+    g = golden("real_desenet_s128.npz")
+    sl = dsn.SegLogits(dev(g["seg_low"]))
+    assert np.array_equal(sl.full().cpu().numpy(), g["seg_full"])
+    assert np.array_equal(dsn.segoutput_to_target(sl).cpu().numpy(), g["mask"])
+    assert np.array_equal(dsn.segoutput_to_target(sl, (96, 170)).cpu().numpy(), g["mask_96x170"])
+    assert np.array_equal(dsn.segoutput_to_target(dev(g["seg_full"]), (96, 170)).cpu().numpy(), g["mask_96x170"])
+    t = dev(g["target"])
+    for nclass in (2, 3):
+        c, l = dsn.batch_pix_accuracy(sl, t)
+        assert [int(c), int(l)] == list(g[f"pix_{nclass}"])
+        i_, u_ = dsn.batch_intersection_union(sl, t, nclass)
+        assert np.array_equal(i_, g[f"inter_{nclass}"]) and np.array_equal(u_, g[f"union_{nclass}"])
+
+
+@pytest.mark.parametrize("C,S,bs", [(2, 640, 8), (3, 320, 3), (4, 256, 2), (2, 1280, 2), (7, 128, 2)])
+def test_seg_full_size_vs_oracle(dsn, C, S, bs):
+    g = torch.Generator().manual_seed(C * 1000 + S)
+    low = torch.randn(bs, C, S // 8, S // 8, generator=g)
+    low[0, :, :3, :3] = 0.25                      # exact ties -> lowest index must win
+    tgt = torch.randint(-1, C + 2, (bs, S, S), generator=g, dtype=torch.int64)
+    tgt[0, 0, :7] = 255
+    tgt[0, 1, :7] = (1 << 40) + 1                 # wraps to int32 value 1 (metrics.py:359 astype('int32'))
+    full = cport.upsample_bilinear_ac(low.numpy(), S, S)
+    pred = cport.argmax_first(full)
+    sl = dsn.SegLogits(low.cuda())
+    mask = dsn.segoutput_to_target(sl)
+    assert mask.dtype == torch.float32 and np.array_equal(mask.cpu().numpy(), pred.astype(np.float32))
+    m8, _ = dsn.ops.seg_fused(low.cuda(), (S, S), mask_dtype=torch.uint8)
+    assert np.array_equal(m8.cpu().numpy(), pred.astype(np.uint8))
+    assert np.array_equal(dsn.segoutput_to_target(torch.from_numpy(full).cuda()).cpu().numpy(), pred.astype(np.float32))
+    assert np.array_equal(sl.full().cpu().numpy(), full)
+    for nclass in (2, 3):
+        rows = port.cm_rows(C, nclass)
+        want = cport.confusion_matrix(pred, tgt.numpy(), C, rows)
+        for src in (sl, torch.from_numpy(full).cuda()):
+            cm = dsn.seg_confusion_matrix(src, tgt.cuda(), nclass).sum(0).cpu().numpy()
+            assert np.array_equal(cm, want), (C, S, nclass)
+            assert cm.sum() == bs * S * S                                          # every pixel counted once
+        i_, u_ = dsn.batch_intersection_union(sl, tgt.cuda(), nclass)
+        i2, u2 = port.batch_intersection_union(torch.from_numpy(full), tgt, nclass)
+        assert np.array_equal(i_, i2) and np.array_equal(u_, u2)
+    # mask + confusion matrix in one launch == separately
+    m2, cm2 = dsn.ops.seg_fused(low.cuda(), (S, S), target=tgt.cuda(), mask_dtype=torch.float32, cm_rows=port.cm_rows(C, 3))
+    assert torch.equal(m2, mask) and np.array_equal(cm2.sum(0).cpu().numpy(), cport.confusion_matrix(pred, tgt.numpy(), C, port.cm_rows(C, 3)))
+
+
+def test_seg_odd_shapes_general_path(dsn):
+    g = torch.Generator().manual_seed(3)
+    for C, h, w, H, W in [(2, 7, 5, 56, 40), (3, 9, 13, 70, 101), (2, 10, 10, 35, 37), (5, 4, 4, 32, 32)]:
+        low = torch.randn(2, C, h, w, generator=g)
+        tgt = torch.randint(0, C, (2, H, W), generator=g, dtype=torch.int64)
+        full = cport.upsample_bilinear_ac(low.numpy(), H, W)
+        pred = cport.argmax_first(full)
+        sl = dsn.SegLogits(low.cuda(), size=(H, W))
+        assert np.array_equal(dsn.segoutput_to_target(sl).cpu().numpy(), pred.astype(np.float32))
+        assert np.array_equal(dsn.segoutput_to_target(sl, (H + 3, 2 * W - 1)).cpu().numpy(),
+                              port.segoutput_to_target_np(full, (H + 3, 2 * W - 1)))
+        want = cport.confusion_matrix(pred, tgt.numpy(), C, port.cm_rows(C, 3))
+        assert np.array_equal(dsn.seg_confusion_matrix(sl, tgt.cuda(), 3).sum(0).cpu().numpy(), want)
+
+
+def test_seg_nan_and_many_classes(dsn):
+    low = torch.randn(1, 12, 8, 8)
+    low[0, 3, 2, 2] = float("nan")
+    low[0, 7, 2, 2] = float("nan")
+    full = cport.upsample_bilinear_ac(low.numpy(), 64, 64)
+    pred = cport.argmax_first(full)
+    assert np.array_equal(dsn.segoutput_to_target(dsn.SegLogits(low.cuda())).cpu().numpy(), pred.astype(np.float32))
+    assert np.array_equal(dsn.segoutput_to_target(torch.from_numpy(full).cuda()).cpu().numpy(), pred.astype(np.float32))
+    tgt = torch.randint(0, 14, (1, 64, 64), dtype=torch.int64)
+    want = cport.confusion_matrix(pred, tgt.numpy(), 12, port.cm_rows(12, 12))
+    assert np.array_equal(dsn.seg_confusion_matrix(dsn.SegLogits(low.cuda()), tgt.cuda(), 12).sum(0).cpu().numpy(), want)
+    assert np.array_equal(dsn.seg_confusion_matrix(torch.from_numpy(full).cuda(), tgt.cuda(), 12).sum(0).cpu().numpy(), want)
+
+
+def test_seg_validation_matches_reference_loop(dsn):
+    g = torch.Generator().manual_seed(4)
+    batches = []
+    for _ in range(3):
+        low = torch.randn(2, 2, 16, 16, generator=g)
+        tgt = torch.randint(0, 3, (2, 128, 128), generator=g, dtype=torch.int64)
+        batches.append((low, tgt))
+
+    class Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.p = torch.nn.Parameter(torch.zeros(1, device="cuda"))
+            self.i = 0
+
+        def forward(self, image):
+            low = batches[self.i][0].cuda()
+            self.i += 1
+            return None, dsn.SegLogits(low)
+
+    loader = [(torch.zeros(2, 3, 128, 128), None, t, None, None) for _, t in batches]
+    for nclass in (2, 3):
+        miou = dsn.seg_validation(Model(), nclass, loader, half_precision=False)
+        ref = [(torch.from_numpy(cport.upsample_bilinear_ac(l.numpy(), 128, 128)), t) for l, t in batches]
+        pa, want = port.seg_validation_accumulate(ref, nclass)
+        assert miou == want and dsn.seg_validation.last["pixAcc"] == pa
