@@ -7,6 +7,7 @@
 // cell index, the contiguous dimension of every channel plane), no shared-memory reuse needed
 // except the decode transposition.
 #include <algorithm>
+#include <cmath>
 
 #include "common.cuh"
 #include "geom.cuh"
@@ -98,67 +99,49 @@ __device__ __forceinline__ int warp_alloc(int *counter, int n_mine) {
 
 constexpr int kClsChunk = 8;
 
-// V consecutive rows per lane.  `Cls` loads the V class confidences of class c (already a
-// probability): cls(c, out[V]).  obj[k] is the objectness probability of row (row0+k); lanes with
-// no passing row (or !valid) skip every class load.  Must be called by all 32 lanes.
-template <int V, class Cls>
-__device__ __forceinline__ void filter_emit(const FilterOut &f, int b, unsigned int row0, int nc, const float (&obj)[V],
-                                            bool valid, Cls cls) {
-    unsigned int pass = 0;
-    if (valid) {
-#pragma unroll
-        for (int k = 0; k < V; ++k) pass |= (obj[k] > f.conf_thres) ? (1u << k) : 0u;      // general.py:668,687
-    }
-    if (!__any_sync(0xffffffffu, pass != 0)) return;
+// One row per lane.  `Cls` provides load(c) -> raw class value of this lane's row and prob(raw) ->
+// class probability (sigmoid for raw head logits, identity for a decoded prediction).  The raw
+// values of a chunk of kClsChunk classes are all loaded before any is used, so a row costs ONE
+// memory round trip per chunk.  obj is the objectness probability; lanes whose row fails
+// `obj > conf_thres` (or !valid) skip every class load.  Must be called by all 32 lanes.
+template <class Cls>
+__device__ __forceinline__ void filter_emit(const FilterOut &f, int b, unsigned int row, int nc, float obj, bool valid,
+                                            const Cls &cls) {
+    const bool pass = valid && obj > f.conf_thres;                                       // general.py:668,687
+    if (!__any_sync(0xffffffffu, pass)) return;
     unsigned long long *kout = f.keys + (size_t)b * f.cap;
     int *counter = f.counts + b;
-    if (!f.multi_label) {
-        // best class, first maximum wins                                   general.py:713-714
-        float best[V];
-        int bcls[V];
-#pragma unroll
-        for (int k = 0; k < V; ++k) { best[k] = 0.f; bcls[k] = 0; }
+    float best = 0.f;
+    int bcls = 0;
+    for (int c0 = 0; c0 < nc; c0 += kClsChunk) {
+        float raw[kClsChunk];
         if (pass) {
-            for (int c = 0; c < nc; ++c) {
-                float cv[V];
-                cls(c, cv);
 #pragma unroll
-                for (int k = 0; k < V; ++k) {
-                    const float conf = __fmul_rn(cv[k], obj[k]);                            // general.py:703
-                    if (c == 0 || argmax_better(conf, best[k])) { best[k] = conf; bcls[k] = c; }
-                }
-            }
+            for (int ci = 0; ci < kClsChunk; ++ci) raw[ci] = (c0 + ci < nc) ? cls.load(c0 + ci) : 0.f;
         }
-        unsigned int emit = 0;
-#pragma unroll
-        for (int k = 0; k < V; ++k)
-            if (((pass >> k) & 1u) && best[k] > f.conf_thres && class_allowed(f, bcls[k])) emit |= 1u << k;   // :714,:717
-        int slot = warp_alloc(counter, __popc(emit));
-#pragma unroll
-        for (int k = 0; k < V; ++k)
-            if ((emit >> k) & 1u) {
-                if (slot < f.cap)
-                    kout[slot] = ((unsigned long long)conf_key(best[k]) << 32) | (unsigned long long)((row0 + k) * (unsigned)nc + bcls[k]);
-                ++slot;
-            }
-    } else {
-        // every (row, class) with conf > thres                               general.py:710-711
-        for (int c0 = 0; c0 < nc; c0 += kClsChunk) {
-            float cf[kClsChunk][V];
-            unsigned int emit = 0;   // bit (ci*V + k)
+        if (!f.multi_label) {
+            // best class, first maximum wins                                   general.py:713
             if (pass) {
 #pragma unroll
                 for (int ci = 0; ci < kClsChunk; ++ci) {
                     const int c = c0 + ci;
                     if (c < nc) {
-                        float cv[V];
-                        cls(c, cv);
-                        const bool ok = class_allowed(f, c);
+                        const float conf = __fmul_rn(cls.prob(raw[ci]), obj);                 // general.py:703
+                        if (c == 0 || argmax_better(conf, best)) { best = conf; bcls = c; }
+                    }
+                }
+            }
+        } else {
+            // every (row, class) with conf > thres                               general.py:710-711
+            float cf[kClsChunk];
+            unsigned int emit = 0;
+            if (pass) {
 #pragma unroll
-                        for (int k = 0; k < V; ++k) {
-                            cf[ci][k] = __fmul_rn(cv[k], obj[k]);
-                            if (ok && ((pass >> k) & 1u) && cf[ci][k] > f.conf_thres) emit |= 1u << (ci * V + k);
-                        }
+                for (int ci = 0; ci < kClsChunk; ++ci) {
+                    const int c = c0 + ci;
+                    if (c < nc) {
+                        cf[ci] = __fmul_rn(cls.prob(raw[ci]), obj);
+                        if (cf[ci] > f.conf_thres && class_allowed(f, c)) emit |= 1u << ci;
                     }
                 }
             }
@@ -166,66 +149,135 @@ __device__ __forceinline__ void filter_emit(const FilterOut &f, int b, unsigned 
             int slot = warp_alloc(counter, __popc(emit));
 #pragma unroll
             for (int ci = 0; ci < kClsChunk; ++ci)
-#pragma unroll
-                for (int k = 0; k < V; ++k)
-                    if ((emit >> (ci * V + k)) & 1u) {
-                        if (slot < f.cap)
-                            kout[slot] = ((unsigned long long)conf_key(cf[ci][k]) << 32) |
-                                         (unsigned long long)((row0 + k) * (unsigned)nc + (c0 + ci));
-                        ++slot;
-                    }
+                if ((emit >> ci) & 1u) {
+                    if (slot < f.cap)
+                        kout[slot] = ((unsigned long long)conf_key(cf[ci]) << 32) | (unsigned long long)(row * (unsigned)nc + (c0 + ci));
+                    ++slot;
+                }
         }
+    }
+    if (!f.multi_label) {
+        const bool emit = pass && best > f.conf_thres && class_allowed(f, bcls);             // general.py:714,717
+        const int slot = warp_alloc(counter, emit ? 1 : 0);
+        if (emit && slot < f.cap)
+            kout[slot] = ((unsigned long long)conf_key(best) << 32) | (unsigned long long)(row * (unsigned)nc + bcls);
     }
 }
 
-// ---- from the raw levels: thread = V consecutive cells of one (image, level, anchor) plane --------
+// ---- from the raw levels -----------------------------------------------------------------------
+// One CTA = a run of kFilterCells cells of ONE (image, level, anchor) plane, so all plane geometry
+// is CTA-uniform.  Phase 1: every thread issues all of its objectness loads (16 B, coalesced,
+// kFilterUnroll in flight), evaluates the sigmoid only for logits above a conservative logit-space
+// bound, and appends the cells that pass `sigmoid(obj) > conf_thres` to a shared-memory list
+// (warp-ballot/scan compaction, cell order preserved inside a warp).  Phase 2: the list is
+// processed one cell per lane — class logits loaded in chunks of 8 (one round trip), conf = obj*cls,
+// best-class or multi-label selection, warp-aggregated emission of the 64-bit keys.  At conf 0.25
+// (~2.6 % of the anchors pass) the kernel is two dependent HBM round trips per CTA and touches only
+// the objectness plane plus the sectors of surviving cells; at conf 0.001 the list holds nearly
+// every cell and phase 2 streams the class planes with coalesced 4 B loads.
+constexpr int kFilterUnroll = 4;
+constexpr int kFilterThreads = 256;
+
+struct ClsFromPlanes {
+    const float *p;        // class-0 plane of this (image, anchor), already offset to the cell
+    size_t plane;
+    __device__ __forceinline__ float load(int c) const { return ldg_stream_f1(p + (size_t)c * plane); }
+    __device__ __forceinline__ float prob(float raw) const { return sigmoidf_ref(raw); }
+};
+
 template <int V>
-__global__ void __launch_bounds__(256) filter_levels_kernel(const HeadGeom g, const FilterOut f) {
+__global__ void __launch_bounds__(kFilterThreads) filter_levels_kernel(const HeadGeom g, const FilterOut f, const float obj_logit_lo) {
+    __shared__ unsigned int list_cell[kFilterThreads * kFilterUnroll * V];
+    __shared__ float list_obj[kFilterThreads * kFilterUnroll * V];
+    __shared__ unsigned int list_n;
     const int b = blockIdx.y;
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;          // unit index inside the image
-    const bool valid = u < g.unit_off[g.nl];
     int l = 0;
-    if (valid)
-        while (l + 1 < g.nl && u >= g.unit_off[l + 1]) ++l;
+    while (l + 1 < g.nl && (int)blockIdx.x >= g.cta_off[l + 1]) ++l;
+    const int cp = blockIdx.x - g.cta_off[l];
+    const int a = cp / g.ctas_per_plane[l];
+    const int tile = cp - a * g.ctas_per_plane[l];
     const int plane = g.plane[l];
-    const int upp = plane / V;                                    // units per plane
-    const int ul = valid ? u - g.unit_off[l] : 0;
-    const int a = ul / upp;
-    const int cell = (ul - a * upp) * V;
-    const float *base = g.raw[l] + ((size_t)(b * g.na + a) * g.no) * plane + cell;
-    float obj[V];
+    const int units = plane / V;
+    const float *pbase = g.raw[l] + ((size_t)(b * g.na + a) * g.no) * plane;
+    const unsigned int prow0 = (unsigned)(g.row_off[l] + a * plane);
+    const int u0 = tile * (kFilterThreads * kFilterUnroll) + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) list_n = 0u;
+    float objraw[kFilterUnroll][V];
 #pragma unroll
-    for (int k = 0; k < V; ++k) obj[k] = 0.f;
-    if (valid) {
-        if constexpr (V == 4) {
-            const float4 t = ldg_stream_f4(base + (size_t)4 * plane);
-            obj[0] = sigmoidf_ref(t.x); obj[1] = sigmoidf_ref(t.y); obj[2] = sigmoidf_ref(t.z); obj[3] = sigmoidf_ref(t.w);
-        } else {
-            obj[0] = sigmoidf_ref(ldg_stream_f1(base + (size_t)4 * plane));
+    for (int j = 0; j < kFilterUnroll; ++j) {
+        const int u = u0 + j * kFilterThreads;
+#pragma unroll
+        for (int k = 0; k < V; ++k) objraw[j][k] = -INFINITY;
+        if (u < units) {
+            if constexpr (V == 4) {
+                const float4 t = ldg_stream_f4(pbase + (size_t)4 * plane + u * 4);
+                objraw[j][0] = t.x; objraw[j][1] = t.y; objraw[j][2] = t.z; objraw[j][3] = t.w;
+            } else {
+                objraw[j][0] = ldg_stream_f1(pbase + (size_t)4 * plane + u);
+            }
         }
     }
-    const unsigned int row0 = (unsigned)(g.row_off[l] + a * plane + cell);
-    auto cls = [&](int c, float (&out)[V]) {
-        const float *pc = base + (size_t)(5 + c) * plane;
-        if constexpr (V == 4) {
-            const float4 t = ldg_stream_f4(pc);
-            out[0] = sigmoidf_ref(t.x); out[1] = sigmoidf_ref(t.y); out[2] = sigmoidf_ref(t.z); out[3] = sigmoidf_ref(t.w);
-        } else {
-            out[0] = sigmoidf_ref(ldg_stream_f1(pc));
+    __syncthreads();
+    // ---- phase 1: objectness test + ordered compaction into the shared list ----------------------
+#pragma unroll
+    for (int j = 0; j < kFilterUnroll; ++j) {
+        float obj[V];
+        unsigned int pass = 0;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            obj[k] = objraw[j][k] >= obj_logit_lo ? sigmoidf_ref(objraw[j][k]) : 0.f;    // yolo.py:266
+            pass |= obj[k] > f.conf_thres ? (1u << k) : 0u;                              // general.py:668
         }
-    };
-    filter_emit<V>(f, b, row0, g.no - 5, obj, valid, cls);
+        if (!__any_sync(0xffffffffu, pass != 0)) continue;
+        const int mine = __popc(pass);
+        int incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += up;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned int base = 0;
+        if (lane == 31) base = atomicAdd(&list_n, (unsigned)total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        unsigned int slot = base + incl - mine;
+        const unsigned int cell = (unsigned)(u0 + j * kFilterThreads) * V;
+#pragma unroll
+        for (int k = 0; k < V; ++k)
+            if ((pass >> k) & 1u) {
+                list_cell[slot] = cell + k;
+                list_obj[slot] = obj[k];
+                ++slot;
+            }
+    }
+    __syncthreads();
+    // ---- phase 2: one surviving cell per lane -------------------------------------------------------
+    const int n = (int)list_n;
+    for (int i0 = 0; i0 < n; i0 += kFilterThreads) {
+        const int i = i0 + threadIdx.x;
+        const bool valid = i < n;
+        const unsigned int cell = valid ? list_cell[i] : 0u;
+        const float obj = valid ? list_obj[i] : 0.f;
+        ClsFromPlanes cls{pbase + (size_t)5 * plane + cell, (size_t)plane};
+        filter_emit(f, b, prow0 + cell, g.no - 5, obj, valid, cls);
+    }
 }
 
 // ---- from a decoded prediction (bs, A, no): lane = one row ---------------------------------------
+struct ClsFromRow {
+    const float *r;
+    __device__ __forceinline__ float load(int c) const { return __ldg(r + 5 + c); }
+    __device__ __forceinline__ float prob(float raw) const { return raw; }
+};
+
 __global__ void __launch_bounds__(256) filter_z_kernel(const float *__restrict__ z, long long A, int no, const FilterOut f) {
     const int b = blockIdx.y;
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = row < A;
     const float *r = z + ((size_t)b * A + (valid ? row : 0)) * no;
-    float obj[1] = {valid ? __ldg(r + 4) : 0.f};
-    auto cls = [&](int c, float (&out)[1]) { out[0] = __ldg(r + 5 + c); };
-    filter_emit<1>(f, b, (unsigned)row, no - 5, obj, valid, cls);
+    const float obj = valid ? __ldg(r + 4) : 0.f;
+    filter_emit(f, b, (unsigned)row, no - 5, obj, valid, ClsFromRow{r});
 }
 
 static int make_filter_out(FilterOut &f, float conf_thres, int multi_label, int nc, const uint64_t *class_mask,
@@ -286,15 +338,24 @@ extern "C" __attribute__((visibility("default"))) int dsn_filter_levels(const fl
     bool vec = true;
     for (int l = 0; l < nl; ++l) vec = vec && (g.plane[l] % 4 == 0) && (((uintptr_t)raw[l] & 15) == 0);
     const int V = vec ? 4 : 1;
-    int units = 0;
+    int ctas = 0;
     for (int l = 0; l < nl; ++l) {
-        g.unit_off[l] = units;
-        units += na * (g.plane[l] / V);
+        g.cta_off[l] = ctas;
+        g.ctas_per_plane[l] = (g.plane[l] / V + kFilterThreads * kFilterUnroll - 1) / (kFilterThreads * kFilterUnroll);
+        ctas += na * g.ctas_per_plane[l];
     }
-    g.unit_off[nl] = units;
-    dim3 grid((units + 255) / 256, bs);
-    if (vec) filter_levels_kernel<4><<<grid, 256, 0, st>>>(g, f);
-    else filter_levels_kernel<1><<<grid, 256, 0, st>>>(g, f);
+    g.cta_off[nl] = ctas;
+    // sigmoid(x) > conf_thres is impossible below this logit (0.1 % relative + 1e-3 absolute margin,
+    // orders of magnitude above the fp32 error of the device sigmoid)
+    float lo = -INFINITY;
+    if (conf_thres > 0.f) {
+        const double c = (double)conf_thres * (1.0 - 1e-3);
+        lo = c >= 1.0 ? INFINITY : (float)(std::log(c / (1.0 - c)) - 1e-3);
+        if (std::isfinite(lo)) lo = std::nextafterf(lo, -INFINITY);
+    }
+    dim3 grid(ctas, bs);
+    if (vec) filter_levels_kernel<4><<<grid, kFilterThreads, 0, st>>>(g, f, lo);
+    else filter_levels_kernel<1><<<grid, kFilterThreads, 0, st>>>(g, f, lo);
     DSN_CHECK_LAUNCH();
     return DSN_OK;
 }

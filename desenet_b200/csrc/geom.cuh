@@ -8,7 +8,8 @@ struct HeadGeom {
     const float *raw[DSN_MAX_LEVELS];   // (bs, na*no, ny, nx) per level
     int ny[DSN_MAX_LEVELS], nx[DSN_MAX_LEVELS], plane[DSN_MAX_LEVELS];
     int row_off[DSN_MAX_LEVELS + 1];    // first row of the level inside z (per image); [nl] = A
-    int unit_off[DSN_MAX_LEVELS + 1];   // filter kernel: first work unit of the level
+    int cta_off[DSN_MAX_LEVELS + 1];    // filter kernel: first CTA of the level (per image)
+    int ctas_per_plane[DSN_MAX_LEVELS]; // filter kernel: CTAs covering one (level, anchor) plane
     int tile_off[DSN_MAX_LEVELS + 1];   // decode kernel: first tile of the level
     float stride[DSN_MAX_LEVELS];
     float anchor_w[DSN_MAX_LEVELS][DSN_MAX_ANCHORS], anchor_h[DSN_MAX_LEVELS][DSN_MAX_ANCHORS];

@@ -24,7 +24,7 @@ struct SegParams {
     float my, mx;      // nearest scales float(H)/float(mask_h), float(W)/float(mask_w)
 };
 
-constexpr int kTileRows = 8;        // output rows per CTA in the fast path
+constexpr int kTileRows = 16;       // output rows per CTA in the fast path
 constexpr int kMaxPackedC = 4;      // template instantiations of the fast path
 
 // ---- packed confusion-matrix counters ------------------------------------------------------
@@ -62,26 +62,56 @@ __device__ __forceinline__ int clamp_target_row(long long t, int rows) {
     return v > rows - 1 ? rows - 1 : v;
 }
 
-// ---- fast path: scale >= 8, W % 4 == 0, mask (if any) at full resolution, C in 2..4 -------------
-// One CTA = 8 output rows x full width of one image; one thread = a 4-pixel column group.
-// 8 output rows touch at most 2 distinct source rows y0 (8*sy < 1) and 4 pixels at most 2 distinct
-// source columns, so a thread needs a 3x3 clamped source patch per class.
-template <int C, bool HAS_TGT, bool HAS_MASK>
+// ---- fast path: upsampling by >= 4 in x and >= 1 in y, W % 4 == 0, mask (if any) at full resolution,
+//      C in 2..4 ------------------------------------------------------------------------------------
+// One CTA = kTileRows output rows x full width of one image; one thread = a 4-pixel column group
+// that walks down the rows.  The thread keeps the HORIZONTALLY interpolated values of the two
+// source rows it is between (T = row y0, B = row y0+1) in registers; when y0 advances (every ~8
+// output rows) T <- B and B is rebuilt from three raw source values per class that were prefetched
+// one source row ahead.  Per output pixel that leaves one FMUL + one FFMA per class, the compare
+// and the store — the kernel has to stay below ~10 issue slots per pixel to remain HBM-bound.
+struct RowCoef {
+    float l0, l1;
+    int y0;
+};
+
+template <int C>
+struct SrcCols {
+    float v[C][3];
+};
+
+template <int C>
+__device__ __forceinline__ SrcCols<C> load_src_row(const float *img, int plane, int row_off, int c0, int c1, int c2) {
+    SrcCols<C> r;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const float *pl = img + (size_t)c * plane + row_off;
+        r.v[c][0] = __ldg(pl + c0);
+        r.v[c][1] = __ldg(pl + c1);
+        r.v[c][2] = __ldg(pl + c2);
+    }
+    return r;
+}
+
+// MASK: bit 0 = write mask_f32, bit 1 = write mask_u8
+template <int C, bool HAS_TGT, int MASK>
 __global__ void __launch_bounds__(512) seg_fused_tile_kernel(const SegParams p) {
     __shared__ unsigned int cm_smem[DSN_MAX_CM_ROWS * kMaxPackedC];
+    __shared__ RowCoef rows[kTileRows];
     const int b = blockIdx.y;
     const int Y0 = blockIdx.x * kTileRows;
     const int G = p.W >> 2;
-    if (HAS_TGT) {
-        if (threadIdx.x < DSN_MAX_CM_ROWS * kMaxPackedC) cm_smem[threadIdx.x] = 0u;
-        __syncthreads();
+    const int plane = p.h * p.w;
+    if (HAS_TGT && threadIdx.x < DSN_MAX_CM_ROWS * kMaxPackedC) cm_smem[threadIdx.x] = 0u;
+    if (threadIdx.x < kTileRows) {
+        const Lerp ly = lerp_coeff(p.sy, min(Y0 + (int)threadIdx.x, p.H - 1), p.h);
+        rows[threadIdx.x].l0 = ly.l0;
+        rows[threadIdx.x].l1 = ly.l1;
+        rows[threadIdx.x].y0 = ly.i0;
     }
-    const float *img = p.logits + (size_t)b * C * p.h * p.w;
-    const Lerp ly_first = lerp_coeff(p.sy, Y0, p.h);
-    const int ya = ly_first.i0;
-    const int r0 = ya * p.w;
-    const int r1 = min(ya + 1, p.h - 1) * p.w;
-    const int r2 = min(ya + 2, p.h - 1) * p.w;
+    __syncthreads();
+    const float *img = p.logits + (size_t)b * C * plane;
+    const int nrows = min(kTileRows, p.H - Y0);
     unsigned long long acc[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[c] = 0ull;
@@ -90,47 +120,70 @@ __global__ void __launch_bounds__(512) seg_fused_tile_kernel(const SegParams p) 
         const int g = g0 + threadIdx.x;
         if (g < G) {
             const int X = g << 2;
-            Lerp lx[4];
+            float l0[4], l1[4];
+            bool shx[4];
+            int xa;
+            {
+                const Lerp lx0 = lerp_coeff(p.sx, X, p.w);
+                xa = lx0.i0;
+                l0[0] = lx0.l0; l1[0] = lx0.l1; shx[0] = false;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) lx[k] = lerp_coeff(p.sx, X + k, p.w);
-            const int xa = lx[0].i0;
-            const int c0 = xa, c1 = min(xa + 1, p.w - 1), c2 = min(xa + 2, p.w - 1);
-            // horizontal lerps of the three candidate source rows            (yolo.py:183)
-            float hz[C][3][4];
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const float *pl = img + (size_t)c * p.h * p.w;
-                float v[3][3];
-                v[0][0] = __ldg(pl + r0 + c0); v[0][1] = __ldg(pl + r0 + c1); v[0][2] = __ldg(pl + r0 + c2);
-                v[1][0] = __ldg(pl + r1 + c0); v[1][1] = __ldg(pl + r1 + c1); v[1][2] = __ldg(pl + r1 + c2);
-                v[2][0] = __ldg(pl + r2 + c0); v[2][1] = __ldg(pl + r2 + c1); v[2][2] = __ldg(pl + r2 + c2);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const bool sh = lx[k].i0 != xa;   // source column advanced by one
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-                        const float a = sh ? v[r][1] : v[r][0];
-                        const float bb = sh ? v[r][2] : v[r][1];
-                        hz[c][r][k] = __fmaf_rn(lx[k].l0, a, __fmul_rn(lx[k].l1, bb));
-                    }
+                for (int k = 1; k < 4; ++k) {
+                    const Lerp lx = lerp_coeff(p.sx, X + k, p.w);
+                    l0[k] = lx.l0; l1[k] = lx.l1; shx[k] = lx.i0 != xa;     // source column advanced by one
                 }
             }
+            const int c0 = xa, c1 = min(xa + 1, p.w - 1), c2 = min(xa + 2, p.w - 1);
+            // horizontal lerp of one source row                                   (yolo.py:183)
+            auto hrow = [&](const SrcCols<C> &s, float (&out)[C][4]) {
 #pragma unroll
-            for (int dy = 0; dy < kTileRows; ++dy) {
-                const int Y = Y0 + dy;
-                if (Y < p.H) {
-                    const Lerp ly = lerp_coeff(p.sy, Y, p.h);
-                    const bool sh = ly.i0 != ya;       // uniform across the CTA
-                    int pred[4];
+                for (int c = 0; c < C; ++c)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float a = shx[k] ? s.v[c][1] : s.v[c][0];
+                        const float bb = shx[k] ? s.v[c][2] : s.v[c][1];
+                        out[c][k] = __fmaf_rn(l0[k], a, __fmul_rn(l1[k], bb));
+                    }
+            };
+            int ycur = rows[0].y0;
+            float T[C][4], B[C][4];
+            bool finite = true;
+            {
+                const SrcCols<C> s0 = load_src_row<C>(img, plane, ycur * p.w, c0, c1, c2);
+                const SrcCols<C> s1 = load_src_row<C>(img, plane, min(ycur + 1, p.h - 1) * p.w, c0, c1, c2);
+                hrow(s0, T);
+                hrow(s1, B);
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) finite = finite && (fabsf(T[c][k]) < INFINITY) && (fabsf(B[c][k]) < INFINITY);
+            }
+            SrcCols<C> nxt = load_src_row<C>(img, plane, min(ycur + 2, p.h - 1) * p.w, c0, c1, c2);   // prefetched
+            const size_t pix0 = ((size_t)b * p.H + Y0) * p.W + X;
+            float *m32 = (MASK & 1) ? p.mask_f32 + pix0 : nullptr;
+            uint8_t *m8 = (MASK & 2) ? p.mask_u8 + pix0 : nullptr;
+            const long long *tp = HAS_TGT ? p.target + pix0 : nullptr;
+            // one output row from the row pair (top, bot); T and B swap roles instead of moving
+            auto row_body = [&](const RowCoef &rc, const float (&top)[C][4], const float (&bot)[C][4], const long long (&tv)[4]) {
+                int pred[4];
+                float predf[4];
+                if (C == 2 && finite) {
+                    // no NaN can appear: plain compare, first maximum wins
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float v0 = __fmaf_rn(rc.l0, top[0][k], __fmul_rn(rc.l1, bot[0][k]));
+                        const float v1 = __fmaf_rn(rc.l0, top[C - 1][k], __fmul_rn(rc.l1, bot[C - 1][k]));
+                        pred[k] = v1 > v0 ? 1 : 0;
+                        predf[k] = v1 > v0 ? 1.0f : 0.0f;
+                    }
+                } else {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         float best = 0.f;
                         int bi = 0;
 #pragma unroll
                         for (int c = 0; c < C; ++c) {
-                            const float t = sh ? hz[c][1][k] : hz[c][0][k];
-                            const float bt = sh ? hz[c][2][k] : hz[c][1][k];
-                            const float val = __fmaf_rn(ly.l0, t, __fmul_rn(ly.l1, bt));
+                            const float val = __fmaf_rn(rc.l0, top[c][k], __fmul_rn(rc.l1, bot[c][k]));
                             if (c == 0) {
                                 best = val;
                             } else if (argmax_better(val, best)) {
@@ -139,30 +192,63 @@ __global__ void __launch_bounds__(512) seg_fused_tile_kernel(const SegParams p) 
                             }
                         }
                         pred[k] = bi;
+                        predf[k] = (float)bi;
                     }
-                    const size_t pix = ((size_t)b * p.H + Y) * p.W + X;
-                    if (HAS_MASK) {
-                        if (p.mask_f32)
-                            stg_stream_f4(p.mask_f32 + pix, make_float4((float)pred[0], (float)pred[1], (float)pred[2], (float)pred[3]));
-                        if (p.mask_u8)
-                            *reinterpret_cast<uint32_t *>(p.mask_u8 + pix) =
-                                (uint32_t)pred[0] | ((uint32_t)pred[1] << 8) | ((uint32_t)pred[2] << 16) | ((uint32_t)pred[3] << 24);
+                }
+                if (MASK & 1) {
+                    stg_stream_f4(m32, make_float4(predf[0], predf[1], predf[2], predf[3]));
+                    m32 += p.W;
+                }
+                if (MASK & 2) {
+                    *reinterpret_cast<uint32_t *>(m8) =
+                        (uint32_t)pred[0] | ((uint32_t)pred[1] << 8) | ((uint32_t)pred[2] << 16) | ((uint32_t)pred[3] << 24);
+                    m8 += p.W;
+                }
+                if (HAS_TGT) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const unsigned long long inc = 1ull << (8 * clamp_target_row(tv[k], p.cm_rows));
+#pragma unroll
+                        for (int c = 0; c < C; ++c) acc[c] += (pred[k] == c) ? inc : 0ull;
                     }
-                    if (HAS_TGT) {
-                        const longlong2 ta = ldg_stream_ll2(p.target + pix);
-                        const longlong2 tb = ldg_stream_ll2(p.target + pix + 2);
-                        const long long tv[4] = {ta.x, ta.y, tb.x, tb.y};
+                }
+            };
+            bool flip = false;                       // false: T is the upper source row, true: B is
+            constexpr int kGroup = 4;                // rows whose target loads are issued together
+            for (int dy0 = 0; dy0 < nrows; dy0 += kGroup) {
+                long long tv[kGroup][4];
+                if (HAS_TGT) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const unsigned long long inc = 1ull << (8 * clamp_target_row(tv[k], p.cm_rows));
-#pragma unroll
-                            for (int c = 0; c < C; ++c) acc[c] += (pred[k] == c) ? inc : 0ull;
+                    for (int r = 0; r < kGroup; ++r) {
+                        if (dy0 + r < nrows) {
+                            const longlong2 ta = ldg_stream_ll2(tp + (size_t)r * p.W);
+                            const longlong2 tb = ldg_stream_ll2(tp + (size_t)r * p.W + 2);
+                            tv[r][0] = ta.x; tv[r][1] = ta.y; tv[r][2] = tb.x; tv[r][3] = tb.y;
                         }
+                    }
+                    tp += (size_t)kGroup * p.W;
+                }
+#pragma unroll
+                for (int r = 0; r < kGroup; ++r) {
+                    const int dy = dy0 + r;
+                    if (dy < nrows) {
+                        const RowCoef rc = rows[dy];
+                        if (rc.y0 != ycur) {                 // CTA-uniform: the source row pair moved down by one
+                            ycur = rc.y0;
+                            if (!flip) hrow(nxt, T); else hrow(nxt, B);       // overwrite the row that fell out
+#pragma unroll
+                            for (int c = 0; c < C; ++c)
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) finite = finite && (fabsf(flip ? B[c][k] : T[c][k]) < INFINITY);
+                            flip = !flip;
+                            nxt = load_src_row<C>(img, plane, min(ycur + 2, p.h - 1) * p.w, c0, c1, c2);
+                        }
+                        if (!flip) row_body(rc, T, B, tv[r]); else row_body(rc, B, T, tv[r]);
                     }
                 }
             }
         }
-        if (HAS_TGT) cm_flush_warp<C>(acc, cm_smem, p.cm_rows);   // <= 32 px per thread per pass
+        if (HAS_TGT) cm_flush_warp<C>(acc, cm_smem, p.cm_rows);   // <= 4 * kTileRows px per thread per pass
     }
     if (HAS_TGT) {
         __syncthreads();
@@ -373,10 +459,20 @@ static int launch_tile(const SegParams &p, cudaStream_t st) {
     const int G = p.W / 4;
     int threads = std::min(512, (G + 31) / 32 * 32);
     dim3 grid((p.H + kTileRows - 1) / kTileRows, p.bs);
-    const bool tgt = p.target != nullptr, mask = p.mask_f32 || p.mask_u8;
-    if (tgt && mask) seg_fused_tile_kernel<C, true, true><<<grid, threads, 0, st>>>(p);
-    else if (tgt) seg_fused_tile_kernel<C, true, false><<<grid, threads, 0, st>>>(p);
-    else seg_fused_tile_kernel<C, false, true><<<grid, threads, 0, st>>>(p);
+    const bool tgt = p.target != nullptr;
+    const int mk = (p.mask_f32 ? 1 : 0) | (p.mask_u8 ? 2 : 0);
+#define DSN_SEG_LAUNCH(T, M) seg_fused_tile_kernel<C, T, M><<<grid, threads, 0, st>>>(p)
+    if (tgt) {
+        if (mk == 0) DSN_SEG_LAUNCH(true, 0);
+        else if (mk == 1) DSN_SEG_LAUNCH(true, 1);
+        else if (mk == 2) DSN_SEG_LAUNCH(true, 2);
+        else DSN_SEG_LAUNCH(true, 3);
+    } else {
+        if (mk == 1) DSN_SEG_LAUNCH(false, 1);
+        else if (mk == 2) DSN_SEG_LAUNCH(false, 2);
+        else DSN_SEG_LAUNCH(false, 3);
+    }
+#undef DSN_SEG_LAUNCH
     DSN_CHECK_LAUNCH();
     return DSN_OK;
 }
@@ -402,7 +498,7 @@ extern "C" __attribute__((visibility("default"))) int dsn_seg_fused(const float 
     p.my = has_mask ? (float)H / (float)mask_h : 1.f;
     p.mx = has_mask ? (float)W / (float)mask_w : 1.f;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool fast = C >= 2 && C <= kMaxPackedC && (W % 4 == 0) && (H - 1) >= 8 * (h - 1) && (W - 1) >= 8 * (w - 1) &&
+    const bool fast = C >= 2 && C <= kMaxPackedC && (W % 4 == 0) && H >= h && (W - 1) >= 4 * (w - 1) && h * w < (1 << 24) &&
                       (!has_mask || (mask_h == H && mask_w == W)) && (!target || cm_rows <= DSN_MAX_CM_ROWS) &&
                       (((uintptr_t)mask_f32 & 15) == 0) && (((uintptr_t)mask_u8 & 3) == 0) && (((uintptr_t)target & 15) == 0);
     if (!fast) return launch_general<false>(p, st);
