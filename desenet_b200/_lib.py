@@ -26,6 +26,9 @@ SIGNATURES = {
     "dsn_nms_levels": (c_int, [_FLOATPP, POINTER(c_int), POINTER(c_int), POINTER(c_float), POINTER(c_float), c_int, c_int,
                                c_int, c_int, c_void_p, c_int64, c_void_p, c_float, c_double, c_int, c_int, c_int, c_float,
                                c_void_p, c_void_p, c_void_p]),
+    "dsn_detect_nms_levels": (c_int, [_FLOATPP, POINTER(c_int), POINTER(c_int), POINTER(c_float), POINTER(c_float), c_int,
+                                      c_int, c_int, c_int, c_float, c_int, POINTER(c_uint64), c_double, c_int, c_int,
+                                      c_int, c_float, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dsn_nms_z": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int64, c_void_p, c_float, c_double, c_int, c_int,
                           c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "dsn_seg_fused": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
@@ -49,7 +52,15 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
+    path = os.environ.get("DSN_LIB") or _build.LIB
+    if os.environ.get("DSN_LIB"):          # tuning builds (e.g. the DSN_TIMING .so)
+        lib = ctypes.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
     try:
         path = _build.build()
     except Exception as e:  # no nvcc on this box: use the prebuilt .so that travelled with the repo

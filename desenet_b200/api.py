@@ -132,9 +132,8 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
     assert 0 <= iou_thres <= 1, f'Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0'
     has_labels = bool(labels) and any(len(l) for l in labels)
     if isinstance(prediction, HeadOutputs) and not has_labels:
-        head = prediction.head
-        keys, counts = ops.filter_levels(head, conf_thres, multi_label, classes)
-        det, det_count = ops.nms_levels(head, keys, counts, conf_thres, iou_thres, agnostic, int(max_det))
+        det, det_count, _ = ops.detect_nms_levels(prediction.head, conf_thres, iou_thres, classes, agnostic, multi_label,
+                                                  int(max_det))
     else:
         z = prediction.z if isinstance(prediction, HeadOutputs) else prediction
         if has_labels:

@@ -12,12 +12,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libdesenet_b200.so")
-SOURCES = ["api.cu", "seg.cu", "detect.cu", "nms.cu"]
-HEADERS = ["common.cuh", "geom.cuh", os.path.join("..", "..", "include", "desenet_b200.h")]
+SOURCES = ["api.cu", "seg.cu", "detect.cu", "nms.cu", "fused.cu"]
+HEADERS = ["common.cuh", "geom.cuh", "filter_core.cuh", "nms_core.cuh", os.path.join("..", "..", "include", "desenet_b200.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-cudart", "static",
 ]
+if os.environ.get("DSN_TIMING"):          # tuning build: phase timeline markers, separate .so
+    NVCC_FLAGS += ["-DDSN_TIMING", "-rdc=true"]
+    LIB = os.path.join(LIBDIR, "libdesenet_b200_timing.so")
 
 
 def _nvcc() -> str:
@@ -39,7 +42,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(HERE, "..", "build", "obj")
+    objdir = os.path.join(HERE, "..", "build", "obj_timing" if os.environ.get("DSN_TIMING") else "obj")
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
     procs = []
@@ -58,7 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose and out:
             print(out)
     tmp = LIB + ".tmp"
-    out = subprocess.run([nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
+    out = subprocess.run([nvcc, "-shared", "-cudart", "static", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
                           "-o", tmp, *objs], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if out.returncode != 0:
         raise RuntimeError(f"link failed:\n{out.stdout}")

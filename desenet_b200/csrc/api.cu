@@ -14,3 +14,10 @@ extern "C" __attribute__((visibility("default"))) const char *dsn_error_string(i
     if (code > 0) return cudaGetErrorString((cudaError_t)code);
     return "unknown desenet_b200 error code";
 }
+
+#ifdef DSN_TIMING
+namespace dsn { __device__ unsigned long long dsn_timing[64]; }
+extern "C" __attribute__((visibility("default"))) int dsn_debug_timing(unsigned long long *host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, dsn::dsn_timing, sizeof(unsigned long long) * 64);
+}
+#endif

@@ -19,6 +19,21 @@
 
 namespace dsn {
 
+// Optional phase timeline for kernel tuning (compiled in only with -DDSN_TIMING; never in the shipped .so)
+#ifdef DSN_TIMING
+extern __device__ unsigned long long dsn_timing[64];
+__device__ __forceinline__ void dsn_mark(int slot) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        dsn_timing[slot] = t;
+    }
+}
+#define DSN_MARK(slot) dsn::dsn_mark(slot)
+#else
+#define DSN_MARK(slot) ((void)0)
+#endif
+
 // Streaming 128-bit loads that do not pollute L1 (inputs are read exactly once).
 __device__ __forceinline__ float4 ldg_stream_f4(const float *p) {
     float4 r;

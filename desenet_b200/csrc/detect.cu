@@ -10,6 +10,7 @@
 #include <cmath>
 
 #include "common.cuh"
+#include "filter_core.cuh"
 #include "geom.cuh"
 
 namespace dsn {
@@ -63,107 +64,6 @@ __global__ void __launch_bounds__(256) detect_decode_kernel(const HeadGeom g, fl
     }
 }
 
-// =============================================================================================
-// Candidate filter
-// =============================================================================================
-struct FilterOut {
-    unsigned long long *keys;
-    long long cap;
-    int *counts;
-    float conf_thres;
-    int multi_label;
-    unsigned long long cmask[4];
-    int use_cmask;
-};
-
-__device__ __forceinline__ bool class_allowed(const FilterOut &f, int cls) {
-    return !f.use_cmask || ((f.cmask[(cls >> 6) & 3] >> (cls & 63)) & 1ull);
-}
-
-// Warp-aggregated slot allocation: every lane passes its emission count; returns the lane's first
-// slot inside keys[b][*].  One global atomic per warp (ballot-style compaction of survivors).
-__device__ __forceinline__ int warp_alloc(int *counter, int n_mine) {
-    const int lane = threadIdx.x & 31;
-    int incl = n_mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int up = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += up;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    int base = 0;
-    if (lane == 31 && total > 0) base = atomicAdd(counter, total);
-    base = __shfl_sync(0xffffffffu, base, 31);
-    return base + incl - n_mine;
-}
-
-constexpr int kClsChunk = 8;
-
-// One row per lane.  `Cls` provides load(c) -> raw class value of this lane's row and prob(raw) ->
-// class probability (sigmoid for raw head logits, identity for a decoded prediction).  The raw
-// values of a chunk of kClsChunk classes are all loaded before any is used, so a row costs ONE
-// memory round trip per chunk.  obj is the objectness probability; lanes whose row fails
-// `obj > conf_thres` (or !valid) skip every class load.  Must be called by all 32 lanes.
-template <class Cls>
-__device__ __forceinline__ void filter_emit(const FilterOut &f, int b, unsigned int row, int nc, float obj, bool valid,
-                                            const Cls &cls) {
-    const bool pass = valid && obj > f.conf_thres;                                       // general.py:668,687
-    if (!__any_sync(0xffffffffu, pass)) return;
-    unsigned long long *kout = f.keys + (size_t)b * f.cap;
-    int *counter = f.counts + b;
-    float best = 0.f;
-    int bcls = 0;
-    for (int c0 = 0; c0 < nc; c0 += kClsChunk) {
-        float raw[kClsChunk];
-        if (pass) {
-#pragma unroll
-            for (int ci = 0; ci < kClsChunk; ++ci) raw[ci] = (c0 + ci < nc) ? cls.load(c0 + ci) : 0.f;
-        }
-        if (!f.multi_label) {
-            // best class, first maximum wins                                   general.py:713
-            if (pass) {
-#pragma unroll
-                for (int ci = 0; ci < kClsChunk; ++ci) {
-                    const int c = c0 + ci;
-                    if (c < nc) {
-                        const float conf = __fmul_rn(cls.prob(raw[ci]), obj);                 // general.py:703
-                        if (c == 0 || argmax_better(conf, best)) { best = conf; bcls = c; }
-                    }
-                }
-            }
-        } else {
-            // every (row, class) with conf > thres                               general.py:710-711
-            float cf[kClsChunk];
-            unsigned int emit = 0;
-            if (pass) {
-#pragma unroll
-                for (int ci = 0; ci < kClsChunk; ++ci) {
-                    const int c = c0 + ci;
-                    if (c < nc) {
-                        cf[ci] = __fmul_rn(cls.prob(raw[ci]), obj);
-                        if (cf[ci] > f.conf_thres && class_allowed(f, c)) emit |= 1u << ci;
-                    }
-                }
-            }
-            if (!__any_sync(0xffffffffu, emit != 0)) continue;
-            int slot = warp_alloc(counter, __popc(emit));
-#pragma unroll
-            for (int ci = 0; ci < kClsChunk; ++ci)
-                if ((emit >> ci) & 1u) {
-                    if (slot < f.cap)
-                        kout[slot] = ((unsigned long long)conf_key(cf[ci]) << 32) | (unsigned long long)(row * (unsigned)nc + (c0 + ci));
-                    ++slot;
-                }
-        }
-    }
-    if (!f.multi_label) {
-        const bool emit = pass && best > f.conf_thres && class_allowed(f, bcls);             // general.py:714,717
-        const int slot = warp_alloc(counter, emit ? 1 : 0);
-        if (emit && slot < f.cap)
-            kout[slot] = ((unsigned long long)conf_key(best) << 32) | (unsigned long long)(row * (unsigned)nc + bcls);
-    }
-}
-
 // ---- from the raw levels -----------------------------------------------------------------------
 // One CTA = a run of kFilterCells cells of ONE (image, level, anchor) plane, so all plane geometry
 // is CTA-uniform.  Phase 1: every thread issues all of its objectness loads (16 B, coalesced,
@@ -177,13 +77,6 @@ __device__ __forceinline__ void filter_emit(const FilterOut &f, int b, unsigned 
 // every cell and phase 2 streams the class planes with coalesced 4 B loads.
 constexpr int kFilterUnroll = 4;
 constexpr int kFilterThreads = 256;
-
-struct ClsFromPlanes {
-    const float *p;        // class-0 plane of this (image, anchor), already offset to the cell
-    size_t plane;
-    __device__ __forceinline__ float load(int c) const { return ldg_stream_f1(p + (size_t)c * plane); }
-    __device__ __forceinline__ float prob(float raw) const { return sigmoidf_ref(raw); }
-};
 
 template <int V>
 __global__ void __launch_bounds__(kFilterThreads) filter_levels_kernel(const HeadGeom g, const FilterOut f, const float obj_logit_lo) {
@@ -260,7 +153,7 @@ __global__ void __launch_bounds__(kFilterThreads) filter_levels_kernel(const Hea
         const unsigned int cell = valid ? list_cell[i] : 0u;
         const float obj = valid ? list_obj[i] : 0.f;
         ClsFromPlanes cls{pbase + (size_t)5 * plane + cell, (size_t)plane};
-        filter_emit(f, b, prow0 + cell, g.no - 5, obj, valid, cls);
+        filter_emit(f, prow0 + cell, g.no - 5, obj, valid, cls, f.counts + b, KeySinkGlobal{f.keys + (size_t)b * f.cap, f.cap});
     }
 }
 
@@ -277,22 +170,7 @@ __global__ void __launch_bounds__(256) filter_z_kernel(const float *__restrict__
     const bool valid = row < A;
     const float *r = z + ((size_t)b * A + (valid ? row : 0)) * no;
     const float obj = valid ? __ldg(r + 4) : 0.f;
-    filter_emit(f, b, (unsigned)row, no - 5, obj, valid, ClsFromRow{r});
-}
-
-static int make_filter_out(FilterOut &f, float conf_thres, int multi_label, int nc, const uint64_t *class_mask,
-                           uint64_t *keys, int64_t cap, int *counts) {
-    if (!keys || !counts || cap < 1) return DSN_E_INVALID;
-    if (!(conf_thres >= 0.f && conf_thres <= 1.f)) return DSN_E_INVALID;     // general.py:671
-    if (class_mask && nc > 256) return DSN_E_UNSUPPORTED;
-    f.keys = (unsigned long long *)keys;
-    f.cap = cap;
-    f.counts = counts;
-    f.conf_thres = conf_thres;
-    f.multi_label = (multi_label && nc > 1) ? 1 : 0;                          // general.py:679
-    f.use_cmask = class_mask != nullptr;
-    for (int i = 0; i < 4; ++i) f.cmask[i] = class_mask ? class_mask[i] : ~0ull;
-    return DSN_OK;
+    filter_emit(f, (unsigned)row, no - 5, obj, valid, ClsFromRow{r}, f.counts + b, KeySinkGlobal{f.keys + (size_t)b * f.cap, f.cap});
 }
 
 }  // namespace dsn
@@ -345,14 +223,7 @@ extern "C" __attribute__((visibility("default"))) int dsn_filter_levels(const fl
         ctas += na * g.ctas_per_plane[l];
     }
     g.cta_off[nl] = ctas;
-    // sigmoid(x) > conf_thres is impossible below this logit (0.1 % relative + 1e-3 absolute margin,
-    // orders of magnitude above the fp32 error of the device sigmoid)
-    float lo = -INFINITY;
-    if (conf_thres > 0.f) {
-        const double c = (double)conf_thres * (1.0 - 1e-3);
-        lo = c >= 1.0 ? INFINITY : (float)(std::log(c / (1.0 - c)) - 1e-3);
-        if (std::isfinite(lo)) lo = std::nextafterf(lo, -INFINITY);
-    }
+    const float lo = obj_logit_lower_bound(conf_thres);
     dim3 grid(ctas, bs);
     if (vec) filter_levels_kernel<4><<<grid, kFilterThreads, 0, st>>>(g, f, lo);
     else filter_levels_kernel<1><<<grid, kFilterThreads, 0, st>>>(g, f, lo);

@@ -8,6 +8,7 @@ struct HeadGeom {
     const float *raw[DSN_MAX_LEVELS];   // (bs, na*no, ny, nx) per level
     int ny[DSN_MAX_LEVELS], nx[DSN_MAX_LEVELS], plane[DSN_MAX_LEVELS];
     int row_off[DSN_MAX_LEVELS + 1];    // first row of the level inside z (per image); [nl] = A
+    int unit_off[DSN_MAX_LEVELS + 1];   // fused kernel: first work unit (V cells) of the level
     int cta_off[DSN_MAX_LEVELS + 1];    // filter kernel: first CTA of the level (per image)
     int ctas_per_plane[DSN_MAX_LEVELS]; // filter kernel: CTAs covering one (level, anchor) plane
     int tile_off[DSN_MAX_LEVELS + 1];   // decode kernel: first tile of the level
@@ -49,6 +50,22 @@ static inline int make_geom(HeadGeom &g, const float *const *raw, const int *ny,
     g.row_off[nl] = (int)rows;
     g.A = (int)rows;
     return DSN_OK;
+}
+
+// (level, anchor, cell) of a row index inside one image, without integer division (nl, na are small).
+struct RowGeom {
+    int l, a, cell, plane;
+};
+__device__ __forceinline__ RowGeom row_geom(const HeadGeom &g, int row) {
+    RowGeom r;
+    r.l = 0;
+    while (r.l + 1 < g.nl && row >= g.row_off[r.l + 1]) ++r.l;
+    r.plane = g.plane[r.l];
+    int c = row - g.row_off[r.l];
+    r.a = 0;
+    while (c >= r.plane) { c -= r.plane; ++r.a; }
+    r.cell = c;
+    return r;
 }
 
 // Box decode of one anchor row from the raw level planes (core/models/yolo.py:266-269), every op

@@ -6,6 +6,7 @@
 // never materialised, yet every upsampled value is rounded exactly as ATen's CPU kernel rounds
 // it (horizontal lerps first, each lerp = fma(l0, a, l1*b)), so argmax ties break identically.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -24,7 +25,6 @@ struct SegParams {
     float my, mx;      // nearest scales float(H)/float(mask_h), float(W)/float(mask_w)
 };
 
-constexpr int kTileRows = 16;       // output rows per CTA in the fast path
 constexpr int kMaxPackedC = 4;      // template instantiations of the fast path
 
 // ---- packed confusion-matrix counters ------------------------------------------------------
@@ -93,117 +93,118 @@ __device__ __forceinline__ SrcCols<C> load_src_row(const float *img, int plane, 
     return r;
 }
 
-// MASK: bit 0 = write mask_f32, bit 1 = write mask_u8
+// MASK: bit 0 = write mask_f32, bit 1 = write mask_u8.
+// Persistent form: the bs*H output rows of the batch are split into gridDim.x CONTIGUOUS runs (one
+// per CTA, grid = SMs x resident CTAs), so the per-thread x set-up is paid once per CTA.  Inside a
+// run the rows are walked SEGMENT by segment: a segment = the output rows that interpolate between
+// the same two source rows (8-9 rows at scale 8), found through a small shared-memory table, so the
+// inner loop is branch-free: two LDS for the row's (l0, l1), C x 4 FMUL+FFMA, the compares, one
+// 16 B streaming store.  Between segments T/B swap roles and the stale one is rebuilt from raw
+// values prefetched one source row ahead.
 template <int C, bool HAS_TGT, int MASK>
-__global__ void __launch_bounds__(512) seg_fused_tile_kernel(const SegParams p) {
+__global__ void __launch_bounds__(512) seg_fused_rows_kernel(const SegParams p, const int rows_per_cta) {
+    extern __shared__ __align__(16) unsigned char seg_smem[];
+    float2 *lam = reinterpret_cast<float2 *>(seg_smem);                    // [H]   (l0, l1) of output row Y
+    int *y0_of = reinterpret_cast<int *>(lam + p.H);                       // [H]   source row y0 of output row Y
+    int *seg_start = y0_of + p.H;                                          // [h+1] first output row whose y0 is the index
     __shared__ unsigned int cm_smem[DSN_MAX_CM_ROWS * kMaxPackedC];
-    __shared__ RowCoef rows[kTileRows];
-    const int b = blockIdx.y;
-    const int Y0 = blockIdx.x * kTileRows;
     const int G = p.W >> 2;
     const int plane = p.h * p.w;
+    const long long total_rows = (long long)p.bs * p.H;
+    const long long r_begin = (long long)blockIdx.x * rows_per_cta;
+    const long long r_end = min(total_rows, r_begin + rows_per_cta);
     if (HAS_TGT && threadIdx.x < DSN_MAX_CM_ROWS * kMaxPackedC) cm_smem[threadIdx.x] = 0u;
-    if (threadIdx.x < kTileRows) {
-        const Lerp ly = lerp_coeff(p.sy, min(Y0 + (int)threadIdx.x, p.H - 1), p.h);
-        rows[threadIdx.x].l0 = ly.l0;
-        rows[threadIdx.x].l1 = ly.l1;
-        rows[threadIdx.x].y0 = ly.i0;
+    for (int Y = threadIdx.x; Y < p.H; Y += blockDim.x) {
+        const Lerp ly = lerp_coeff(p.sy, Y, p.h);
+        lam[Y] = make_float2(ly.l0, ly.l1);
+        y0_of[Y] = ly.i0;
     }
+    for (int y = threadIdx.x; y <= p.h; y += blockDim.x) seg_start[y] = p.H;   // sentinel for unused / last+1
     __syncthreads();
-    const float *img = p.logits + (size_t)b * C * plane;
-    const int nrows = min(kTileRows, p.H - Y0);
+    for (int Y = threadIdx.x; Y < p.H; Y += blockDim.x)
+        if (Y == 0 || y0_of[Y] != y0_of[Y - 1]) seg_start[y0_of[Y]] = Y;       // y0 is monotone, steps of <= 1 (H >= h)
+    __syncthreads();
     unsigned long long acc[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[c] = 0ull;
 
     for (int g0 = 0; g0 < G; g0 += blockDim.x) {
+        if (g0 + (int)(threadIdx.x & ~31u) >= G) break;        // whole warp beyond the row: nothing to do
         const int g = g0 + threadIdx.x;
-        if (g < G) {
-            const int X = g << 2;
-            float l0[4], l1[4];
-            bool shx[4];
-            int xa;
-            {
-                const Lerp lx0 = lerp_coeff(p.sx, X, p.w);
-                xa = lx0.i0;
-                l0[0] = lx0.l0; l1[0] = lx0.l1; shx[0] = false;
+        const bool active = g < G;
+        const int X = (active ? g : 0) << 2;
+        float l0[4], l1[4];
+        bool shx[4];
+        int xa;
+        {
+            const Lerp lx0 = lerp_coeff(p.sx, X, p.w);
+            xa = lx0.i0;
+            l0[0] = lx0.l0; l1[0] = lx0.l1; shx[0] = false;
 #pragma unroll
-                for (int k = 1; k < 4; ++k) {
-                    const Lerp lx = lerp_coeff(p.sx, X + k, p.w);
-                    l0[k] = lx.l0; l1[k] = lx.l1; shx[k] = lx.i0 != xa;     // source column advanced by one
+            for (int k = 1; k < 4; ++k) {
+                const Lerp lx = lerp_coeff(p.sx, X + k, p.w);
+                l0[k] = lx.l0; l1[k] = lx.l1; shx[k] = lx.i0 != xa;     // source column advanced by one
+            }
+        }
+        const int c0 = xa, c1 = min(xa + 1, p.w - 1), c2 = min(xa + 2, p.w - 1);
+        // horizontal lerp of one source row; returns false if a raw value is inf/NaN          (yolo.py:183)
+        auto hrow = [&](const SrcCols<C> &s, float (&out)[C][4]) -> bool {
+            bool fin = true;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                fin = fin && (fabsf(s.v[c][0]) < INFINITY) && (fabsf(s.v[c][1]) < INFINITY) && (fabsf(s.v[c][2]) < INFINITY);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float a = shx[k] ? s.v[c][1] : s.v[c][0];
+                    const float bb = shx[k] ? s.v[c][2] : s.v[c][1];
+                    out[c][k] = __fmaf_rn(l0[k], a, __fmul_rn(l1[k], bb));
                 }
             }
-            const int c0 = xa, c1 = min(xa + 1, p.w - 1), c2 = min(xa + 2, p.w - 1);
-            // horizontal lerp of one source row                                   (yolo.py:183)
-            auto hrow = [&](const SrcCols<C> &s, float (&out)[C][4]) {
+            return fin;
+        };
+        float *m32 = (MASK & 1) ? p.mask_f32 + (size_t)r_begin * p.W + X : nullptr;     // (b*H + Y)*W + X == r*W + X
+        uint8_t *m8 = (MASK & 2) ? p.mask_u8 + (size_t)r_begin * p.W + X : nullptr;
+        const long long *tp = HAS_TGT ? p.target + (size_t)r_begin * p.W + X : nullptr;
+        int since_flush = 0;
+        bool finite = true;
+
+        // one output row from the row pair (top, bot)
+        auto row_body = [&](const float2 lm, const float (&top)[C][4], const float (&bot)[C][4], const long long (&tv)[4]) {
+            int pred[4];
+            float predf[4];
+            if (C == 2 && finite) {
+                // no NaN can appear: plain compare, first maximum wins
 #pragma unroll
-                for (int c = 0; c < C; ++c)
+                for (int k = 0; k < 4; ++k) {
+                    const float v0 = __fmaf_rn(lm.x, top[0][k], __fmul_rn(lm.y, bot[0][k]));
+                    const float v1 = __fmaf_rn(lm.x, top[C - 1][k], __fmul_rn(lm.y, bot[C - 1][k]));
+                    pred[k] = v1 > v0 ? 1 : 0;
+                    predf[k] = v1 > v0 ? 1.0f : 0.0f;
+                }
+            } else {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float a = shx[k] ? s.v[c][1] : s.v[c][0];
-                        const float bb = shx[k] ? s.v[c][2] : s.v[c][1];
-                        out[c][k] = __fmaf_rn(l0[k], a, __fmul_rn(l1[k], bb));
-                    }
-            };
-            int ycur = rows[0].y0;
-            float T[C][4], B[C][4];
-            bool finite = true;
-            {
-                const SrcCols<C> s0 = load_src_row<C>(img, plane, ycur * p.w, c0, c1, c2);
-                const SrcCols<C> s1 = load_src_row<C>(img, plane, min(ycur + 1, p.h - 1) * p.w, c0, c1, c2);
-                hrow(s0, T);
-                hrow(s1, B);
+                for (int k = 0; k < 4; ++k) {
+                    float best = 0.f;
+                    int bi = 0;
 #pragma unroll
-                for (int c = 0; c < C; ++c)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) finite = finite && (fabsf(T[c][k]) < INFINITY) && (fabsf(B[c][k]) < INFINITY);
-            }
-            SrcCols<C> nxt = load_src_row<C>(img, plane, min(ycur + 2, p.h - 1) * p.w, c0, c1, c2);   // prefetched
-            const size_t pix0 = ((size_t)b * p.H + Y0) * p.W + X;
-            float *m32 = (MASK & 1) ? p.mask_f32 + pix0 : nullptr;
-            uint8_t *m8 = (MASK & 2) ? p.mask_u8 + pix0 : nullptr;
-            const long long *tp = HAS_TGT ? p.target + pix0 : nullptr;
-            // one output row from the row pair (top, bot); T and B swap roles instead of moving
-            auto row_body = [&](const RowCoef &rc, const float (&top)[C][4], const float (&bot)[C][4], const long long (&tv)[4]) {
-                int pred[4];
-                float predf[4];
-                if (C == 2 && finite) {
-                    // no NaN can appear: plain compare, first maximum wins
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float v0 = __fmaf_rn(rc.l0, top[0][k], __fmul_rn(rc.l1, bot[0][k]));
-                        const float v1 = __fmaf_rn(rc.l0, top[C - 1][k], __fmul_rn(rc.l1, bot[C - 1][k]));
-                        pred[k] = v1 > v0 ? 1 : 0;
-                        predf[k] = v1 > v0 ? 1.0f : 0.0f;
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        float best = 0.f;
-                        int bi = 0;
-#pragma unroll
-                        for (int c = 0; c < C; ++c) {
-                            const float val = __fmaf_rn(rc.l0, top[c][k], __fmul_rn(rc.l1, bot[c][k]));
-                            if (c == 0) {
-                                best = val;
-                            } else if (argmax_better(val, best)) {
-                                best = val;
-                                bi = c;
-                            }
+                    for (int c = 0; c < C; ++c) {
+                        const float val = __fmaf_rn(lm.x, top[c][k], __fmul_rn(lm.y, bot[c][k]));
+                        if (c == 0) {
+                            best = val;
+                        } else if (argmax_better(val, best)) {
+                            best = val;
+                            bi = c;
                         }
-                        pred[k] = bi;
-                        predf[k] = (float)bi;
                     }
+                    pred[k] = bi;
+                    predf[k] = (float)bi;
                 }
-                if (MASK & 1) {
-                    stg_stream_f4(m32, make_float4(predf[0], predf[1], predf[2], predf[3]));
-                    m32 += p.W;
-                }
-                if (MASK & 2) {
+            }
+            if (active) {
+                if (MASK & 1) stg_stream_f4(m32, make_float4(predf[0], predf[1], predf[2], predf[3]));
+                if (MASK & 2)
                     *reinterpret_cast<uint32_t *>(m8) =
                         (uint32_t)pred[0] | ((uint32_t)pred[1] << 8) | ((uint32_t)pred[2] << 16) | ((uint32_t)pred[3] << 24);
-                    m8 += p.W;
-                }
                 if (HAS_TGT) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -212,51 +213,93 @@ __global__ void __launch_bounds__(512) seg_fused_tile_kernel(const SegParams p) 
                         for (int c = 0; c < C; ++c) acc[c] += (pred[k] == c) ? inc : 0ull;
                     }
                 }
-            };
-            bool flip = false;                       // false: T is the upper source row, true: B is
-            constexpr int kGroup = 4;                // rows whose target loads are issued together
-            for (int dy0 = 0; dy0 < nrows; dy0 += kGroup) {
-                long long tv[kGroup][4];
+            }
+            if (MASK & 1) m32 += p.W;
+            if (MASK & 2) m8 += p.W;
+        };
+        // output rows [Y, ye) of one segment
+        auto segment = [&](int Y, const int ye, const float (&top)[C][4], const float (&bot)[C][4]) {
+            for (; Y + 4 <= ye; Y += 4) {
+                long long tv[4][4];
                 if (HAS_TGT) {
 #pragma unroll
-                    for (int r = 0; r < kGroup; ++r) {
-                        if (dy0 + r < nrows) {
-                            const longlong2 ta = ldg_stream_ll2(tp + (size_t)r * p.W);
-                            const longlong2 tb = ldg_stream_ll2(tp + (size_t)r * p.W + 2);
-                            tv[r][0] = ta.x; tv[r][1] = ta.y; tv[r][2] = tb.x; tv[r][3] = tb.y;
+                    for (int q = 0; q < 4; ++q) {
+                        tv[q][0] = tv[q][1] = tv[q][2] = tv[q][3] = 0;
+                        if (active) {
+                            const longlong2 ta = ldg_stream_ll2(tp + (size_t)q * p.W);
+                            const longlong2 tb = ldg_stream_ll2(tp + (size_t)q * p.W + 2);
+                            tv[q][0] = ta.x; tv[q][1] = ta.y; tv[q][2] = tb.x; tv[q][3] = tb.y;
                         }
                     }
-                    tp += (size_t)kGroup * p.W;
+                    tp += (size_t)4 * p.W;
                 }
 #pragma unroll
-                for (int r = 0; r < kGroup; ++r) {
-                    const int dy = dy0 + r;
-                    if (dy < nrows) {
-                        const RowCoef rc = rows[dy];
-                        if (rc.y0 != ycur) {                 // CTA-uniform: the source row pair moved down by one
-                            ycur = rc.y0;
-                            if (!flip) hrow(nxt, T); else hrow(nxt, B);       // overwrite the row that fell out
-#pragma unroll
-                            for (int c = 0; c < C; ++c)
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) finite = finite && (fabsf(flip ? B[c][k] : T[c][k]) < INFINITY);
-                            flip = !flip;
-                            nxt = load_src_row<C>(img, plane, min(ycur + 2, p.h - 1) * p.w, c0, c1, c2);
-                        }
-                        if (!flip) row_body(rc, T, B, tv[r]); else row_body(rc, B, T, tv[r]);
+                for (int q = 0; q < 4; ++q) row_body(lam[Y + q], top, bot, tv[q]);
+                if (HAS_TGT) {
+                    since_flush += 4;
+                    if (since_flush >= 60) {              // 4 px per row: an 8-bit field holds at most 255
+                        cm_flush_warp<C>(acc, cm_smem, p.cm_rows);
+                        since_flush = 0;
                     }
                 }
             }
+            for (; Y < ye; ++Y) {
+                long long tv[4] = {0, 0, 0, 0};
+                if (HAS_TGT) {
+                    if (active) {
+                        const longlong2 ta = ldg_stream_ll2(tp);
+                        const longlong2 tb = ldg_stream_ll2(tp + 2);
+                        tv[0] = ta.x; tv[1] = ta.y; tv[2] = tb.x; tv[3] = tb.y;
+                    }
+                    tp += p.W;
+                    ++since_flush;
+                }
+                row_body(lam[Y], top, bot, tv);
+            }
+        };
+
+        long long r = r_begin;
+        while (r < r_end) {
+            const int b = (int)(r / p.H);
+            int Y = (int)(r - (long long)b * p.H);
+            const int Yend = (int)min((long long)p.H, Y + (r_end - r));        // rows of image b inside this run
+            r += Yend - Y;
+            const float *img = p.logits + (size_t)b * C * plane;
+            int y0 = y0_of[Y];
+            float T[C][4], B[C][4];
+            {
+                const SrcCols<C> s0 = load_src_row<C>(img, plane, y0 * p.w, c0, c1, c2);
+                const SrcCols<C> s1 = load_src_row<C>(img, plane, min(y0 + 1, p.h - 1) * p.w, c0, c1, c2);
+                const bool f0 = hrow(s0, T);
+                const bool f1 = hrow(s1, B);
+                finite = finite && f0 && f1;
+            }
+            for (;;) {
+                // T = source row y0, B = y0+1
+                SrcCols<C> nxt = load_src_row<C>(img, plane, min(y0 + 2, p.h - 1) * p.w, c0, c1, c2);   // prefetch
+                int ye = min(seg_start[y0 + 1], Yend);
+                segment(Y, ye, T, B);
+                Y = ye;
+                if (Y >= Yend) break;
+                ++y0;
+                finite = hrow(nxt, T) && finite;          // T <- source row y0+1 (new bottom); B is the new top
+                nxt = load_src_row<C>(img, plane, min(y0 + 2, p.h - 1) * p.w, c0, c1, c2);
+                ye = min(seg_start[y0 + 1], Yend);
+                segment(Y, ye, B, T);
+                Y = ye;
+                if (Y >= Yend) break;
+                ++y0;
+                finite = hrow(nxt, B) && finite;          // back to T = top, B = bottom
+            }
         }
-        if (HAS_TGT) cm_flush_warp<C>(acc, cm_smem, p.cm_rows);   // <= 4 * kTileRows px per thread per pass
+        if (HAS_TGT) cm_flush_warp<C>(acc, cm_smem, p.cm_rows);
     }
     if (HAS_TGT) {
         __syncthreads();
         const int nb = p.cm_rows * C;
         if (threadIdx.x < nb) {
-            const unsigned int r = threadIdx.x / C, c = threadIdx.x % C;
-            const unsigned int cnt = cm_smem[r * C + c];
-            if (cnt) atomicAdd(p.cm + ((size_t)(b % p.cm_slots) * p.cm_rows + r) * C + c, (unsigned long long)cnt);
+            const unsigned int cnt = cm_smem[threadIdx.x];
+            if (cnt) atomicAdd(p.cm + (size_t)(blockIdx.x % p.cm_slots) * nb + threadIdx.x, (unsigned long long)cnt);
         }
     }
 }
@@ -454,27 +497,57 @@ static int launch_general(const SegParams &p, cudaStream_t st) {
     return DSN_OK;
 }
 
-template <int C>
-static int launch_tile(const SegParams &p, cudaStream_t st) {
-    const int G = p.W / 4;
-    int threads = std::min(512, (G + 31) / 32 * 32);
-    dim3 grid((p.H + kTileRows - 1) / kTileRows, p.bs);
-    const bool tgt = p.target != nullptr;
-    const int mk = (p.mask_f32 ? 1 : 0) | (p.mask_u8 ? 2 : 0);
-#define DSN_SEG_LAUNCH(T, M) seg_fused_tile_kernel<C, T, M><<<grid, threads, 0, st>>>(p)
-    if (tgt) {
-        if (mk == 0) DSN_SEG_LAUNCH(true, 0);
-        else if (mk == 1) DSN_SEG_LAUNCH(true, 1);
-        else if (mk == 2) DSN_SEG_LAUNCH(true, 2);
-        else DSN_SEG_LAUNCH(true, 3);
-    } else {
-        if (mk == 1) DSN_SEG_LAUNCH(false, 1);
-        else if (mk == 2) DSN_SEG_LAUNCH(false, 2);
-        else DSN_SEG_LAUNCH(false, 3);
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
     }
-#undef DSN_SEG_LAUNCH
+    return n;
+}
+
+template <int C, bool T, int M>
+static int launch_rows_one(const SegParams &p, cudaStream_t st) {
+    const int G = p.W / 4;
+    const int threads = std::min(512, (G + 31) / 32 * 32);
+    const size_t smem = (sizeof(float2) + sizeof(int)) * (size_t)p.H + sizeof(int) * (size_t)(p.h + 1);
+    static bool configured = false;           // per template instantiation
+    if (!configured) {
+        DSN_CUDA(cudaFuncSetAttribute(seg_fused_rows_kernel<C, T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        configured = true;
+    }
+    int occ = 0;
+    DSN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seg_fused_rows_kernel<C, T, M>, threads, smem));
+    if (occ < 1) occ = 1;
+    const long long total_rows = (long long)p.bs * p.H;
+    long long grid = std::min<long long>((long long)sm_count() * occ, (total_rows + 7) / 8);
+    int rows_per_cta = (int)((total_rows + grid - 1) / grid);
+    static int forced = -1;                  // experiment knob: DSN_SEG_ROWS=<rows per CTA>
+    if (forced < 0) {
+        const char *e = getenv("DSN_SEG_ROWS");
+        forced = e ? atoi(e) : 0;
+    }
+    if (forced > 0) rows_per_cta = forced;
+    grid = (total_rows + rows_per_cta - 1) / rows_per_cta;
+    seg_fused_rows_kernel<C, T, M><<<(unsigned)grid, threads, smem, st>>>(p, rows_per_cta);
     DSN_CHECK_LAUNCH();
     return DSN_OK;
+}
+
+template <int C>
+static int launch_tile(const SegParams &p, cudaStream_t st) {
+    const bool tgt = p.target != nullptr;
+    const int mk = (p.mask_f32 ? 1 : 0) | (p.mask_u8 ? 2 : 0);
+    if (tgt) {
+        if (mk == 0) return launch_rows_one<C, true, 0>(p, st);
+        if (mk == 1) return launch_rows_one<C, true, 1>(p, st);
+        if (mk == 2) return launch_rows_one<C, true, 2>(p, st);
+        return launch_rows_one<C, true, 3>(p, st);
+    }
+    if (mk == 1) return launch_rows_one<C, false, 1>(p, st);
+    if (mk == 2) return launch_rows_one<C, false, 2>(p, st);
+    return launch_rows_one<C, false, 3>(p, st);
 }
 
 }  // namespace dsn
@@ -498,7 +571,7 @@ extern "C" __attribute__((visibility("default"))) int dsn_seg_fused(const float 
     p.my = has_mask ? (float)H / (float)mask_h : 1.f;
     p.mx = has_mask ? (float)W / (float)mask_w : 1.f;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool fast = C >= 2 && C <= kMaxPackedC && (W % 4 == 0) && H >= h && (W - 1) >= 4 * (w - 1) && h * w < (1 << 24) &&
+    const bool fast = C >= 2 && C <= kMaxPackedC && (W % 4 == 0) && H >= h && H <= 4096 && (W - 1) >= 4 * (w - 1) && h * w < (1 << 24) &&
                       (!has_mask || (mask_h == H && mask_w == W)) && (!target || cm_rows <= DSN_MAX_CM_ROWS) &&
                       (((uintptr_t)mask_f32 & 15) == 0) && (((uintptr_t)mask_u8 & 3) == 0) && (((uintptr_t)target & 15) == 0);
     if (!fast) return launch_general<false>(p, st);

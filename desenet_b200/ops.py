@@ -152,6 +152,32 @@ def nms_levels(head: Head, keys: torch.Tensor, counts: torch.Tensor, conf_thres:
     return det, det_count
 
 
+def detect_nms_levels(head: Head, conf_thres: float, iou_thres: float, classes=None, agnostic: bool = False,
+                      multi_label: bool = False, max_det: int = 300, max_nms: int = MAX_NMS, max_wh: float = MAX_WH,
+                      keys: Optional[torch.Tensor] = None, counts: Optional[torch.Tensor] = None,
+                      det: Optional[torch.Tensor] = None, det_count: Optional[torch.Tensor] = None):
+    """Fused decode + filter + NMS, one launch (yolo.py:259-277 + general.py:659-750).
+    Returns ``(det (bs, max_det, 6), det_count (bs), counts (bs))``."""
+    lib = _lib.load()
+    ml = bool(multi_label) and head.nc > 1
+    with torch.cuda.device(head.device):
+        if keys is None:
+            keys = torch.empty((head.bs, max(head.A * (head.nc if ml else 1), 1)), dtype=torch.int64, device=head.device)
+        if counts is None:
+            counts = torch.empty((head.bs,), dtype=torch.int32, device=head.device)
+        if det is None:
+            det = torch.empty((head.bs, max(max_det, 0), 6), dtype=torch.float32, device=head.device)
+        if det_count is None:
+            det_count = torch.empty((head.bs,), dtype=torch.int32, device=head.device)
+        rc = lib.dsn_detect_nms_levels(head.c_raw, head.c_ny, head.c_nx, head.c_stride, head.c_anchor, head.nl, head.bs,
+                                       head.na, head.no, float(conf_thres), int(ml), class_mask(classes, head.nc),
+                                       float(iou_thres), int(bool(agnostic)), int(max_nms), int(max_det), float(max_wh),
+                                       _ptr(keys), int(keys.shape[1]), _ptr(counts), _ptr(det), _ptr(det_count),
+                                       _stream(head.device))
+    _lib.check(rc, "dsn_detect_nms_levels")
+    return det, det_count, counts
+
+
 def nms_z(z: torch.Tensor, keys: torch.Tensor, counts: torch.Tensor, conf_thres: float, iou_thres: float,
           agnostic: bool, max_det: int, max_nms: int = MAX_NMS, max_wh: float = MAX_WH):
     lib = _lib.load()

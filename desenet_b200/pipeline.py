@@ -15,7 +15,7 @@ class PostProcessor:
     def __init__(self, bs: int, size, nc: int, n_segcls: int, anchor_grid, stride, *, conf_thres=0.25,
                  iou_thres=0.45, classes=None, agnostic=False, multi_label=False, max_det=300, mode="detect",
                  nclass: Optional[int] = None, mask_dtype=torch.float32, device=None, overlap_streams=True,
-                 na: int = 3):
+                 na: int = 3, fused_det: bool = False):
         assert mode in ("detect", "eval", "det_only")
         assert 0 <= conf_thres <= 1 and 0 <= iou_thres <= 1
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -27,6 +27,7 @@ class PostProcessor:
         self.nclass = int(nclass if nclass is not None else max(n_segcls, 2))
         self.cm_rows = ops.cm_rows_for(n_segcls, self.nclass)
         self.na = na
+        self.fused_det = fused_det
         st = [float(s) for s in torch.as_tensor(stride).reshape(-1).tolist()]
         self.level_shapes = [(bs, na * (nc + 5), self.H // int(s), self.W // int(s)) for s in st]
         A = na * sum(s[2] * s[3] for s in self.level_shapes)
@@ -42,7 +43,7 @@ class PostProcessor:
             self.side = torch.cuda.Stream(device=d, priority=-1) if (overlap_streams and mode != "det_only") else None
             self.ev_in = torch.cuda.Event()
             self.ev_seg = torch.cuda.Event()
-        self.kernels_per_step = 2 + (0 if mode == "det_only" else 1)
+        self.kernels_per_step = (1 if fused_det else 2) + (0 if mode == "det_only" else 1)
         self._graphs = {}
 
     # ---- enqueue-only device path --------------------------------------------------------------
@@ -77,6 +78,10 @@ class PostProcessor:
 
     def _det(self, head):
         kw = self.kw
+        if self.fused_det:
+            ops.detect_nms_levels(head, kw["conf_thres"], kw["iou_thres"], kw["classes"], kw["agnostic"], kw["multi_label"],
+                                  kw["max_det"], keys=self.keys, counts=self.counts, det=self.det, det_count=self.det_count)
+            return
         ops.filter_levels(head, kw["conf_thres"], kw["multi_label"], kw["classes"], cap=int(self.keys.shape[1]),
                           keys=self.keys, counts=self.counts)
         ops.nms_levels(head, self.keys, self.counts, kw["conf_thres"], kw["iou_thres"], kw["agnostic"], kw["max_det"],

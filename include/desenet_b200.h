@@ -103,6 +103,16 @@ int dsn_nms_z(const float *z, int bs, int64_t A, int no,
               double iou_thres, int agnostic, int max_nms, int max_det, float max_wh,
               float *det, int *det_count, void *stream);
 
+/* Fused detection path: dsn_filter_levels + dsn_nms_levels in ONE launch, one CTA per image
+ * (objectness scan -> shared-memory row list -> class pass -> keys -> lazy NMS).  Same results as the
+ * two calls; `keys` (bs, cap) and `counts` (bs) are still written (workspace + candidate counts).
+ * Replaces yolo.py:259-277 + general.py:659-750 for callers that hold the raw head outputs. */
+int dsn_detect_nms_levels(const float *const *raw, const int *ny, const int *nx, const float *stride,
+                          const float *anchor_grid, int nl, int bs, int na, int no,
+                          float conf_thres, int multi_label, const uint64_t *class_mask,
+                          double iou_thres, int agnostic, int max_nms, int max_det, float max_wh,
+                          uint64_t *keys, int64_t cap, int *counts, float *det, int *det_count, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Segmentation tail.
  * ------------------------------------------------------------------------------------------ */

@@ -116,11 +116,18 @@ def test_nms_fused_equals_strict_and_oracle(dsn, golden, name):
     z = ho.z
     sets = NMS_PARAM_SETS if "over30k" not in name else [NMS_PARAM_SETS[1], dict(conf_thres=0.3, iou_thres=0.5, max_det=50)]
     for kw in sets:
-        fused = dsn.non_max_suppression(ho, **kw)
+        fused = dsn.non_max_suppression(ho, **kw)                      # one fused launch
         strict = dsn.non_max_suppression(z, **kw)
+        # and the two-kernel path (filter_levels -> nms_levels) gives the same rows
+        ml = bool(kw.get("multi_label", False))
+        keys, counts = dsn.ops.filter_levels(ho.head, kw["conf_thres"], ml, kw.get("classes"))
+        det, dc = dsn.ops.nms_levels(ho.head, keys, counts, kw["conf_thres"], kw["iou_thres"], kw.get("agnostic", False),
+                                     kw.get("max_det", 300))
+        two = [det[i, :int(dc[i])] for i in range(det.shape[0])]
         want = port.non_max_suppression(z.cpu(), nms_impl="c", **kw)
         assert_dets_equal(strict, [w.numpy() for w in want], f"{name} strict {kw}")
         assert_dets_equal(fused, [w.numpy() for w in want], f"{name} fused {kw}")
+        assert_dets_equal(two, [w.numpy() for w in want], f"{name} two-kernel {kw}")
 
 
 def test_nms_fused_close_to_reference_fixture(dsn, golden):
