@@ -14,7 +14,6 @@ import json
 import os
 import statistics
 import sys
-import threading
 import time
 
 import torch
@@ -34,6 +33,7 @@ CONFIGS = {
     5: dict(name="cfg5 Detect nc80 640x640 bs128/GPU conf.001 iou.6 multi_label max_det300 detection-only",
             S=640, bs=128, nc=80, C=2, conf=0.001, iou=0.6, multi_label=True, max_det=300, mode="det_only"),
 }
+FUSED_DET_DEFAULT = False    # the fused single-launch detection kernel is opt-in until it beats filter+NMS
 NBUF = 4      # rotating input sets: the working set between two uses of a buffer exceeds the 126 MB L2
 
 
@@ -61,66 +61,70 @@ def measured_peak_gbs():
 
 
 # ---------------------------------------------------------------------------------------------
-# clocks sampler (NVML) — runs DURING the timed region
+# clocks sampler: `nvidia-smi -lms` in a SEPARATE process (the recipe's clocks line) so that no NVML call
+# in this process competes with the kernel / graph launches; samples cover pre-warm + the timed region
 # ---------------------------------------------------------------------------------------------
-class ClockSampler(threading.Thread):
-    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+class ClockSampler:
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
-    def __init__(self, device_index: int, period_s: float = 0.01):
-        super().__init__(daemon=True)
-        self.period = period_s
-        self.samples = []
-        self.reasons = set()
-        self.max_mhz = None
-        self.ok = False
-        self._stop_evt = threading.Event()
+    def __init__(self, device_index: int, period_ms: int = 100):
+        import subprocess
+        import tempfile
+        self.proc = None
+        self.path = None
         try:
-            import pynvml
-            pynvml.nvmlInit()
             uuid = str(torch.cuda.get_device_properties(device_index).uuid)
             if not uuid.startswith("GPU-"):
                 uuid = "GPU-" + uuid
-            try:
-                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
-            except Exception:
-                self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
-            self.nv = pynvml
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-            self.ok = True
+            fd, self.path = tempfile.mkstemp(prefix="dsn_clocks_", suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", uuid, f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", str(period_ms), "-f", self.path],
+                                         stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         except Exception as e:  # pragma: no cover
             self.err = repr(e)
 
-    def run(self):
-        if not self.ok:
-            return
-        nv = self.nv
-        while not self._stop_evt.is_set():
-            try:
-                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
-                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                self.samples.append((time.perf_counter(), float(mhz), util))
-                for bit, name in self.REASONS.items():
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            time.sleep(self.period)
+    def start(self):
+        return self
 
     def stop(self):
-        self._stop_evt.set()
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
 
-    def summary(self, t0=None, t1=None):
-        if not self.ok or not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
-        sel = [m for (t, m, u) in self.samples if (t0 is None or t >= t0) and (t1 is None or t <= t1)]
-        if not sel:
-            sel = [m for (_, m, _) in self.samples[-5:]]
-        return {"sm_mhz": statistics.median(sel), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(sel)}
+    def summary(self, skip_first: int = 0):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0,
+               "how": "nvidia-smi -lms 100 in a separate process over pre-warm + warm-up + timed region"}
+        if not self.path or not os.path.exists(self.path):
+            return out
+        mhz, mx, reasons = [], None, set()
+        with open(self.path) as f:
+            for line in f:
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) < 8:
+                    continue
+                try:
+                    mhz.append(float(parts[1]))
+                    mx = float(parts[2])
+                except ValueError:
+                    continue
+                for name, v in zip(self.NAMES, parts[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        mhz = mhz[skip_first:] or mhz
+        if mhz:
+            out.update(sm_mhz=statistics.median(mhz), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(mhz))
+        return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -202,7 +206,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch kernels directly instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--prewarm-ms", type=float, default=300.0)
+    ap.add_argument("--prewarm-ms", type=float, default=600.0)
+    ap.add_argument("--two-kernel-det", action="store_true", help="filter + NMS as two launches instead of the fused kernel")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -243,7 +248,8 @@ def main():
 
     def make_pp():
         return PostProcessor(bs, S, nc, C, DEFAULT_ANCHORS, DEFAULT_STRIDES, conf_thres=cfg["conf"], iou_thres=cfg["iou"],
-                             multi_label=cfg["multi_label"], max_det=cfg["max_det"], mode=mode, nclass=max(C, 2), device=dev)
+                             multi_label=cfg["multi_label"], max_det=cfg["max_det"], mode=mode, nclass=max(C, 2), device=dev,
+                             fused_det=FUSED_DET_DEFAULT and not args.two_kernel_det)
 
     pp = make_pp()
     heads = [ops.Head(s["levels"], DEFAULT_ANCHORS, DEFAULT_STRIDES) for s in d_sets]
@@ -265,7 +271,7 @@ def main():
         torch.cuda.synchronize(dev)
 
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    time.sleep(0.3)      # let nvidia-smi start; its idle samples are dropped below
     # ---- untimed: clock ramp + W warm-up steps ----------------------------------------------------
     t_end = time.perf_counter() + args.prewarm_ms / 1e3
     i = 0
@@ -280,6 +286,9 @@ def main():
     # ---- timed: exactly K steps --------------------------------------------------------------------
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if eval_mode:
+        warm = pp.cm.sum(0)                 # load the reduction (and NCCL) kernels outside the timed region
+        if world > 1:
+            dist.all_reduce(warm)
         pp.cm.zero_()
         torch.cuda.synchronize(dev)
     t_wall0 = time.perf_counter()
@@ -300,7 +309,9 @@ def main():
     if world > 1:
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
     ms_max = float(ms_t.item())
-    clocks = sampler.summary(t_wall0, t_wall1)
+    time.sleep(0.12)     # make sure at least one sample lands after the timed region started
+    sampler.stop()
+    clocks = sampler.summary(skip_first=3)
 
     # sanity on the last batch's results (outside the timed region)
     n_det = pp.det_count.cpu()
@@ -335,9 +346,14 @@ def main():
     def k_seg(i):
         pp._seg(d_sets[i % NBUF]["seg"], d_sets[i % NBUF]["target"])
 
+    def k_det_fused(i):
+        ops.detect_nms_levels(heads[i % NBUF], kw["conf_thres"], kw["iou_thres"], kw["classes"], kw["agnostic"],
+                              kw["multi_label"], kw["max_det"], keys=pp.keys, counts=pp.counts, det=pp.det, det_count=pp.det_count)
+
     kern_us = {"filter": time_alone(k_filter, reps)}
     k_filter(0)
     kern_us["nms"] = time_alone(k_nms, reps)
+    kern_us["det_fused"] = time_alone(k_det_fused, reps)
     if mode != "det_only":
         kern_us["seg"] = time_alone(k_seg, reps)
 
@@ -387,7 +403,6 @@ def main():
                "d2h_bytes_per_step": hp.d2h_bytes, "steps": e_steps, "ms_per_step": 1e3 * float(e_t.item()) / e_steps,
                "note": "pinned host inputs -> H2D -> kernels -> D2H of detections+counts and mask/CM every step; "
                        "2 slots on 2 streams; wall clock incl. final synchronize"}
-    sampler.stop()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -406,6 +421,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["name"], "images_per_gpu": bs, "l2": f"rotating {NBUF} input sets (working set > 126 MB L2 between reuses)",
                        "launch": "cuda-graph replay" if use_graph else "direct launches",
+                       "det_path": "fused single launch" if pp.fused_det else "filter + NMS (2 launches)",
                        "candidates_per_image": cand_per_img, "detections_per_image": det_per_img,
                        "algorithmic_bytes_per_image": ab["total"]},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
