@@ -28,31 +28,63 @@ struct SegParams {
 constexpr int kMaxPackedC = 4;      // template instantiations of the fast path
 
 // ---- packed confusion-matrix counters ------------------------------------------------------
-// Per thread: one uint64 per predicted class, eight 8-bit fields = target rows 0..7.  A thread
-// adds at most 32..64 pixels between flushes, far below 255.  Flush: widen to 16-bit fields,
-// REDUX-add across the warp (32 lanes * 64 px < 65536), one shared-memory atomic per
-// (row, class) per warp, one global atomic per (row, class) per CTA.
-template <int C>
-__device__ __forceinline__ void cm_flush_warp(unsigned long long (&acc)[C], unsigned int *cm_smem, int rows) {
-    const int lane = threadIdx.x & 31;
+// Per thread: 8-bit fields, one per target row, packed in a 32-bit word (cm_rows <= 4, the nclass = 2
+// case) or a 64-bit word (cm_rows <= 8).  For C == 2 two words are kept — all pixels and pixels predicted
+// as class 1 (class 0 = difference, taken after the reduction); otherwise one word per class.  A thread adds
+// at most 255 pixels per field between flushes.  Flush: widen to 16-bit fields, REDUX-add across the warp
+// (32 lanes * 255 < 65536), one shared-memory atomic per (row, class) per warp; one global atomic per
+// (row, class) per CTA at the end.
+template <int C, typename W>
+struct CmAcc {
+    static constexpr int kWords = (C == 2) ? 2 : C;
+    W w[kWords];
+    __device__ __forceinline__ void clear() {
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-        const unsigned long long even = acc[c] & 0x00FF00FF00FF00FFull;         // rows 0,2,4,6
-        const unsigned long long odd = (acc[c] >> 8) & 0x00FF00FF00FF00FFull;   // rows 1,3,5,7
-        unsigned int wsum[4];
-        wsum[0] = __reduce_add_sync(0xffffffffu, (unsigned int)even);           // rows 0,2
-        wsum[1] = __reduce_add_sync(0xffffffffu, (unsigned int)(even >> 32));   // rows 4,6
-        wsum[2] = __reduce_add_sync(0xffffffffu, (unsigned int)odd);            // rows 1,3
-        wsum[3] = __reduce_add_sync(0xffffffffu, (unsigned int)(odd >> 32));    // rows 5,7
-        if (lane < rows) {
-            const int f = lane >> 1;   // field inside the even/odd word pair
-            unsigned int word = (lane & 1) ? ((f >> 1) ? wsum[3] : wsum[2]) : ((f >> 1) ? wsum[1] : wsum[0]);
-            unsigned int cnt = (word >> (16 * (f & 1))) & 0xFFFFu;
-            if (cnt) atomicAdd(&cm_smem[lane * C + c], cnt);
-        }
-        acc[c] = 0ull;
+        for (int i = 0; i < kWords; ++i) w[i] = 0;
     }
-}
+    __device__ __forceinline__ void add(int pred, int row) {
+        const W inc = (W)1 << (8 * row);
+        if (C == 2) {
+            w[0] += inc;
+            w[1] += pred ? inc : (W)0;
+        } else {
+#pragma unroll
+            for (int c = 0; c < C; ++c) w[c] += (pred == c) ? inc : (W)0;
+        }
+    }
+    __device__ __forceinline__ void flush(unsigned int *cm_smem, int rows) {
+        const int lane = threadIdx.x & 31;
+        unsigned int cnt[kWords];
+#pragma unroll
+        for (int i = 0; i < kWords; ++i) {
+            // rows 0,2 | 1,3 | 4,6 | 5,7 as 16-bit fields of four 32-bit words
+            const unsigned long long v = (unsigned long long)w[i];
+            const unsigned int e_lo = (unsigned int)v & 0x00FF00FFu, o_lo = ((unsigned int)v >> 8) & 0x00FF00FFu;
+            const unsigned int s_e_lo = __reduce_add_sync(0xffffffffu, e_lo), s_o_lo = __reduce_add_sync(0xffffffffu, o_lo);
+            unsigned int s_e_hi = 0, s_o_hi = 0;
+            if (sizeof(W) == 8) {
+                const unsigned int hi = (unsigned int)(v >> 32);
+                s_e_hi = __reduce_add_sync(0xffffffffu, hi & 0x00FF00FFu);
+                s_o_hi = __reduce_add_sync(0xffffffffu, (hi >> 8) & 0x00FF00FFu);
+            }
+            // lane r extracts row r
+            const unsigned int word = (lane & 4) ? ((lane & 1) ? s_o_hi : s_e_hi) : ((lane & 1) ? s_o_lo : s_e_lo);
+            cnt[i] = (word >> (16 * ((lane >> 1) & 1))) & 0xFFFFu;
+            w[i] = 0;
+        }
+        if (lane < rows) {
+            if (C == 2) {
+                const unsigned int ones = cnt[1], zeros = cnt[0] - cnt[1];
+                if (zeros) atomicAdd(&cm_smem[lane * C + 0], zeros);
+                if (ones) atomicAdd(&cm_smem[lane * C + 1], ones);
+            } else {
+#pragma unroll
+                for (int c = 0; c < kWords; ++c)
+                    if (cnt[c]) atomicAdd(&cm_smem[lane * C + c], cnt[c]);
+            }
+        }
+    }
+};
 
 __device__ __forceinline__ int clamp_target_row(long long t, int rows) {
     // metrics.py:359,380 wrap the int64 target to int32 (`astype('int32')`); negatives are neither
@@ -101,7 +133,7 @@ __device__ __forceinline__ SrcCols<C> load_src_row(const float *img, int plane, 
 // inner loop is branch-free: two LDS for the row's (l0, l1), C x 4 FMUL+FFMA, the compares, one
 // 16 B streaming store.  Between segments T/B swap roles and the stale one is rebuilt from raw
 // values prefetched one source row ahead.
-template <int C, bool HAS_TGT, int MASK>
+template <int C, bool HAS_TGT, int MASK, typename W>
 __global__ void __launch_bounds__(512) seg_fused_rows_kernel(const SegParams p, const int rows_per_cta) {
     extern __shared__ __align__(16) unsigned char seg_smem[];
     float2 *lam = reinterpret_cast<float2 *>(seg_smem);                    // [H]   (l0, l1) of output row Y
@@ -124,9 +156,8 @@ __global__ void __launch_bounds__(512) seg_fused_rows_kernel(const SegParams p, 
     for (int Y = threadIdx.x; Y < p.H; Y += blockDim.x)
         if (Y == 0 || y0_of[Y] != y0_of[Y - 1]) seg_start[y0_of[Y]] = Y;       // y0 is monotone, steps of <= 1 (H >= h)
     __syncthreads();
-    unsigned long long acc[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] = 0ull;
+    CmAcc<C, W> acc;
+    acc.clear();
 
     for (int g0 = 0; g0 < G; g0 += blockDim.x) {
         if (g0 + (int)(threadIdx.x & ~31u) >= G) break;        // whole warp beyond the row: nothing to do
@@ -207,17 +238,13 @@ __global__ void __launch_bounds__(512) seg_fused_rows_kernel(const SegParams p, 
                         (uint32_t)pred[0] | ((uint32_t)pred[1] << 8) | ((uint32_t)pred[2] << 16) | ((uint32_t)pred[3] << 24);
                 if (HAS_TGT) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const unsigned long long inc = 1ull << (8 * clamp_target_row(tv[k], p.cm_rows));
-#pragma unroll
-                        for (int c = 0; c < C; ++c) acc[c] += (pred[k] == c) ? inc : 0ull;
-                    }
+                    for (int k = 0; k < 4; ++k) acc.add(pred[k], clamp_target_row(tv[k], p.cm_rows));
                 }
             }
             if (MASK & 1) m32 += p.W;
             if (MASK & 2) m8 += p.W;
         };
-        // output rows [Y, ye) of one segment
+        // output rows [Y, ye) of one segment; the target loads of 4 rows are issued together (8 x 16 B in flight)
         auto segment = [&](int Y, const int ye, const float (&top)[C][4], const float (&bot)[C][4]) {
             for (; Y + 4 <= ye; Y += 4) {
                 long long tv[4][4];
@@ -238,7 +265,7 @@ __global__ void __launch_bounds__(512) seg_fused_rows_kernel(const SegParams p, 
                 if (HAS_TGT) {
                     since_flush += 4;
                     if (since_flush >= 60) {              // 4 px per row: an 8-bit field holds at most 255
-                        cm_flush_warp<C>(acc, cm_smem, p.cm_rows);
+                        acc.flush(cm_smem, p.cm_rows);
                         since_flush = 0;
                     }
                 }
@@ -292,7 +319,7 @@ __global__ void __launch_bounds__(512) seg_fused_rows_kernel(const SegParams p, 
                 finite = hrow(nxt, B) && finite;          // back to T = top, B = bottom
             }
         }
-        if (HAS_TGT) cm_flush_warp<C>(acc, cm_smem, p.cm_rows);
+        if (HAS_TGT) acc.flush(cm_smem, p.cm_rows);
     }
     if (HAS_TGT) {
         __syncthreads();
@@ -301,6 +328,232 @@ __global__ void __launch_bounds__(512) seg_fused_rows_kernel(const SegParams p, 
             const unsigned int cnt = cm_smem[threadIdx.x];
             if (cnt) atomicAdd(p.cm + (size_t)(blockIdx.x % p.cm_slots) * nb + threadIdx.x, (unsigned long long)cnt);
         }
+    }
+}
+
+// ---- eval mode with a TMA-fed target ring -------------------------------------------------------------
+// The int64 target is 8 B per pixel — 98 % of the bytes of an eval step — and a CTA's run of output rows is
+// one contiguous range of it.  Instead of per-thread loads (registers bound the bytes in flight and the kernel
+// sat at ~3.8 TB/s on long-scoreboard stalls), a dedicated PRODUCER warp streams the run through a ring of
+// shared-memory stages with TMA bulk copies (cp.async.bulk + mbarrier complete_tx); the CONSUMER warps wait on
+// a stage's "full" barrier, read their pixels' targets with LDS.128 and release the stage through its "empty"
+// barrier.  The ring keeps ~56 KB per CTA in flight with zero register cost; everything else (segment walk,
+// packed confusion-matrix counters) is as in seg_fused_rows_kernel.
+__device__ __forceinline__ uint32_t seg_smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void seg_mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(seg_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void seg_mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(seg_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void seg_mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(seg_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void seg_mbar_wait(unsigned long long *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SEG_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SEG_DONE;\n"
+        "bra SEG_WAIT;\n"
+        "SEG_DONE:\n"
+        "}\n" ::"r"(seg_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void seg_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(seg_smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(seg_smem_u32(bar))
+                 : "memory");
+}
+
+constexpr int kMaxStages = 16;
+
+template <int C, int MASK, typename W>
+__global__ void __launch_bounds__(544) seg_eval_tma_kernel(const SegParams p, const int rows_per_cta, const int stage_rows,
+                                                           const int nstage) {
+    extern __shared__ __align__(128) unsigned char seg_smem[];
+    // layout: ring | lam[H] | y0_of[H]
+    const size_t stage_bytes = (size_t)stage_rows * p.W * sizeof(long long);
+    long long *ring = reinterpret_cast<long long *>(seg_smem);
+    float2 *lam = reinterpret_cast<float2 *>(seg_smem + stage_bytes * nstage);
+    int *y0_of = reinterpret_cast<int *>(lam + p.H);
+    __shared__ unsigned int cm_smem[DSN_MAX_CM_ROWS * kMaxPackedC];
+    __shared__ __align__(8) unsigned long long full_bar[kMaxStages], empty_bar[kMaxStages];
+    const int G = p.W >> 2;
+    const int plane = p.h * p.w;
+    const int n_cons = blockDim.x - 32;                       // consumer threads (multiple of 32, >= G)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool producer = warp == (n_cons >> 5);
+    const long long total_rows = (long long)p.bs * p.H;
+    const long long r_begin = (long long)blockIdx.x * rows_per_cta;
+    const long long r_end = min(total_rows, r_begin + rows_per_cta);
+    const int run_rows = (int)(r_end - r_begin);
+    if (threadIdx.x < DSN_MAX_CM_ROWS * kMaxPackedC) cm_smem[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nstage; ++i) {
+            seg_mbar_init(&full_bar[i], 1);
+            seg_mbar_init(&empty_bar[i], n_cons >> 5);        // one arrival per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int Y = threadIdx.x; Y < p.H; Y += blockDim.x) {
+        const Lerp ly = lerp_coeff(p.sy, Y, p.h);
+        lam[Y] = make_float2(ly.l0, ly.l1);
+        y0_of[Y] = ly.i0;
+    }
+    __syncthreads();
+    const int n_stages_total = (run_rows + stage_rows - 1) / stage_rows;
+
+    if (producer) {
+        if (lane == 0) {
+            const long long *src = p.target + (size_t)r_begin * p.W;
+            int st = 0;
+            uint32_t ph = 1;                                  // parity of the PREVIOUS use of the slot
+            for (int k = 0; k < n_stages_total; ++k) {
+                if (k >= nstage) seg_mbar_wait(&empty_bar[st], ph);
+                const int rows_here = min(stage_rows, run_rows - k * stage_rows);
+                const uint32_t bytes = (uint32_t)((size_t)rows_here * p.W * sizeof(long long));
+                seg_mbar_expect_tx(&full_bar[st], bytes);
+                seg_bulk_g2s(reinterpret_cast<unsigned char *>(ring) + stage_bytes * st,
+                             src + (size_t)k * stage_rows * p.W, bytes, &full_bar[st]);
+                if (++st == nstage) { st = 0; ph ^= 1u; }
+            }
+        }
+    } else {
+        const int g = threadIdx.x;
+        const bool active = g < G;
+        const int X = (active ? g : 0) << 2;
+        float l0[4], l1[4];
+        bool shx[4];
+        int xa;
+        {
+            const Lerp lx0 = lerp_coeff(p.sx, X, p.w);
+            xa = lx0.i0;
+            l0[0] = lx0.l0; l1[0] = lx0.l1; shx[0] = false;
+#pragma unroll
+            for (int k = 1; k < 4; ++k) {
+                const Lerp lx = lerp_coeff(p.sx, X + k, p.w);
+                l0[k] = lx.l0; l1[k] = lx.l1; shx[k] = lx.i0 != xa;
+            }
+        }
+        const int c0 = xa, c1 = min(xa + 1, p.w - 1), c2 = min(xa + 2, p.w - 1);
+        auto hrow = [&](const SrcCols<C> &sc, float (&out)[C][4]) -> bool {
+            bool fin = true;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                fin = fin && (fabsf(sc.v[c][0]) < INFINITY) && (fabsf(sc.v[c][1]) < INFINITY) && (fabsf(sc.v[c][2]) < INFINITY);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float a = shx[k] ? sc.v[c][1] : sc.v[c][0];
+                    const float bb = shx[k] ? sc.v[c][2] : sc.v[c][1];
+                    out[c][k] = __fmaf_rn(l0[k], a, __fmul_rn(l1[k], bb));
+                }
+            }
+            return fin;
+        };
+        CmAcc<C, W> acc;
+        acc.clear();
+        float *m32 = (MASK & 1) ? p.mask_f32 + (size_t)r_begin * p.W + X : nullptr;
+        uint8_t *m8 = (MASK & 2) ? p.mask_u8 + (size_t)r_begin * p.W + X : nullptr;
+        bool finite = true;
+        auto row_body = [&](const float2 lm, const float (&top)[C][4], const float (&bot)[C][4], const long long *trow) {
+            int pred[4];
+            if (C == 2 && finite) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float v0 = __fmaf_rn(lm.x, top[0][k], __fmul_rn(lm.y, bot[0][k]));
+                    const float v1 = __fmaf_rn(lm.x, top[C - 1][k], __fmul_rn(lm.y, bot[C - 1][k]));
+                    pred[k] = v1 > v0 ? 1 : 0;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float best = 0.f;
+                    int bi = 0;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const float val = __fmaf_rn(lm.x, top[c][k], __fmul_rn(lm.y, bot[c][k]));
+                        if (c == 0) {
+                            best = val;
+                        } else if (argmax_better(val, best)) {
+                            best = val;
+                            bi = c;
+                        }
+                    }
+                    pred[k] = bi;
+                }
+            }
+            if (active) {
+                const longlong2 ta = *reinterpret_cast<const longlong2 *>(trow + X);
+                const longlong2 tb = *reinterpret_cast<const longlong2 *>(trow + X + 2);
+                const long long tv[4] = {ta.x, ta.y, tb.x, tb.y};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc.add(pred[k], clamp_target_row(tv[k], p.cm_rows));
+                if (MASK & 1) stg_stream_f4(m32, make_float4((float)pred[0], (float)pred[1], (float)pred[2], (float)pred[3]));
+                if (MASK & 2)
+                    *reinterpret_cast<uint32_t *>(m8) =
+                        (uint32_t)pred[0] | ((uint32_t)pred[1] << 8) | ((uint32_t)pred[2] << 16) | ((uint32_t)pred[3] << 24);
+            }
+            if (MASK & 1) m32 += p.W;
+            if (MASK & 2) m8 += p.W;
+        };
+
+        int b = (int)(r_begin / p.H);
+        int Y = (int)(r_begin - (long long)b * p.H);
+        const float *img = p.logits + (size_t)b * C * plane;
+        float T[C][4], B[C][4];
+        SrcCols<C> nxt;
+        int ycur = 0, since_flush = 0;
+        bool fresh = true, flip = false;
+        int st = 0;                                           // ring slot of the current stage
+        uint32_t phase = 0;                                   // parity of that slot's current fill
+        for (int rel0 = 0; rel0 < run_rows; rel0 += stage_rows) {
+            const int rows_here = min(stage_rows, run_rows - rel0);
+            seg_mbar_wait(&full_bar[st], phase);
+            const long long *trow = reinterpret_cast<const long long *>(reinterpret_cast<const unsigned char *>(ring) + stage_bytes * st);
+            for (int rs = 0; rs < rows_here; ++rs, trow += p.W) {
+                if (fresh) {                                  // first row of the run or of an image
+                    fresh = false;
+                    flip = false;
+                    ycur = y0_of[Y];
+                    const SrcCols<C> s0 = load_src_row<C>(img, plane, ycur * p.w, c0, c1, c2);
+                    const SrcCols<C> s1 = load_src_row<C>(img, plane, min(ycur + 1, p.h - 1) * p.w, c0, c1, c2);
+                    nxt = load_src_row<C>(img, plane, min(ycur + 2, p.h - 1) * p.w, c0, c1, c2);
+                    const bool f0 = hrow(s0, T);
+                    const bool f1 = hrow(s1, B);
+                    finite = finite && f0 && f1;
+                } else if (y0_of[Y] != ycur) {                // CTA-uniform: source row pair moved down by one
+                    ycur = y0_of[Y];
+                    const bool f2 = flip ? hrow(nxt, B) : hrow(nxt, T);
+                    finite = finite && f2;
+                    flip = !flip;
+                    nxt = load_src_row<C>(img, plane, min(ycur + 2, p.h - 1) * p.w, c0, c1, c2);
+                }
+                if (!flip) row_body(lam[Y], T, B, trow); else row_body(lam[Y], B, T, trow);
+                if (++Y == p.H) {
+                    Y = 0;
+                    img += (size_t)C * plane;
+                    fresh = true;
+                }
+            }
+            __syncwarp();                                     // done with this stage: hand it back to the producer
+            if (lane == 0) seg_mbar_arrive(&empty_bar[st]);
+            if (++st == nstage) { st = 0; phase ^= 1u; }
+            since_flush += rows_here;
+            if (since_flush >= 60) {                          // 4 px per row: an 8-bit field holds at most 255
+                acc.flush(cm_smem, p.cm_rows);
+                since_flush = 0;
+            }
+        }
+        acc.flush(cm_smem, p.cm_rows);
+    }
+    __syncthreads();
+    const int nb = p.cm_rows * C;
+    if (threadIdx.x < nb) {
+        const unsigned int cnt = cm_smem[threadIdx.x];
+        if (cnt) atomicAdd(p.cm + (size_t)(blockIdx.x % p.cm_slots) * nb + threadIdx.x, (unsigned long long)cnt);
     }
 }
 
@@ -497,6 +750,8 @@ static int launch_general(const SegParams &p, cudaStream_t st) {
     return DSN_OK;
 }
 
+static inline int G_of(const SegParams &p) { return p.W / 4; }
+
 static int sm_count() {
     static int n = 0;
     if (n == 0) {
@@ -507,18 +762,18 @@ static int sm_count() {
     return n;
 }
 
-template <int C, bool T, int M>
-static int launch_rows_one(const SegParams &p, cudaStream_t st) {
+template <int C, bool T, int M, typename W>
+static int launch_rows_w(const SegParams &p, cudaStream_t st) {
     const int G = p.W / 4;
     const int threads = std::min(512, (G + 31) / 32 * 32);
     const size_t smem = (sizeof(float2) + sizeof(int)) * (size_t)p.H + sizeof(int) * (size_t)(p.h + 1);
     static bool configured = false;           // per template instantiation
     if (!configured) {
-        DSN_CUDA(cudaFuncSetAttribute(seg_fused_rows_kernel<C, T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        DSN_CUDA(cudaFuncSetAttribute(seg_fused_rows_kernel<C, T, M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
     }
     int occ = 0;
-    DSN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seg_fused_rows_kernel<C, T, M>, threads, smem));
+    DSN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seg_fused_rows_kernel<C, T, M, W>, threads, smem));
     if (occ < 1) occ = 1;
     const long long total_rows = (long long)p.bs * p.H;
     long long grid = std::min<long long>((long long)sm_count() * occ, (total_rows + 7) / 8);
@@ -530,15 +785,62 @@ static int launch_rows_one(const SegParams &p, cudaStream_t st) {
     }
     if (forced > 0) rows_per_cta = forced;
     grid = (total_rows + rows_per_cta - 1) / rows_per_cta;
-    seg_fused_rows_kernel<C, T, M><<<(unsigned)grid, threads, smem, st>>>(p, rows_per_cta);
+    seg_fused_rows_kernel<C, T, M, W><<<(unsigned)grid, threads, smem, st>>>(p, rows_per_cta);
     DSN_CHECK_LAUNCH();
     return DSN_OK;
+}
+
+template <int C, int M, typename W>
+static int launch_eval_tma_w(const SegParams &p, cudaStream_t st) {
+    const int G = p.W / 4;
+    const int cons = (G + 31) / 32 * 32;
+    const int threads = cons + 32;
+    const int stage_rows = 2;
+    const size_t stage_bytes = (size_t)stage_rows * p.W * sizeof(long long);
+    int nstage = (int)std::min<size_t>(kMaxStages, std::max<size_t>(3, (56 * 1024) / stage_bytes));
+    const size_t smem = stage_bytes * nstage + (sizeof(float2) + sizeof(int)) * (size_t)p.H;
+    static bool configured = false;           // per template instantiation
+    if (!configured) {
+        DSN_CUDA(cudaFuncSetAttribute(seg_eval_tma_kernel<C, M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    int occ = 0;
+    DSN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seg_eval_tma_kernel<C, M, W>, threads, smem));
+    if (occ < 1) return DSN_E_UNSUPPORTED;
+    const long long total_rows = (long long)p.bs * p.H;
+    long long grid = std::min<long long>((long long)sm_count() * occ, (total_rows + 7) / 8);
+    const int rows_per_cta = (int)((total_rows + grid - 1) / grid);
+    grid = (total_rows + rows_per_cta - 1) / rows_per_cta;
+    seg_eval_tma_kernel<C, M, W><<<(unsigned)grid, threads, smem, st>>>(p, rows_per_cta, stage_rows, nstage);
+    DSN_CHECK_LAUNCH();
+    return DSN_OK;
+}
+
+template <int C, bool T, int M>
+static int launch_rows_one(const SegParams &p, cudaStream_t st) {
+    if (!T || p.cm_rows <= 4) return launch_rows_w<C, T, M, unsigned int>(p, st);
+    return launch_rows_w<C, T, M, unsigned long long>(p, st);
+}
+template <int C, int M>
+static int launch_eval_tma(const SegParams &p, cudaStream_t st) {
+    if (p.cm_rows <= 4) return launch_eval_tma_w<C, M, unsigned int>(p, st);
+    return launch_eval_tma_w<C, M, unsigned long long>(p, st);
 }
 
 template <int C>
 static int launch_tile(const SegParams &p, cudaStream_t st) {
     const bool tgt = p.target != nullptr;
     const int mk = (p.mask_f32 ? 1 : 0) | (p.mask_u8 ? 2 : 0);
+    // eval mode: the TMA-fed target ring (seg_eval_tma_kernel) is parity-green but measured no faster than the
+    // streaming-load variant on B200 (55.6 vs 55.3 us at bs 64, 640x640), so it is opt-in: DSN_SEG_TMA=1
+    static int use_tma = -1;
+    if (use_tma < 0) { const char *e = getenv("DSN_SEG_TMA"); use_tma = (e && atoi(e)) ? 1 : 0; }
+    if (tgt && use_tma && G_of(p) <= 512 && (size_t)2 * p.W * 8 * 3 <= 160 * 1024) {
+        if (mk == 0) return launch_eval_tma<C, 0>(p, st);
+        if (mk == 1) return launch_eval_tma<C, 1>(p, st);
+        if (mk == 2) return launch_eval_tma<C, 2>(p, st);
+        return launch_eval_tma<C, 3>(p, st);
+    }
     if (tgt) {
         if (mk == 0) return launch_rows_one<C, true, 0>(p, st);
         if (mk == 1) return launch_rows_one<C, true, 1>(p, st);
