@@ -22,7 +22,7 @@ from . import ops
 __all__ = [
     "HeadOutputs", "SegLogits", "detect_forward", "non_max_suppression", "segoutput_to_target",
     "batch_pix_accuracy", "batch_intersection_union", "seg_confusion_matrix", "seg_stats_from_cm",
-    "seg_validation", "xywh2xyxy",
+    "seg_validation", "xywh2xyxy", "scale_coords", "clip_coords",
 ]
 
 
@@ -146,6 +146,23 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
     if any(v < 0 for v in n):
         raise RuntimeError("desenet_b200: candidate buffer overflow (internal capacity error)")
     return [det[i, :n[i]] for i in range(len(n))]      # views of a per-call buffer: caller-owned
+
+
+# ------------------------------------------------------------------------------------------------
+# f1  scale_coords / clip_coords        core/utils/general.py:598-623
+# ------------------------------------------------------------------------------------------------
+def scale_coords(img1_shape, coords, img0_shape, ratio_pad=None):
+    """Same signature and in-place behaviour as the reference: rescale ``coords`` (n, 4) xyxy (any row-strided
+    view, e.g. ``det[:, :4]``) from ``img1_shape`` to ``img0_shape`` and clip; returns ``coords``."""
+    params = torch.tensor([ops.letterbox_params(img1_shape, img0_shape, ratio_pad)], dtype=torch.float32,
+                          device=coords.device)
+    return ops.scale_coords_(coords, params)
+
+
+def clip_coords(boxes, shape):
+    """general.py:614-623 on a CUDA tensor (n, 4), in place: clamp to the image ``shape`` (h, w)."""
+    params = torch.tensor([[0.0, 0.0, 1.0, float(shape[1]), float(shape[0])]], dtype=torch.float32, device=boxes.device)
+    ops.scale_coords_(boxes, params)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -281,3 +281,40 @@ def upsample_bilinear_ac(x: torch.Tensor, size: Tuple[int, int]) -> torch.Tensor
                                           _stream(x.device))
     _lib.check(rc, "dsn_upsample_bilinear_ac")
     return out
+
+
+def letterbox_params(img1_shape, img0_shape, ratio_pad=None):
+    """(pad_x, pad_y, gain, w0, h0) exactly as scale_coords derives them in Python (general.py:600-605)."""
+    if ratio_pad is None:
+        gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
+        pad = (img1_shape[1] - img0_shape[1] * gain) / 2, (img1_shape[0] - img0_shape[0] * gain) / 2
+    else:
+        gain = ratio_pad[0][0]
+        pad = ratio_pad[1]
+    return [float(pad[0]), float(pad[1]), float(gain), float(img0_shape[1]), float(img0_shape[0])]
+
+
+def scale_coords_(boxes: torch.Tensor, params: torch.Tensor, counts: Optional[torch.Tensor] = None, do_round: bool = False):
+    """In-place scale_coords + clip_coords (general.py:598-623) on ``boxes``: (n, >=4) rows of one image or
+    (bs, rows, >=4) with per-image ``params`` (bs, 5) fp32 on the device (see ``letterbox_params``)."""
+    lib = _lib.load()
+    if not boxes.is_cuda or boxes.dtype != torch.float32:
+        raise RuntimeError("desenet_b200: boxes must be a float32 CUDA tensor; this package has no CPU path")
+    if boxes.stride(-1) != 1:
+        raise ValueError("box rows must be contiguous in their last dimension")
+    if boxes.dim() == 2:
+        bs, rows, row_stride, image_stride = 1, int(boxes.shape[0]), int(boxes.stride(0)), 0
+    elif boxes.dim() == 3:
+        bs, rows, row_stride, image_stride = int(boxes.shape[0]), int(boxes.shape[1]), int(boxes.stride(1)), int(boxes.stride(0))
+    else:
+        raise ValueError("boxes must be (n, >=4) or (bs, rows, >=4)")
+    params = _require_cuda(params, "params").reshape(-1, 5)
+    if int(params.shape[0]) != bs:
+        raise ValueError("one (pad_x, pad_y, gain, w0, h0) row per image expected")
+    if rows == 0 or bs == 0:
+        return boxes
+    with torch.cuda.device(boxes.device):
+        rc = lib.dsn_scale_coords(_ptr(boxes), row_stride, image_stride, _ptr(counts), bs, rows, _ptr(params),
+                                  int(bool(do_round)), _stream(boxes.device))
+    _lib.check(rc, "dsn_scale_coords")
+    return boxes

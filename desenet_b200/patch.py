@@ -30,6 +30,9 @@ _FUNCS = {
     "batch_intersection_union": api.batch_intersection_union,
     "seg_validation": api.seg_validation,
 }
+# scale_coords / clip_coords are also called on CPU tensors and numpy arrays by the reference (plots, dataset
+# code), so they are patched with a dispatcher that only takes CUDA float32 tensors
+
 # modules of the reference that define or import those names
 _MODULES = ("core.utils.general", "core.utils.plots", "core.utils.metrics", "core.models.common",
             "scripts.val", "scripts.detect", "scripts.show_seg_mIoU", "scripts.train", "val", "detect")
@@ -127,6 +130,20 @@ def install(model: Optional[nn.Module] = None, fused: bool = True, modules: Opti
         for fn, repl in _FUNCS.items():
             if hasattr(mod, fn):
                 h._set(mod, fn, repl)
+    # scale_coords: CUDA float32 tensors go to the kernel, everything else (CPU tensors, numpy) to the original
+    for name in (modules or _MODULES):
+        mod = sys.modules.get(name)
+        orig = getattr(mod, "scale_coords", None) if mod is not None else None
+        if orig is None or getattr(orig, "_dsn_dispatch", False):
+            continue
+
+        def scale_coords(img1_shape, coords, img0_shape, ratio_pad=None, _orig=orig):
+            if isinstance(coords, torch.Tensor) and coords.is_cuda and coords.dtype == torch.float32:
+                return api.scale_coords(img1_shape, coords, img0_shape, ratio_pad)
+            return _orig(img1_shape, coords, img0_shape, ratio_pad)
+
+        scale_coords._dsn_dispatch = True
+        h._set(mod, "scale_coords", scale_coords)
     if model is not None:
         patched_classes = set()
         for m in model.modules():

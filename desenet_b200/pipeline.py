@@ -15,7 +15,7 @@ class PostProcessor:
     def __init__(self, bs: int, size, nc: int, n_segcls: int, anchor_grid, stride, *, conf_thres=0.25,
                  iou_thres=0.45, classes=None, agnostic=False, multi_label=False, max_det=300, mode="detect",
                  nclass: Optional[int] = None, mask_dtype=torch.float32, device=None, overlap_streams=True,
-                 na: int = 3, fused_det: bool = False):
+                 na: int = 3, fused_det: bool = False, scale_params: Optional[torch.Tensor] = None, round_boxes: bool = False):
         assert mode in ("detect", "eval", "det_only")
         assert 0 <= conf_thres <= 1 and 0 <= iou_thres <= 1
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -28,6 +28,9 @@ class PostProcessor:
         self.cm_rows = ops.cm_rows_for(n_segcls, self.nclass)
         self.na = na
         self.fused_det = fused_det
+        # optional fused scale_coords/clip_coords (+ round) of the detections, general.py:598-623 / detect.py:218
+        self.scale_params = scale_params
+        self.round_boxes = round_boxes
         st = [float(s) for s in torch.as_tensor(stride).reshape(-1).tolist()]
         self.level_shapes = [(bs, na * (nc + 5), self.H // int(s), self.W // int(s)) for s in st]
         A = na * sum(s[2] * s[3] for s in self.level_shapes)
@@ -81,11 +84,17 @@ class PostProcessor:
         if self.fused_det:
             ops.detect_nms_levels(head, kw["conf_thres"], kw["iou_thres"], kw["classes"], kw["agnostic"], kw["multi_label"],
                                   kw["max_det"], keys=self.keys, counts=self.counts, det=self.det, det_count=self.det_count)
+            self._scale()
             return
         ops.filter_levels(head, kw["conf_thres"], kw["multi_label"], kw["classes"], cap=int(self.keys.shape[1]),
                           keys=self.keys, counts=self.counts)
         ops.nms_levels(head, self.keys, self.counts, kw["conf_thres"], kw["iou_thres"], kw["agnostic"], kw["max_det"],
                        det=self.det, det_count=self.det_count)
+        self._scale()
+
+    def _scale(self):
+        if self.scale_params is not None and self.det.shape[1] > 0:
+            ops.scale_coords_(self.det, self.scale_params, self.det_count, self.round_boxes)
 
     def _seg(self, seg_low, target):
         if self.mode == "detect":

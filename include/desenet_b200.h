@@ -147,6 +147,21 @@ int dsn_seg_fullres(const float *logits, int bs, int C, int H, int W,
 int dsn_upsample_bilinear_ac(const float *in, int64_t planes, int h, int w, int H, int W,
                              float *out, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Next row of the scope table: the step every caller runs right after
+ * non_max_suppression.
+ * ------------------------------------------------------------------------------------------ */
+
+/* scale_coords + clip_coords (core/utils/general.py:598-623), in place: box rows [x1,y1,x2,y2,...] are
+ * mapped from the letterboxed network input back to the original image, (x - pad) / gain in fp32, and
+ * clamped to [0, w0] x [0, h0]; do_round != 0 additionally rounds half-to-even (scripts/detect.py:218).
+ *   boxes        device, image b's row i starts at boxes + b*image_stride + i*row_stride (floats)
+ *   counts       device (bs) int32 valid rows per image, or NULL = rows_per_image for every image
+ *   params       device (bs, 5) fp32: pad_x, pad_y, gain, w0, h0 — the reference computes them in Python
+ *                (general.py:600-605) and applies them as fp32 scalars */
+int dsn_scale_coords(float *boxes, int64_t row_stride, int64_t image_stride, const int *counts, int bs,
+                     int rows_per_image, const float *params, int do_round, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

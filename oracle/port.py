@@ -379,6 +379,31 @@ def seg_validation_accumulate(batches, n_segcls: int) -> Tuple[float, float]:
 
 
 # --------------------------------------------------------------------------------------------
+# f1  scale_coords / clip_coords            general.py:598-623
+# --------------------------------------------------------------------------------------------
+def scale_coords(img1_shape, coords: torch.Tensor, img0_shape, ratio_pad=None, do_round: bool = False) -> torch.Tensor:
+    """Restatement with the reference's own tensor ops (fp32 tensor - Python float, / Python float, clamp);
+    returns a new tensor.  ``do_round`` adds detect.py:218's ``.round()``."""
+    if ratio_pad is None:
+        gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
+        pad = (img1_shape[1] - img0_shape[1] * gain) / 2, (img1_shape[0] - img0_shape[0] * gain) / 2
+    else:
+        gain = ratio_pad[0][0]
+        pad = ratio_pad[1]
+    c = coords.clone()
+    c[:, 0] -= pad[0]
+    c[:, 2] -= pad[0]
+    c[:, 1] -= pad[1]
+    c[:, 3] -= pad[1]
+    c[:, :4] /= gain
+    c[:, 0].clamp_(0, img0_shape[1])
+    c[:, 1].clamp_(0, img0_shape[0])
+    c[:, 2].clamp_(0, img0_shape[1])
+    c[:, 3].clamp_(0, img0_shape[0])
+    return c.round() if do_round else c
+
+
+# --------------------------------------------------------------------------------------------
 # Synthetic inputs (SURVEY §8d): family T (throughput) — seeded, device-independent (CPU RNG)
 # --------------------------------------------------------------------------------------------
 def synth_head_outputs(bs: int, S: int, nc: int, C: int = 2, seed: int = 0, obj_mean: float = -4.0,
