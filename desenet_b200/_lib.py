@@ -36,6 +36,9 @@ SIGNATURES = {
     "dsn_seg_fullres": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                 c_void_p, c_int, c_int, c_void_p]),
     "dsn_upsample_bilinear_ac": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dsn_box_iou": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "dsn_process_batch": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                  c_int, c_void_p, c_void_p]),
     "dsn_scale_coords": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
 }
 

@@ -22,7 +22,7 @@ from . import ops
 __all__ = [
     "HeadOutputs", "SegLogits", "detect_forward", "non_max_suppression", "segoutput_to_target",
     "batch_pix_accuracy", "batch_intersection_union", "seg_confusion_matrix", "seg_stats_from_cm",
-    "seg_validation", "xywh2xyxy", "scale_coords", "clip_coords",
+    "seg_validation", "xywh2xyxy", "scale_coords", "clip_coords", "box_iou", "process_batch",
 ]
 
 
@@ -163,6 +163,26 @@ def clip_coords(boxes, shape):
     """general.py:614-623 on a CUDA tensor (n, 4), in place: clamp to the image ``shape`` (h, w)."""
     params = torch.tensor([[0.0, 0.0, 1.0, float(shape[1]), float(shape[0])]], dtype=torch.float32, device=boxes.device)
     ops.scale_coords_(boxes, params)
+
+
+# ------------------------------------------------------------------------------------------------
+# f2  box_iou / process_batch (SURVEY.md section 8f rank 2)   general.py:626-648, scripts/val.py:101-122
+# ------------------------------------------------------------------------------------------------
+def box_iou(box1, box2):
+    """general.py:626-648: (N, M) IoU matrix, fp32, on the device."""
+    return ops.box_iou(box1, box2)
+
+
+def process_batch(detections, labels, iouv):
+    """Same signature and result as scripts/val.py:101-122: ``detections`` (N, 6) [xyxy, conf, cls], ``labels`` (M, 5)
+    [cls, xyxy] -> ``correct`` (N, len(iouv)) bool on ``iouv.device``.  Equal IoUs of one detection with two
+    labels resolve to the lowest label index (the reference's order there depends on numpy's unstable argsort)."""
+    n, m = int(detections.shape[0]), int(labels.shape[0])
+    if n == 0 or m == 0:
+        return torch.zeros(n, iouv.shape[0], dtype=torch.bool, device=iouv.device)
+    off = torch.tensor([0, m], dtype=torch.int32, device=detections.device)
+    c = ops.process_batch(detections, None, labels.float().contiguous(), off, iouv.float().contiguous(), m)
+    return c[0].bool()
 
 
 # ------------------------------------------------------------------------------------------------

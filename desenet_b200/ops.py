@@ -318,3 +318,43 @@ def scale_coords_(boxes: torch.Tensor, params: torch.Tensor, counts: Optional[to
                                   int(bool(do_round)), _stream(boxes.device))
     _lib.check(rc, "dsn_scale_coords")
     return boxes
+
+
+def box_iou(box1: torch.Tensor, box2: torch.Tensor) -> torch.Tensor:
+    """general.py:626-648: (N, M) IoU matrix of xyxy boxes (row-strided views such as ``labels[:, 1:]`` are fine)."""
+    lib = _lib.load()
+    for t, name in ((box1, "box1"), (box2, "box2")):
+        if not t.is_cuda or t.dtype != torch.float32:
+            raise RuntimeError(f"desenet_b200: {name} must be a float32 CUDA tensor; this package has no CPU path")
+        if t.dim() != 2 or t.shape[1] != 4 or (t.shape[0] > 0 and t.stride(1) != 1):
+            raise ValueError(f"{name} must be (n, 4) with contiguous rows")
+    n, m = int(box1.shape[0]), int(box2.shape[0])
+    with torch.cuda.device(box1.device):
+        out = torch.empty((n, m), dtype=torch.float32, device=box1.device)
+        rc = lib.dsn_box_iou(_ptr(box1), int(box1.stride(0)) if n else 4, n, _ptr(box2), int(box2.stride(0)) if m else 4, m,
+                             _ptr(out), _stream(box1.device))
+    _lib.check(rc, "dsn_box_iou")
+    return out
+
+
+def process_batch(det: torch.Tensor, det_count: Optional[torch.Tensor], labels: torch.Tensor, label_off: torch.Tensor,
+                  iouv: torch.Tensor, max_labels_per_image: int, correct: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """val.py:101-122 for a batch: ``det`` (bs, rows, >=6), ``labels`` (L, 5) [cls, xyxy] of all images back to back,
+    ``label_off`` (bs+1) int32.  Returns ``correct`` (bs, rows, niou) uint8."""
+    lib = _lib.load()
+    det = det if det.dim() == 3 else det.unsqueeze(0)
+    if not det.is_cuda or det.dtype != torch.float32 or det.stride(2) != 1:
+        raise RuntimeError("desenet_b200: det must be a float32 CUDA tensor with contiguous rows; there is no CPU path")
+    bs, rows = int(det.shape[0]), int(det.shape[1])
+    labels = _require_cuda(labels.reshape(-1, 5), "labels")
+    label_off = _require_cuda(label_off, "label_off", torch.int32)
+    iouv = _require_cuda(iouv, "iouv")
+    niou = int(iouv.numel())
+    with torch.cuda.device(det.device):
+        if correct is None:
+            correct = torch.zeros((bs, rows, niou), dtype=torch.uint8, device=det.device)
+        rc = lib.dsn_process_batch(_ptr(det), int(det.stride(0)), int(det.stride(1)), _ptr(det_count), bs, rows, _ptr(labels),
+                                   _ptr(label_off), int(max_labels_per_image), _ptr(iouv), niou, _ptr(correct),
+                                   _stream(det.device))
+    _lib.check(rc, "dsn_process_batch")
+    return correct

@@ -162,6 +162,24 @@ int dsn_upsample_bilinear_ac(const float *in, int64_t planes, int h, int w, int 
 int dsn_scale_coords(float *boxes, int64_t row_stride, int64_t image_stride, const int *counts, int bs,
                      int rows_per_image, const float *params, int do_round, void *stream);
 
+/* box_iou (core/utils/general.py:626-648): out (n, m) fp32 = IoU of every box1 row with every box2 row
+ * (xyxy, rows `stride` floats apart), evaluated with the reference's fp32 tensor arithmetic. */
+int dsn_box_iou(const float *box1, int64_t stride1, int n, const float *box2, int64_t stride2, int m,
+                float *out, void *stream);
+
+/* process_batch (scripts/val.py:101-122) for a whole batch, one CTA per image:
+ *   det          device, image b's detection row i at det + b*det_image_stride + i*det_row_stride: [x1,y1,x2,y2,conf,cls]
+ *   det_count    device (bs) int32 valid rows (NULL = max_rows everywhere)
+ *   labels       device (L, 5) fp32 rows [cls, x1, y1, x2, y2] of all images back to back
+ *   label_off    device (bs+1) int32: image b owns label rows [label_off[b], label_off[b+1])
+ *   iouv         device (niou) fp32 IoU thresholds (val.py:188: linspace(0.5, 0.95, 10))
+ *   correct      device (bs, max_rows, niou) uint8 (0/1); rows >= det_count[b] are left untouched
+ * Same matching as the reference (per detection its best class-matching label with IoU >= iouv[0], then per label
+ * the first such detection in detection order); equal IoUs of one detection resolve to the lowest label index. */
+int dsn_process_batch(const float *det, int64_t det_image_stride, int64_t det_row_stride, const int *det_count,
+                      int bs, int max_rows, const float *labels, const int *label_off, int max_labels_per_image,
+                      const float *iouv, int niou, unsigned char *correct, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

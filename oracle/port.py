@@ -404,6 +404,41 @@ def scale_coords(img1_shape, coords: torch.Tensor, img0_shape, ratio_pad=None, d
 
 
 # --------------------------------------------------------------------------------------------
+# f2  box_iou / process_batch     general.py:626-648, val.py:101-122
+# --------------------------------------------------------------------------------------------
+def box_iou(box1: torch.Tensor, box2: torch.Tensor) -> torch.Tensor:
+    def box_area(box):
+        return (box[2] - box[0]) * (box[3] - box[1])
+    area1 = box_area(box1.T)
+    area2 = box_area(box2.T)
+    inter = (torch.min(box1[:, None, 2:], box2[:, 2:]) - torch.max(box1[:, None, :2], box2[:, :2])).clamp(0).prod(2)
+    return inter / (area1[:, None] + area2 - inter)
+
+
+def process_batch(detections: torch.Tensor, labels: torch.Tensor, iouv: torch.Tensor) -> torch.Tensor:
+    """Canonical restatement of val.py:101-122 without the numpy sort: per detection its best class-matching
+    label with IoU >= iouv[0] (equal IoUs: lowest label index), then per label the first such detection in
+    detection order, correct[d] = iou >= iouv."""
+    n, m = detections.shape[0], labels.shape[0]
+    correct = torch.zeros(n, iouv.shape[0], dtype=torch.bool)
+    if n == 0 or m == 0:
+        return correct
+    iou = box_iou(labels[:, 1:], detections[:, :4])                     # (m, n)
+    ok = (iou >= iouv[0]) & (labels[:, 0:1] == detections[:, 5])
+    taken = set()
+    for d in range(n):
+        ls = torch.nonzero(ok[:, d]).flatten().tolist()
+        if not ls:
+            continue
+        best = max(ls, key=lambda l: (float(iou[l, d]), -l))
+        if best in taken:
+            continue
+        taken.add(best)
+        correct[d] = iou[best, d] >= iouv
+    return correct
+
+
+# --------------------------------------------------------------------------------------------
 # Synthetic inputs (SURVEY §8d): family T (throughput) — seeded, device-independent (CPU RNG)
 # --------------------------------------------------------------------------------------------
 def synth_head_outputs(bs: int, S: int, nc: int, C: int = 2, seed: int = 0, obj_mean: float = -4.0,
