@@ -19,6 +19,37 @@
 
 namespace dsn {
 
+// ---- per-device one-time kernel configuration (host) --------------------------------------------------------
+// cudaFuncSetAttribute is per device: remember, per kernel and per device, that the opt-in dynamic shared memory
+// size was raised.  A relaxed atomic bitmask per call site keeps the entry points re-entrant.
+constexpr int kMaxDevices = 64;
+struct DeviceOnce {
+    unsigned long long done = 0ull;
+    template <class F>
+    int run(F &&f) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return (int)e;
+        const unsigned long long bit = 1ull << (dev % kMaxDevices);
+        if (__atomic_load_n(&done, __ATOMIC_RELAXED) & bit) return 0;
+        const int rc = f();
+        if (rc == 0) __atomic_fetch_or(&done, bit, __ATOMIC_RELAXED);
+        return rc;
+    }
+};
+template <class Kernel>
+static inline int raise_dynamic_smem(DeviceOnce &once, Kernel kernel, int bytes) {
+    return once.run([&]() { return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); });
+}
+static inline int sm_count_current_device() {
+    static int cache[kMaxDevices] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    int &n = cache[dev % kMaxDevices];
+    if (n == 0 && (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)) n = 148;
+    return n;
+}
+
 // Optional phase timeline for kernel tuning (compiled in only with -DDSN_TIMING; never in the shipped .so)
 #ifdef DSN_TIMING
 extern __device__ unsigned long long dsn_timing[64];
@@ -30,8 +61,13 @@ __device__ __forceinline__ void dsn_mark(int slot) {
     }
 }
 #define DSN_MARK(slot) dsn::dsn_mark(slot)
+// accumulate the time since the previous DSN_LAP / DSN_LAP_START of this thread into dsn_timing[slot]
+#define DSN_LAP_START() unsigned long long dsn_lap_t = 0; if (threadIdx.x == 0 && blockIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dsn_lap_t))
+#define DSN_LAP(slot) do { if (threadIdx.x == 0 && blockIdx.x == 0) { unsigned long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); dsn::dsn_timing[slot] += t__ - dsn_lap_t; dsn_lap_t = t__; } } while (0)
 #else
 #define DSN_MARK(slot) ((void)0)
+#define DSN_LAP_START() ((void)0)
+#define DSN_LAP(slot) ((void)0)
 #endif
 
 // Streaming 128-bit loads that do not pollute L1 (inputs are read exactly once).

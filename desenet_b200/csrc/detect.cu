@@ -195,7 +195,10 @@ extern "C" __attribute__((visibility("default"))) int dsn_detect_decode(const fl
     g.tile_off[nl] = tiles;
     const size_t smem = (size_t)2 * cells * no * sizeof(float);
     if (smem > 200 * 1024) return DSN_E_UNSUPPORTED;
-    if (smem > 48 * 1024) DSN_CUDA(cudaFuncSetAttribute(detect_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) {                   // large `no` (e.g. 85): opt in to more dynamic shared memory, once per device
+        static DeviceOnce once;
+        if (int rc2 = raise_dynamic_smem(once, detect_decode_kernel, 200 * 1024)) return rc2;
+    }
     detect_decode_kernel<<<dim3(tiles, bs), 256, smem, (cudaStream_t)stream>>>(g, z, xp, cells);
     DSN_CHECK_LAUNCH();
     return DSN_OK;

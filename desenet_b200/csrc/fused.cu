@@ -45,6 +45,8 @@ struct FusedSmem {
     int ncand;
 };
 
+static_assert(sizeof(FusedSmem) <= 227 * 1024, "FusedSmem must fit the 227 KB opt-in shared memory of an sm_100a CTA");
+
 // ---- mbarrier + TMA bulk copy (cp.async.bulk: 1-D, no tensor map needed) ----------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
@@ -301,11 +303,9 @@ extern "C" __attribute__((visibility("default"))) int dsn_detect_nms_levels(
     }
     const float lo = obj_logit_lower_bound(conf_thres);
     const size_t smem = sizeof(FusedSmem);
-    static bool configured = false;
-    if (!configured) {
-        DSN_CUDA(cudaFuncSetAttribute(detect_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static DeviceOnce once;
+    rc = raise_dynamic_smem(once, detect_fused_kernel, (int)smem);
+    if (rc) return rc;
     detect_fused_kernel<<<bs, kNmsThreads, smem, st>>>(g, f, p, lo);
     DSN_CHECK_LAUNCH();
     return DSN_OK;

@@ -40,11 +40,9 @@ template <class BoxSrc>
 static int launch_nms(const NmsParams &p, const BoxSrc &src, int bs, cudaStream_t st) {
     if (bs == 0) return DSN_OK;
     const size_t smem = sizeof(NmsSmem);
-    static bool configured = false;   // per template instantiation
-    if (!configured) {
-        DSN_CUDA(cudaFuncSetAttribute(nms_kernel<BoxSrc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static DeviceOnce once;           // per template instantiation
+    const int rc = raise_dynamic_smem(once, nms_kernel<BoxSrc>, (int)smem);
+    if (rc) return rc;
     nms_kernel<BoxSrc><<<bs, kNmsThreads, smem, st>>>(p, src);
     DSN_CHECK_LAUNCH();
     return DSN_OK;

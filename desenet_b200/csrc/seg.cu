@@ -752,26 +752,15 @@ static int launch_general(const SegParams &p, cudaStream_t st) {
 
 static inline int G_of(const SegParams &p) { return p.W / 4; }
 
-static int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;
-    }
-    return n;
-}
+static int sm_count() { return sm_count_current_device(); }
 
 template <int C, bool T, int M, typename W>
 static int launch_rows_w(const SegParams &p, cudaStream_t st) {
     const int G = p.W / 4;
     const int threads = std::min(512, (G + 31) / 32 * 32);
     const size_t smem = (sizeof(float2) + sizeof(int)) * (size_t)p.H + sizeof(int) * (size_t)(p.h + 1);
-    static bool configured = false;           // per template instantiation
-    if (!configured) {
-        DSN_CUDA(cudaFuncSetAttribute(seg_fused_rows_kernel<C, T, M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
-    }
+    static DeviceOnce once;                   // per template instantiation
+    if (int rc = raise_dynamic_smem(once, seg_fused_rows_kernel<C, T, M, W>, 200 * 1024)) return rc;
     int occ = 0;
     DSN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seg_fused_rows_kernel<C, T, M, W>, threads, smem));
     if (occ < 1) occ = 1;
@@ -799,11 +788,8 @@ static int launch_eval_tma_w(const SegParams &p, cudaStream_t st) {
     const size_t stage_bytes = (size_t)stage_rows * p.W * sizeof(long long);
     int nstage = (int)std::min<size_t>(kMaxStages, std::max<size_t>(3, (56 * 1024) / stage_bytes));
     const size_t smem = stage_bytes * nstage + (sizeof(float2) + sizeof(int)) * (size_t)p.H;
-    static bool configured = false;           // per template instantiation
-    if (!configured) {
-        DSN_CUDA(cudaFuncSetAttribute(seg_eval_tma_kernel<C, M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
-    }
+    static DeviceOnce once;                   // per template instantiation
+    if (int rc = raise_dynamic_smem(once, seg_eval_tma_kernel<C, M, W>, 200 * 1024)) return rc;
     int occ = 0;
     DSN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seg_eval_tma_kernel<C, M, W>, threads, smem));
     if (occ < 1) return DSN_E_UNSUPPORTED;
