@@ -208,6 +208,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--prewarm-ms", type=float, default=600.0)
     ap.add_argument("--two-kernel-det", action="store_true", help="filter + NMS as two launches instead of the fused kernel")
+    ap.add_argument("--fused-det", action="store_true", help="use the fused single-launch detection kernel")
     ap.add_argument("--in-flight", type=int, default=2, help="independent batches in flight (one CUDA stream + workspace each)")
     args = ap.parse_args()
 
@@ -250,7 +251,7 @@ def main():
     def make_pp():
         return PostProcessor(bs, S, nc, C, DEFAULT_ANCHORS, DEFAULT_STRIDES, conf_thres=cfg["conf"], iou_thres=cfg["iou"],
                              multi_label=cfg["multi_label"], max_det=cfg["max_det"], mode=mode, nclass=max(C, 2), device=dev,
-                             fused_det=FUSED_DET_DEFAULT and not args.two_kernel_det)
+                             fused_det=(FUSED_DET_DEFAULT or args.fused_det) and not args.two_kernel_det)
 
     # `in_flight` independent batches are processed concurrently, each on its own stream with its own
     # workspace (a serving loop keeps several batches in flight; the latency-bound detection chain of one

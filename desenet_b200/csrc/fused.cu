@@ -26,8 +26,8 @@
 
 namespace dsn {
 
-constexpr int kStageFloats = 25600;      // objectness logits staged per round (100 KB)
-constexpr int kListCap = 6144;           // rows in the shared list
+constexpr int kStageFloats = 16384;      // objectness logits staged per round (64 KB)
+constexpr int kListCap = kStageFloats;   // rows in the shared list: a whole stage can pass, so the list never overflows
 constexpr int kMaxPieces = 24;           // bulk copies per round
 
 struct FusedSmem {
@@ -41,7 +41,6 @@ struct FusedSmem {
     // resume point of the plane walk (thread 0 only)
     int next_l, next_a, next_c;
     unsigned int list_n;
-    unsigned int pass_total;
     int ncand;
 };
 
@@ -82,29 +81,35 @@ struct ClsFromRowPlanes {
     __device__ __forceinline__ float prob(float raw) const { return sigmoidf_ref(raw); }
 };
 
-// key -> global key buffer; while the image has few candidates also key + decoded box -> shared stash
-// (the box is decoded only for rows that actually emit a candidate)
+// key -> global key buffer; while the image has few candidates the key is also stashed in shared memory, and the
+// four box-logit sectors of an emitting row are started towards L2 so that the NMS's box decode hits there
 struct KeySinkStash {
     unsigned long long *kout;
     long long cap;
     NmsSmem *nms;
-    float bl[4];           // raw box logits of this lane's row
-    int gx, gy;
-    float stride, aw, ah, off_mul;
-    __device__ __forceinline__ void operator()(int slot, unsigned long long key, int cls) const {
+    const float *box0;     // box-logit 0 of this lane's row
+    size_t plane;
+    __device__ __forceinline__ void operator()(int slot, unsigned long long key, int /*cls*/) const {
         if (slot < cap) kout[slot] = key;
-        if (slot < kRankSortMax) {
-            nms->key[slot] = key;
-            nms->box[slot] = xywh2xyxy(decode_xy(bl[0], gx, stride), decode_xy(bl[1], gy, stride), decode_wh(bl[2], aw),
-                                       decode_wh(bl[3], ah));                    // yolo.py:268-269, general.py:706
-            nms->off[slot] = __fmul_rn((float)cls, off_mul);                     // general.py:732
-        }
+        if (slot < kRankSortMax) nms->key[slot] = key;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) asm volatile("prefetch.global.L2 [%0];" ::"l"(box0 + (size_t)o * plane));
     }
+};
+
+// raw class logits were loaded by the caller together with the objectness logit (one round trip)
+struct ClsPreloaded {
+    const float *raw;      // kClsChunk values of the first chunk, already in registers
+    const float *p;        // class-0 logit of this row (further chunks are loaded on demand)
+    size_t plane;
+    __device__ __forceinline__ float load(int c) const { return c < kClsChunk ? raw[c] : ldg_stream_f1(p + (size_t)c * plane); }
+    __device__ __forceinline__ float prob(float v) const { return sigmoidf_ref(v); }
 };
 
 // class pass over the rows listed in shared memory                         general.py:687-718
 __device__ __forceinline__ void fused_flush_list(FusedSmem &s, const HeadGeom &g, const FilterOut &f, const NmsParams &p, int b) {
     const int n = (int)s.list_n;
+    const int nc = g.no - 5;
     unsigned long long *kout = f.keys + (size_t)b * f.cap;
     for (int i0 = 0; i0 < n; i0 += kNmsThreads) {
         const int i = i0 + threadIdx.x;
@@ -113,27 +118,27 @@ __device__ __forceinline__ void fused_flush_list(FusedSmem &s, const HeadGeom &g
         const RowGeom rg = row_geom(g, (int)row);
         const int plane = rg.plane;
         const float *base = g.raw[rg.l] + ((size_t)(b * g.na + rg.a) * g.no) * plane + rg.cell;
-        const int nx = g.nx[rg.l];
-        const int gy = rg.cell / nx;
-        KeySinkStash sink{kout, f.cap, &s.nms, {0.f, 0.f, 0.f, 0.f}, rg.cell - gy * nx, gy, g.stride[rg.l],
-                          g.anchor_w[rg.l][rg.a], g.anchor_h[rg.l][rg.a], p.off_mul};
-        float ol = -INFINITY;
+        // the list only holds rows whose objectness logit cleared the conservative bound, so nearly all of them pass
+        // the exact test: load the objectness logit AND the first chunk of class logits in the same round trip
+        float ol = -INFINITY, raw[kClsChunk];
+#pragma unroll
+        for (int ci = 0; ci < kClsChunk; ++ci) raw[ci] = 0.f;
         if (valid) {
-            // objectness + box logits ride in the same round trip as the class logits filter_emit loads
             ol = ldg_stream_f1(base + (size_t)4 * plane);
 #pragma unroll
-            for (int o = 0; o < 4; ++o) sink.bl[o] = ldg_stream_f1(base + (size_t)o * plane);
+            for (int ci = 0; ci < kClsChunk; ++ci)
+                if (ci < nc) raw[ci] = ldg_stream_f1(base + (size_t)(5 + ci) * plane);
         }
         const float obj = valid ? sigmoidf_ref(ol) : 0.f;                         // yolo.py:266
-        ClsFromRowPlanes cls{base + (size_t)5 * plane, (size_t)plane};
-        filter_emit(f, row, g.no - 5, obj, valid, cls, &s.ncand, sink);
+        KeySinkStash sink{kout, f.cap, &s.nms, base, (size_t)plane};
+        ClsPreloaded cls{raw, base + (size_t)5 * plane, (size_t)plane};
+        filter_emit(f, row, nc, obj, valid, cls, &s.ncand, sink);
     }
 }
 
 // append the rows of stage floats [lo, hi) whose logit clears the bound to the shared list
-__device__ __forceinline__ void fused_scan_range(FusedSmem &s, int lo, int hi, float obj_logit_lo, bool count_only) {
+__device__ __forceinline__ void fused_scan_range(FusedSmem &s, int lo, int hi, float obj_logit_lo) {
     const int lane = threadIdx.x & 31;
-    unsigned int cnt = 0;
     for (int o0 = lo; o0 < hi; o0 += kNmsThreads * 4) {
         const int o = o0 + threadIdx.x * 4;
         unsigned int pass = 0;
@@ -141,10 +146,6 @@ __device__ __forceinline__ void fused_scan_range(FusedSmem &s, int lo, int hi, f
             const float4 v = *reinterpret_cast<const float4 *>(&s.stage[o]);
             pass = (v.x >= obj_logit_lo ? 1u : 0u) | (v.y >= obj_logit_lo ? 2u : 0u) | (v.z >= obj_logit_lo ? 4u : 0u) |
                    (v.w >= obj_logit_lo ? 8u : 0u);
-        }
-        if (count_only) {
-            cnt += __popc(pass);
-            continue;
         }
         if (!__any_sync(0xffffffffu, pass != 0)) continue;
         const int mine = __popc(pass);
@@ -168,10 +169,6 @@ __device__ __forceinline__ void fused_scan_range(FusedSmem &s, int lo, int hi, f
                 if ((pass >> k) & 1u) s.list[slot++] = row + k;
         }
     }
-    if (count_only) {
-        cnt = __reduce_add_sync(0xffffffffu, cnt);
-        if (lane == 0 && cnt) atomicAdd(&s.pass_total, cnt);
-    }
 }
 
 __global__ void __launch_bounds__(kNmsThreads) detect_fused_kernel(const HeadGeom g, const FilterOut f, const NmsParams p,
@@ -188,10 +185,10 @@ __global__ void __launch_bounds__(kNmsThreads) detect_fused_kernel(const HeadGeo
     }
     __syncthreads();
     uint32_t parity = 0;
+    DSN_LAP_START();
     for (int round = 0;; ++round) {
         // ---- 1a. one thread walks the (level, anchor) objectness planes and issues the bulk copies ----
         if (threadIdx.x == 0) {
-            s.pass_total = 0u;
             int l = s.next_l, a = s.next_a, c = s.next_c, used = 0, np = 0;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // stage was read through the generic proxy
             uint32_t bytes = 0;
@@ -227,33 +224,19 @@ __global__ void __launch_bounds__(kNmsThreads) detect_fused_kernel(const HeadGeo
         const int used = s.piece_off[np];
         mbar_wait(&s.mbar, parity);
         parity ^= 1u;
+        DSN_LAP(42);   // plan + TMA stage wait
         DSN_MARK(1 + (round < 3 ? round : 3));
-        // ---- 1b. scan from shared memory ------------------------------------------------------------------
-        fused_scan_range(s, 0, used, obj_logit_lo, true);     // how many rows would be listed?
+        // ---- 1b. scan from shared memory (the list can hold a whole stage, so one pass suffices) --------------------
+        fused_scan_range(s, 0, used, obj_logit_lo);
         __syncthreads();
-        if (s.list_n + s.pass_total <= (unsigned)kListCap) {
-            fused_scan_range(s, 0, used, obj_logit_lo, false);
-            __syncthreads();
-        } else {
-            // dense input: scan in slices that cannot overflow the list, flushing in between
-            constexpr int kSlice = kNmsThreads * 4;
-            for (int lo = 0; lo < used; lo += kSlice) {
-                if (s.list_n + kSlice > (unsigned)kListCap) {
-                    __syncthreads();
-                    fused_flush_list(s, g, f, p, b);
-                    __syncthreads();
-                    if (threadIdx.x == 0) s.list_n = 0u;
-                    __syncthreads();
-                }
-                fused_scan_range(s, lo, min(used, lo + kSlice), obj_logit_lo, false);
-                __syncthreads();
-            }
-        }
+        DSN_LAP(43);   // scan
+        // ---- 2. class pass over the rows of this stage ---------------------------------------------------------------
+        fused_flush_list(s, g, f, p, b);
+        __syncthreads();
+        DSN_LAP(44);   // class pass
+        if (threadIdx.x == 0) s.list_n = 0u;
+        // (the loop head's __syncthreads orders this reset and the stage reuse before the next round)
     }
-    DSN_MARK(5);
-    // ---- 2. class pass over what is left in the list ------------------------------------------------------
-    fused_flush_list(s, g, f, p, b);
-    __syncthreads();
     DSN_MARK(8);
     const int total = s.ncand;
     if (threadIdx.x == 0) f.counts[b] = total;
@@ -267,7 +250,7 @@ __global__ void __launch_bounds__(kNmsThreads) detect_fused_kernel(const HeadGeo
     }
     // ---- 3. NMS ------------------------------------------------------------------------------------------
     BoxFromLevels src{g};
-    nms_image(s.nms, p, src, b, p.keys + (size_t)b * p.cap, total, /*stashed=*/total <= kRankSortMax);
+    nms_image(s.nms, p, src, b, p.keys + (size_t)b * p.cap, total, /*stashed_keys=*/total <= kRankSortMax);
 }
 
 }  // namespace dsn

@@ -257,30 +257,8 @@ static __device__ void rank_sort(unsigned long long *a, int m) {
 // NMS of one image by one CTA of kNmsThreads threads (see nms.cu for the algorithm).  `keys`/`n` =
 // the image's candidate keys in global memory; results go to p.det / p.det_count.
 // ---------------------------------------------------------------------------------------------
-// rank sort of m <= kRankSortMax (key, box, off) triples that already sit (unsorted) in s.key/s.box/s.off
-static __device__ void rank_sort_stashed(NmsSmem &s, int m) {
-    int mp = 32;
-    while (mp < m) mp <<= 1;
-    int T = kNmsThreads / mp;
-    T = T > 32 ? 32 : T;
-    const int ki = threadIdx.x / T, sub = threadIdx.x - ki * T;
-    unsigned long long mine = ~0ull;
-    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
-    float of = 0.f;
-    int rank = 0;
-    if (ki < m) {
-        mine = s.key[ki];
-        if (sub == 0) { bx = s.box[ki]; of = s.off[ki]; }
-        for (int i = sub; i < m; i += T) rank += s.key[i] < mine ? 1 : 0;
-    }
-    for (int d = 1; d < T; d <<= 1) rank += __shfl_xor_sync(0xffffffffu, rank, d);
-    __syncthreads();
-    if (ki < m && sub == 0) { s.key[rank] = mine; s.box[rank] = bx; s.off[rank] = of; }
-    __syncthreads();
-}
-
-// `stashed`: the caller already placed the n <= kRankSortMax candidates (key, un-offset box, class offset),
-// unsorted, in s.key/s.box/s.off — no key gather and no box fetch are needed.
+// `stashed`: the caller already placed the n <= kRankSortMax candidate keys, unsorted, in s.key — no gather from
+// global memory is needed.
 template <class BoxSrc>
 __device__ void nms_image(NmsSmem &s, const NmsParams &p, const BoxSrc &src, int b, const unsigned long long *keys, int n,
                           bool stashed = false) {
@@ -320,22 +298,18 @@ __device__ void nms_image(NmsSmem &s, const NmsParams &p, const BoxSrc &src, int
         DSN_MARK(10);
         DSN_LAP(32);   // select
         // ---- 2. gather + sort ------------------------------------------------------------------
-        if (stashed) {                      // implies first chunk, m == n <= kRankSortMax
-            rank_sort_stashed(s, m);
-            seen += m;
-            if (m > p.max_nms - consumed) m = p.max_nms - consumed;
-            consumed += m;
-        } else {
         int mp = 32;
         while (mp < m) mp <<= 1;
-        if (threadIdx.x == 0) s.m = 0u;
-        if (m > kRankSortMax)
-            for (int i = threadIdx.x; i < mp; i += kNmsThreads) s.key[i] = ~0ull;
-        __syncthreads();
-        for_each_key(keys, n, [&](unsigned long long k) {
-            if (k >= cur && k <= chunk_hi) s.key[atomicAdd(&s.m, 1u)] = k;
-        });
-        __syncthreads();
+        if (!stashed) {                     // stashed implies first chunk, m == n <= kRankSortMax, keys in s.key
+            if (threadIdx.x == 0) s.m = 0u;
+            if (m > kRankSortMax)
+                for (int i = threadIdx.x; i < mp; i += kNmsThreads) s.key[i] = ~0ull;
+            __syncthreads();
+            for_each_key(keys, n, [&](unsigned long long k) {
+                if (k >= cur && k <= chunk_hi) s.key[atomicAdd(&s.m, 1u)] = k;
+            });
+            __syncthreads();
+        }
         DSN_MARK(11);
         DSN_LAP(33);   // gather
         if (m <= kRankSortMax) rank_sort(s.key, m);
@@ -353,7 +327,6 @@ __device__ void nms_image(NmsSmem &s, const NmsParams &p, const BoxSrc &src, int
             s.off[i] = __fmul_rn((float)(ref - row * (unsigned)p.nc), p.off_mul);      // general.py:732
         }
         __syncthreads();
-        }
         DSN_MARK(13);
         DSN_LAP(35);   // boxes
         // ---- 3b. class-aware culling ------------------------------------------------------------------

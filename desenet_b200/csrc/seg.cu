@@ -107,6 +107,17 @@ struct RowCoef {
     int y0;
 };
 
+// Vertical lerp of 4 pixels of one class with Blackwell's packed fp32x2 arithmetic (FMUL2 / FFMA2, sm_100+): two
+// correctly rounded fp32 results per instruction, bit-identical to fmaf(l0, t, l1*b) per pixel, half the issue slots.
+__device__ __forceinline__ void vlerp4(const float2 lm, const float (&t)[4], const float (&b)[4], float (&o)[4]) {
+    const float2 l0 = make_float2(lm.x, lm.x), l1 = make_float2(lm.y, lm.y);
+    const float2 m01 = __fmul2_rn(l1, make_float2(b[0], b[1]));
+    const float2 m23 = __fmul2_rn(l1, make_float2(b[2], b[3]));
+    const float2 r01 = __ffma2_rn(l0, make_float2(t[0], t[1]), m01);
+    const float2 r23 = __ffma2_rn(l0, make_float2(t[2], t[3]), m23);
+    o[0] = r01.x; o[1] = r01.y; o[2] = r23.x; o[3] = r23.y;
+}
+
 template <int C>
 struct SrcCols {
     float v[C][3];
@@ -205,21 +216,25 @@ __global__ void __launch_bounds__(512) seg_fused_rows_kernel(const SegParams p, 
             float predf[4];
             if (C == 2 && finite) {
                 // no NaN can appear: plain compare, first maximum wins
+                float v0[4], v1[4];
+                vlerp4(lm, top[0], bot[0], v0);
+                vlerp4(lm, top[C - 1], bot[C - 1], v1);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const float v0 = __fmaf_rn(lm.x, top[0][k], __fmul_rn(lm.y, bot[0][k]));
-                    const float v1 = __fmaf_rn(lm.x, top[C - 1][k], __fmul_rn(lm.y, bot[C - 1][k]));
-                    pred[k] = v1 > v0 ? 1 : 0;
-                    predf[k] = v1 > v0 ? 1.0f : 0.0f;
+                    pred[k] = v1[k] > v0[k] ? 1 : 0;
+                    predf[k] = v1[k] > v0[k] ? 1.0f : 0.0f;
                 }
             } else {
+                float vals[C][4];
+#pragma unroll
+                for (int c = 0; c < C; ++c) vlerp4(lm, top[c], bot[c], vals[c]);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     float best = 0.f;
                     int bi = 0;
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
-                        const float val = __fmaf_rn(lm.x, top[c][k], __fmul_rn(lm.y, bot[c][k]));
+                        const float val = vals[c][k];
                         if (c == 0) {
                             best = val;
                         } else if (argmax_better(val, best)) {
@@ -461,20 +476,22 @@ __global__ void __launch_bounds__(544) seg_eval_tma_kernel(const SegParams p, co
         auto row_body = [&](const float2 lm, const float (&top)[C][4], const float (&bot)[C][4], const long long *trow) {
             int pred[4];
             if (C == 2 && finite) {
+                float v0[4], v1[4];
+                vlerp4(lm, top[0], bot[0], v0);
+                vlerp4(lm, top[C - 1], bot[C - 1], v1);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float v0 = __fmaf_rn(lm.x, top[0][k], __fmul_rn(lm.y, bot[0][k]));
-                    const float v1 = __fmaf_rn(lm.x, top[C - 1][k], __fmul_rn(lm.y, bot[C - 1][k]));
-                    pred[k] = v1 > v0 ? 1 : 0;
-                }
+                for (int k = 0; k < 4; ++k) pred[k] = v1[k] > v0[k] ? 1 : 0;
             } else {
+                float vals[C][4];
+#pragma unroll
+                for (int c = 0; c < C; ++c) vlerp4(lm, top[c], bot[c], vals[c]);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     float best = 0.f;
                     int bi = 0;
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
-                        const float val = __fmaf_rn(lm.x, top[c][k], __fmul_rn(lm.y, bot[c][k]));
+                        const float val = vals[c][k];
                         if (c == 0) {
                             best = val;
                         } else if (argmax_better(val, best)) {
