@@ -145,7 +145,7 @@ __device__ __forceinline__ SrcCols<C> load_src_row(const float *img, int plane, 
 // 16 B streaming store.  Between segments T/B swap roles and the stale one is rebuilt from raw
 // values prefetched one source row ahead.
 template <int C, bool HAS_TGT, int MASK, typename W>
-__global__ void __launch_bounds__(512) seg_fused_rows_kernel(const SegParams p, const int rows_per_cta) {
+__global__ void __maxnreg__(HAS_TGT ? 96 : 128) seg_fused_rows_kernel(const SegParams p, const int rows_per_cta) {
     extern __shared__ __align__(16) unsigned char seg_smem[];
     float2 *lam = reinterpret_cast<float2 *>(seg_smem);                    // [H]   (l0, l1) of output row Y
     int *y0_of = reinterpret_cast<int *>(lam + p.H);                       // [H]   source row y0 of output row Y
