@@ -26,6 +26,7 @@ struct SegParams {
 };
 
 constexpr int kMaxPackedC = 4;      // template instantiations of the fast path
+constexpr int kPrefetchRows = 8;    // eval kernel: target rows pulled into L2 this far ahead of the register loads
 
 // ---- packed confusion-matrix counters ------------------------------------------------------
 // Per thread: 8-bit fields, one per target row, packed in a 32-bit word (cm_rows <= 4, the nclass = 2
@@ -207,6 +208,7 @@ __global__ void __maxnreg__(HAS_TGT ? 96 : 128) seg_fused_rows_kernel(const SegP
         float *m32 = (MASK & 1) ? p.mask_f32 + (size_t)r_begin * p.W + X : nullptr;     // (b*H + Y)*W + X == r*W + X
         uint8_t *m8 = (MASK & 2) ? p.mask_u8 + (size_t)r_begin * p.W + X : nullptr;
         const long long *tp = HAS_TGT ? p.target + (size_t)r_begin * p.W + X : nullptr;
+        const long long *tgt_end = HAS_TGT ? p.target + (size_t)total_rows * p.W : nullptr;
         int since_flush = 0;
         bool finite = true;
 
@@ -264,6 +266,16 @@ __global__ void __maxnreg__(HAS_TGT ? 96 : 128) seg_fused_rows_kernel(const SegP
             for (; Y + 4 <= ye; Y += 4) {
                 long long tv[4][4];
                 if (HAS_TGT) {
+                    // Registers bound the bytes a thread can have in flight (8 x 16 B here), and a dependent DRAM round
+                    // trip is ~2.5 us on this part, so the rows two groups ahead are pulled into L2 without registers:
+                    // one prefetch per 128 B line (4 lanes x 32 B), i.e. by every fourth lane.
+                    if (active && (threadIdx.x & 3) == 0) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const long long *pa = tp + (size_t)(q + kPrefetchRows) * p.W;
+                            if (pa < tgt_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+                        }
+                    }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         tv[q][0] = tv[q][1] = tv[q][2] = tv[q][3] = 0;
