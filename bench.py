@@ -313,6 +313,10 @@ def main():
         warm = sum(q.cm.sum(0) for q in pps)     # load the reduction (and NCCL) kernels outside the timed region
         if world > 1:
             dist.all_reduce(warm)
+            wd = pp.det.new_empty((world,) + tuple(pp.det.shape))
+            dist.all_gather_into_tensor(wd.view(-1, *pp.det.shape[1:]), pp.det)
+            wc = pp.det_count.new_empty((world,) + tuple(pp.det_count.shape))
+            dist.all_gather_into_tensor(wc.view(-1), pp.det_count)
         for q in pps:
             q.cm.zero_()
         torch.cuda.synchronize(dev)
@@ -327,6 +331,11 @@ def main():
         cm_total = sum(q.cm.sum(0) for q in pps)
         if world > 1:
             dist.all_reduce(cm_total)                     # int64 confusion matrix, NCCL over NVLink
+            # the other collective of the path: fixed-capacity detection buffers of the last batch to every rank
+            all_det = pp.det.new_empty((world,) + tuple(pp.det.shape))
+            all_cnt = pp.det_count.new_empty((world,) + tuple(pp.det_count.shape))
+            dist.all_gather_into_tensor(all_det.view(-1, *pp.det.shape[1:]), pp.det)
+            dist.all_gather_into_tensor(all_cnt.view(-1), pp.det_count)
     ev1.record()
     torch.cuda.synchronize(dev)
     t_wall1 = time.perf_counter()
@@ -458,6 +467,8 @@ def main():
         }
         if cm_total is not None:
             line["config"]["cm_total"] = cm_total.cpu().tolist()
+            line["config"]["collectives"] = ("int64 confusion-matrix all_reduce + detection all_gather (NCCL), once at the end of "
+                                             "the timed region" if world > 1 else "none (1 GPU)")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

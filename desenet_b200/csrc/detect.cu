@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kFilterThreads) filter_levels_kernel(const Hea
         const unsigned int cell = valid ? list_cell[i] : 0u;
         const float obj = valid ? list_obj[i] : 0.f;
         ClsFromPlanes cls{pbase + (size_t)5 * plane + cell, (size_t)plane};
-        filter_emit(f, prow0 + cell, g.no - 5, obj, valid, cls, f.counts + b, KeySinkGlobal{f.keys + (size_t)b * f.cap, f.cap});
+        filter_emit(f, prow0 + cell, g.no - 5, obj, valid, cls, f.counts + b, KeySinkGlobal(f.keys + (size_t)b * f.cap, f.cap));
     }
 }
 
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) filter_z_kernel(const float *__restrict__
     const bool valid = row < A;
     const float *r = z + ((size_t)b * A + (valid ? row : 0)) * no;
     const float obj = valid ? __ldg(r + 4) : 0.f;
-    filter_emit(f, (unsigned)row, no - 5, obj, valid, ClsFromRow{r}, f.counts + b, KeySinkGlobal{f.keys + (size_t)b * f.cap, f.cap});
+    filter_emit(f, (unsigned)row, no - 5, obj, valid, ClsFromRow{r}, f.counts + b, KeySinkGlobal(f.keys + (size_t)b * f.cap, f.cap));
 }
 
 }  // namespace dsn

@@ -53,7 +53,8 @@ constexpr int kClsChunk = 8;
 // Default emission sink: the key goes to the image's key buffer in global memory.
 struct KeySinkGlobal {
     unsigned long long *kout;
-    long long cap;
+    int cap;               // candidate capacity of the image's key buffer (fits 32 bits: A * nc < 2^32 and counts are int)
+    __device__ __forceinline__ KeySinkGlobal(unsigned long long *k, long long c) : kout(k), cap(c > 0x7fffffffLL ? 0x7fffffff : (int)c) {}
     __device__ __forceinline__ void operator()(int slot, unsigned long long key, int /*cls*/) const {
         if (slot < cap) kout[slot] = key;
     }
@@ -124,19 +125,24 @@ __device__ __forceinline__ void filter_emit(const FilterOut &f, unsigned int row
             if (pass) {
 #pragma unroll
                 for (int ci = 0; ci < kClsChunk; ++ci) {
-                    const int c = c0 + ci;
-                    if (c < nc) {
+                    if (c0 + ci < nc) {
                         cf[ci] = __fmul_rn(cls.prob(raw[ci]), obj);
-                        if (cf[ci] > f.conf_thres && class_allowed(f, c)) emit |= 1u << ci;
+                        emit |= cf[ci] > f.conf_thres ? (1u << ci) : 0u;
                     }
+                }
+                if (f.use_cmask) {                            // rare: filter the chunk's classes in one go
+#pragma unroll
+                    for (int ci = 0; ci < kClsChunk; ++ci)
+                        if (!class_allowed(f, c0 + ci)) emit &= ~(1u << ci);
                 }
             }
             if (!__any_sync(0xffffffffu, emit != 0)) continue;
             int slot = warp_alloc(counter, __popc(emit));
+            const unsigned int ref0 = row * (unsigned)nc + (unsigned)c0;
 #pragma unroll
             for (int ci = 0; ci < kClsChunk; ++ci)
                 if ((emit >> ci) & 1u) {
-                    sink(slot, ((unsigned long long)conf_key(cf[ci]) << 32) | (unsigned long long)(row * (unsigned)nc + (c0 + ci)), c0 + ci);
+                    sink(slot, ((unsigned long long)conf_key(cf[ci]) << 32) | (unsigned long long)(ref0 + ci), c0 + ci);
                     ++slot;
                 }
         }
