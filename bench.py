@@ -131,20 +131,34 @@ class ClockSampler:
 # CPU arm: the reference's algorithm on the host cores (oracle port = the same torch / torchvision /
 # numpy wheels the reference calls; the Python reference itself cannot travel to the GPU box)
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_pass(cfg, levels, seg_low, target):
-    """One pass of the reference path on CPU tensors; returns nothing (timed by the caller)."""
+def cpu_reference_pass(cfg, levels, seg_low, target, stages=None):
+    """One pass of the reference path on CPU tensors (timed by the caller); `stages` accumulates per-stage seconds."""
     from oracle import port
+
+    def lap(name, t0):
+        if stages is not None:
+            stages[name] = stages.get(name, 0.0) + (time.perf_counter() - t0)
+
+    t0 = time.perf_counter()
     z, _ = port.decode_levels(levels, port.DEFAULT_ANCHORS, port.DEFAULT_STRIDES, cfg["nc"])
+    lap("decode", t0)
+    t0 = time.perf_counter()
     for i in range(z.shape[0]):     # per image, as the oracle does (no 10 s break)
         port.non_max_suppression(z[i:i + 1], cfg["conf"], cfg["iou"], multi_label=cfg["multi_label"], max_det=cfg["max_det"])
+    lap("nms", t0)
     if cfg["mode"] == "det_only":
         return
+    t0 = time.perf_counter()
     full = port.upsample_x8_aten(seg_low)
+    lap("upsample", t0)
+    t0 = time.perf_counter()
     if cfg["mode"] == "detect":
         port.segoutput_to_target(full, (cfg["S"], cfg["S"]))
+        lap("argmax_mask", t0)
     else:
         port.batch_pix_accuracy(full, target)
         port.batch_intersection_union(full, target, max(cfg["C"], 2))
+        lap("seg_metrics", t0)
 
 
 def cpu_sample_size(cfg):
@@ -153,14 +167,14 @@ def cpu_sample_size(cfg):
     return 16 if cfg["S"] <= 640 else 4
 
 
-def time_cpu(cfg, seed, repeats, n=None):
+def time_cpu(cfg, seed, repeats, n=None, stages=None):
     from desenet_b200.synth import synth_head_outputs
     n = cpu_sample_size(cfg) if n is None else n
     levels, seg_low, target = synth_head_outputs(n, cfg["S"], cfg["nc"], cfg["C"], seed=seed, with_target=cfg["mode"] == "eval")
     times = []
     for _ in range(repeats):
         t0 = time.perf_counter()
-        cpu_reference_pass(cfg, levels, seg_low, target)
+        cpu_reference_pass(cfg, levels, seg_low, target, stages)
         times.append(time.perf_counter() - t0)
     return n, times
 
@@ -372,13 +386,16 @@ def main():
     kw = pp.kw
     reps = max(args.steps, 50)
 
-    def k_filter(i):
+    def k_cut(i):
+        ops.conf_cut_levels(heads[i % NBUF], kw["conf_thres"], kw["multi_label"], kw["classes"], cut=pp.cut)
+
+    def k_filter(i):       # the filter alone; with the confidence cut it reuses the cut of the last k_cut call (same images)
         ops.filter_levels(heads[i % NBUF], kw["conf_thres"], kw["multi_label"], kw["classes"], cap=int(pp.keys.shape[1]),
-                          keys=pp.keys, counts=pp.counts)
+                          keys=pp.keys, counts=pp.counts, cut=pp.cut if pp.conf_cut else None)
 
     def k_nms(i):
         ops.nms_levels(heads[0], pp.keys, pp.counts, kw["conf_thres"], kw["iou_thres"], kw["agnostic"], kw["max_det"],
-                       det=pp.det, det_count=pp.det_count)
+                       det=pp.det, det_count=pp.det_count, cut=pp.cut if pp.conf_cut else None)
 
     def k_seg(i):
         pp._seg(d_sets[i % NBUF]["seg"], d_sets[i % NBUF]["target"])
@@ -387,7 +404,16 @@ def main():
         ops.detect_nms_levels(heads[i % NBUF], kw["conf_thres"], kw["iou_thres"], kw["classes"], kw["agnostic"],
                               kw["multi_label"], kw["max_det"], keys=pp.keys, counts=pp.counts, det=pp.det, det_count=pp.det_count)
 
-    kern_us = {"filter": time_alone(k_filter, reps)}
+    kern_us = {}
+    if pp.conf_cut:
+        kern_us["conf_cut"] = time_alone(k_cut, reps)
+        k_cut(0)           # every image of a set is a roll of set 0: per-image cuts differ, so time the filter on set 0 only
+        heads_f = [heads[0]]
+        kern_us["filter"] = time_alone(lambda i: ops.filter_levels(heads_f[0], kw["conf_thres"], kw["multi_label"], kw["classes"],
+                                                                   cap=int(pp.keys.shape[1]), keys=pp.keys, counts=pp.counts,
+                                                                   cut=pp.cut), reps)
+    else:
+        kern_us["filter"] = time_alone(k_filter, reps)
     k_filter(0)
     kern_us["nms"] = time_alone(k_nms, reps)
     kern_us["det_fused"] = time_alone(k_det_fused, reps)
@@ -445,8 +471,10 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
         time_cpu(cfg, args.seed, 1)
-        n, times = time_cpu(cfg, args.seed, 3)
+        stages = {}
+        n, times = time_cpu(cfg, args.seed, 3, stages=stages)
         cpu = {"value": n / min(times), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+               "stage_ms_per_image": {k: round(1e3 * v / (3 * n), 3) for k, v in stages.items()},
                "sample": f"{n} images of the same synthetic workload, best of 3 after 1 warm-up; oracle port = the "
                          "torch/torchvision/numpy CPU kernels the reference calls (the Python reference cannot travel)"}
 
@@ -458,7 +486,8 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["name"], "images_per_gpu": bs, "l2": f"rotating {NBUF} input sets (working set > 126 MB L2 between reuses)",
                        "launch": "cuda-graph replay" if use_graph else "direct launches",
-                       "det_path": "fused single launch" if pp.fused_det else "filter + NMS (2 launches)",
+                       "det_path": "fused single launch" if pp.fused_det else
+                       ("confidence cut + filter + NMS (3 launches)" if pp.conf_cut else "filter + NMS (2 launches)"),
                        "in_flight_batches": n_fl,
                        "candidates_per_image": cand_per_img, "detections_per_image": det_per_img,
                        "algorithmic_bytes_per_image": ab["total"]},

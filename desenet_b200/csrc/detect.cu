@@ -8,6 +8,9 @@
 // except the decode transposition.
 #include <algorithm>
 #include <cmath>
+#include <cstring>
+
+#include <cooperative_groups.h>
 
 #include "common.cuh"
 #include "filter_core.cuh"
@@ -153,8 +156,297 @@ __global__ void __launch_bounds__(kFilterThreads) filter_levels_kernel(const Hea
         const unsigned int cell = valid ? list_cell[i] : 0u;
         const float obj = valid ? list_obj[i] : 0.f;
         ClsFromPlanes cls{pbase + (size_t)5 * plane + cell, (size_t)plane};
-        filter_emit(f, prow0 + cell, g.no - 5, obj, valid, cls, f.counts + b, KeySinkGlobal(f.keys + (size_t)b * f.cap, f.cap));
+        filter_emit(f, prow0 + cell, g.no - 5, obj, valid, cls, f.counts + b, KeySinkGlobal(f.keys + (size_t)b * f.cap, f.cap),
+                    f.cut_hi ? f.cut_hi + b : nullptr);
     }
+}
+
+// ---- dense multi-label filter --------------------------------------------------------------------------------------
+// Eval setting (conf 0.001, multi_label): nearly every cell passes the objectness test and every class plane has to
+// be streamed, so the kernel above is bound by instruction issue (one sigmoid per (cell, class)), not by HBM.  Here
+// the test `sigmoid(cls) * obj > T` is first decided in LOGIT space against a per-cell bound
+//     L = logit(T' / obj) - margin,   T' = (1 - 1e-3) * max(conf_thres, confidence of the cut)
+// (one log per cell instead of one sigmoid per class): a class logit below L cannot give a candidate, whatever the
+// last-ulp behaviour of the device sigmoid (margins are ~1000x its error).  The few (cell, class) pairs above L are
+// compacted per warp through shared memory (16-bit indices into the warp's parked chunk of raw logits) and only
+// those get the exact arithmetic (sigmoid, product, the strict compares of
+// general.py:710-711 and the cut on the key) - one pair per lane, keys stored coalesced.
+// One warp = 128 consecutive cells (4 per lane, 16-byte loads), classes in chunks of 8; one CTA = 1024 cells of
+// one (image, level, anchor) plane.  Warps never synchronise with each other.
+constexpr int kDenseThreads = 256;
+constexpr int kDenseWarps = kDenseThreads / 32;
+constexpr int kDenseCells = kDenseThreads * 4;
+constexpr int kDenseChunk = 8;
+constexpr int kDenseRound = 256;
+struct DenseSmem {
+    float tile[kDenseWarps][kDenseChunk][128];          // raw class logits of the warp's cells, one chunk
+    float obj[kDenseWarps][128];                        // raw objectness logit per cell
+    unsigned short idx[kDenseWarps][kDenseChunk * 128]; // compacted (class-in-chunk << 7 | cell) of the pairs above L
+    unsigned long long kbuf[kDenseWarps][kDenseRound];  // keys of one round, written out together
+};
+
+__global__ void __launch_bounds__(kDenseThreads, 3) filter_dense_kernel(const HeadGeom g, const FilterOut f, const float obj_logit_lo,
+                                                                                   const float obj_logit_hi) {
+    extern __shared__ __align__(16) unsigned char dense_smem_raw[];
+    DenseSmem &sm = *reinterpret_cast<DenseSmem *>(dense_smem_raw);
+    const int b = blockIdx.y;
+    int l = 0;
+    while (l + 1 < g.nl && (int)blockIdx.x >= g.cta_off[l + 1]) ++l;
+    const int cp = blockIdx.x - g.cta_off[l];
+    const int a = cp / g.ctas_per_plane[l];
+    const int tile = cp - a * g.ctas_per_plane[l];
+    const int plane = g.plane[l];
+    const int nc = g.no - 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cell0 = tile * kDenseCells + threadIdx.x * 4;       // plane % 4 == 0: the 4 cells are all in or all out
+    const bool in = cell0 < plane;
+    const float *pbase = g.raw[l] + ((size_t)(b * g.na + a) * g.no) * plane + (in ? cell0 : 0);
+    const unsigned int row0 = (unsigned)(g.row_off[l] + a * plane + tile * kDenseCells + warp * 128);   // warp's first row
+    const unsigned int cut = f.cut_hi ? f.cut_hi[b] : 0xFFFFFFFFu;
+    const float cut_conf = __uint_as_float(~cut);                 // keys <= cut  <=>  conf >= cut_conf  (0 when no cut)
+    const float t_lo = fmaxf(f.conf_thres, cut_conf) * 0.999f;
+    // ---- first chunk of class planes: issued together with the objectness load (one round trip, not two) ----------
+    float4 v[kDenseChunk];
+#pragma unroll
+    for (int ci = 0; ci < kDenseChunk; ++ci) {
+        v[ci] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        if (in && ci < nc) v[ci] = ldg_stream_f4(pbase + (size_t)(5 + ci) * plane);
+    }
+    // ---- objectness: the per-cell logit bound L = -ln(obj / T' - 1) - margin, obj = 1 / (1 + exp(-o)) ------------------
+    // Approximate exp / division / log are enough here: the margins (0.1 % on T, 4e-3 on L) are >1000x their error
+    // wherever a candidate can exist (obj >= T, so obj / T' - 1 >= 1e-3 and the subtraction loses < 1e-3 relative).
+    // The strict test obj > conf_thres (general.py:668) is decided in logit space outside the narrow band
+    // [obj_logit_lo, obj_logit_hi) and by the exact sigmoid inside it.
+    float L[4];
+    bool any = false;
+    {
+        float4 o4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        if (in) o4 = ldg_stream_f4(pbase + (size_t)4 * plane);
+        const float ol[4] = {o4.x, o4.y, o4.z, o4.w};
+        const float inv_t = __fdividef(1.0f, t_lo);                                      // +inf when T' == 0
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            L[k] = INFINITY;
+            bool pass = ol[k] >= obj_logit_hi;
+            if (!pass && ol[k] >= obj_logit_lo) pass = sigmoidf_ref(ol[k]) > f.conf_thres;   // yolo.py:266, general.py:668
+            if (pass) {
+                const float q = __fdividef(inv_t, 1.0f + __expf(-ol[k])) - 1.0f;
+                if (q > 0.f) L[k] = -__logf(q) - 4e-3f;                                 // q == +inf -> -inf: everything passes
+            }
+            any = any || L[k] < INFINITY;
+        }
+        *reinterpret_cast<float4 *>(&sm.obj[warp][lane * 4]) = o4;                       // raw logits; sigmoid per survivor
+    }
+    if (!__any_sync(0xffffffffu, any)) return;
+    unsigned long long *kout = f.keys + (size_t)b * f.cap;
+    const unsigned int cap = f.cap > 0x7fffffffLL ? 0x7fffffffu : (unsigned)f.cap;
+    int *counter = f.counts + b;
+    // class planes in chunks of kDenseChunk; the NEXT chunk's loads are issued before the current chunk's survivors are
+    // worked on, so the HBM round trip overlaps the compaction and the exact pass
+    int nk = 0;                                         // keys waiting in the warp's kbuf (warp-uniform)
+    auto flush = [&]() {                                // ONE atomic on the image's counter, coalesced 8-byte stores
+        unsigned int base = 0;
+        if (lane == 0) base = (unsigned)atomicAdd(counter, nk);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        __syncwarp();
+        for (int i = lane; i < nk; i += 32)
+            if (base + i < cap) kout[base + i] = sm.kbuf[warp][i];
+        __syncwarp();
+        nk = 0;
+    };
+    for (int c0 = 0; c0 < nc; c0 += kDenseChunk) {
+        // ---- logit-space test of the chunk in registers -------------------------------------------------------------
+        unsigned int mask = 0;
+#pragma unroll
+        for (int ci = 0; ci < kDenseChunk; ++ci) {
+            mask |= (v[ci].x > L[0] ? 1u : 0u) << (ci * 4 + 0);
+            mask |= (v[ci].y > L[1] ? 1u : 0u) << (ci * 4 + 1);
+            mask |= (v[ci].z > L[2] ? 1u : 0u) << (ci * 4 + 2);
+            mask |= (v[ci].w > L[3] ? 1u : 0u) << (ci * 4 + 3);
+        }
+        const bool work = __any_sync(0xffffffffu, mask != 0);
+        if (work) {                                     // park the raw logits for the exact pass
+            __syncwarp();                               // previous chunk's readers are done with tile / idx
+#pragma unroll
+            for (int ci = 0; ci < kDenseChunk; ++ci) *reinterpret_cast<float4 *>(&sm.tile[warp][ci][lane * 4]) = v[ci];
+        }
+        if (c0 + kDenseChunk < nc) {
+#pragma unroll
+            for (int ci = 0; ci < kDenseChunk; ++ci) {
+                v[ci] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                if (any && c0 + kDenseChunk + ci < nc) v[ci] = ldg_stream_f4(pbase + (size_t)(5 + c0 + kDenseChunk + ci) * plane);
+            }
+        }
+        if (!work) continue;
+        const int mine = __popc(mask);
+        int incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += up;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int slot = incl - mine;
+        for (unsigned int m = mask; m; m &= m - 1) {
+            const int bit = __ffs(m) - 1;
+            sm.idx[warp][slot++] = (unsigned short)(((bit >> 2) << 7) | (lane * 4 + (bit & 3)));
+        }
+        __syncwarp();
+        // ---- exact arithmetic for the surviving pairs, one per lane; keys are staged in the warp's kbuf and leave
+        // together when it fills up (or at the end) ----------------------------------------------------------------
+        for (int e0 = 0; e0 < total; e0 += 32) {
+            if (nk > kDenseRound - 32) flush();
+            const int e = e0 + lane;
+            bool emit = false;
+            unsigned long long key = 0ull;
+            if (e < total) {
+                const unsigned int id = sm.idx[warp][e];
+                const int ci = id >> 7, cell = id & 127;
+                const float conf = __fmul_rn(sigmoidf_ref(sm.tile[warp][ci][cell]), sigmoidf_ref(sm.obj[warp][cell]));   // general.py:703
+                const unsigned int ck = conf_key(conf);
+                emit = conf > f.conf_thres && ck <= cut && class_allowed(f, c0 + ci);                     // general.py:710,717
+                key = ((unsigned long long)ck << 32) | (unsigned long long)((row0 + cell) * (unsigned)nc + (unsigned)(c0 + ci));
+            }
+            const unsigned int bal = __ballot_sync(0xffffffffu, emit);
+            if (emit) sm.kbuf[warp][nk + __popc(bal & ((1u << lane) - 1u))] = key;
+            nk += __popc(bal);
+        }
+    }
+    if (nk > 0) flush();
+}
+
+// ---- confidence cut for huge candidate sets (eval setting, multi-label) -------------------------------------------
+// With conf 0.001 and multi_label the filter would emit up to A*nc candidates per image (1.28 M at nc = 80), while
+// the greedy NMS stops after max_det survivors and never looks past the max_nms = 30000 best (general.py:728-736).
+// A SAMPLE of the image (every kCutStride-th unit of 4 cells, all classes) is histogrammed by confidence; from it a
+// cut is chosen above which about 2 x `target` candidates are expected, and the filter then emits only candidates at
+// or above the cut - exactly the best ones, so the NMS result is unchanged as long as the NMS stops by itself.  If it
+// runs out of emitted candidates first (cut_dropped[b] says a cut was in force) it reports det_count = -2 and the
+// caller re-runs that batch without the cut.
+// One CLUSTER of up to kCutCluster CTAs per image (sized at launch from the sampled work): every CTA histograms its share of the sample in its own shared memory,
+// CTA 0 then sums the histograms over distributed shared memory and picks the bin.  A task = one sampled unit x one
+// chunk of 8 classes, so an image with many classes spreads over all threads and each waits for two round trips.
+constexpr int kCutStride = 64;
+constexpr int kCutBins = 2048;
+constexpr int kCutFactor = 2;
+constexpr int kCutThreads = 256;
+constexpr int kCutCluster = 4;
+
+__device__ __forceinline__ unsigned int cut_bin(unsigned int key_hi, unsigned int lo_hi, int sh) {
+    return key_hi <= lo_hi ? 0u : min((key_hi - lo_hi) >> sh, (unsigned)kCutBins - 1u);
+}
+
+__global__ void __launch_bounds__(kCutThreads)
+conf_cut_kernel(const HeadGeom g, const FilterOut f, const float obj_logit_lo, unsigned int lo_hi, int sh, unsigned int want,
+                unsigned int *__restrict__ cut_hi, int *__restrict__ cut_dropped) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ unsigned int sh_hist[kCutBins];
+    __shared__ unsigned int warp_sum[kCutThreads / 32];
+    __shared__ unsigned int chosen;
+    const int csize = (int)cluster.num_blocks();     // 1 .. kCutCluster CTAs per image (launch attribute)
+    const int b = blockIdx.x / csize;
+    const int rank = (int)cluster.block_rank();
+    for (int i = threadIdx.x; i < kCutBins; i += kCutThreads) sh_hist[i] = 0u;
+    if (threadIdx.x == 0) chosen = 0xFFFFFFFFu;
+    __syncthreads();
+    const int total_units = g.unit_off[g.nl];
+    const int nc = g.no - 5;
+    const int sampled = (total_units + kCutStride - 1) / kCutStride;
+    const int nsplit = f.multi_label ? (nc + 7) / 8 : 1;          // best-class mode needs all classes of a cell in one thread
+    const int span = f.multi_label ? 8 : nc;
+    for (int t = rank * kCutThreads + threadIdx.x; t < sampled * nsplit; t += csize * kCutThreads) {
+        const int su = t / nsplit;
+        const int cbeg = (t - su * nsplit) * 8;
+        const RowGeom rg = row_geom(g, su * kCutStride * 4);          // sampled unit = 4 consecutive rows
+        const float *base = g.raw[rg.l] + ((size_t)(b * g.na + rg.a) * g.no) * rg.plane + rg.cell;
+        const float4 o4 = ldg_stream_f4(base + (size_t)4 * rg.plane);
+        const float ol[4] = {o4.x, o4.y, o4.z, o4.w};
+        float obj[4];
+        unsigned int pass = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            obj[k] = ol[k] >= obj_logit_lo ? sigmoidf_ref(ol[k]) : 0.f;
+            pass |= obj[k] > f.conf_thres ? (1u << k) : 0u;
+        }
+        if (!pass) continue;
+        float best[4] = {0.f, 0.f, 0.f, 0.f};
+        int bcls[4] = {0, 0, 0, 0};
+        for (int c0 = cbeg; c0 < min(nc, cbeg + span); c0 += 8) {      // 8 class planes per round trip
+            float4 c4[8];
+#pragma unroll
+            for (int ci = 0; ci < 8; ++ci)
+                c4[ci] = c0 + ci < nc ? ldg_stream_f4(base + (size_t)(5 + c0 + ci) * rg.plane) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int ci = 0; ci < 8; ++ci) {
+                const int c = c0 + ci;
+                if (c >= nc) break;
+                const float cl[4] = {c4[ci].x, c4[ci].y, c4[ci].z, c4[ci].w};
+                const bool ok = class_allowed(f, c);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (!((pass >> k) & 1u)) continue;
+                    const float conf = __fmul_rn(sigmoidf_ref(cl[k]), obj[k]);
+                    if (f.multi_label) {
+                        if (ok && conf > f.conf_thres) atomicAdd(&sh_hist[cut_bin(conf_key(conf), lo_hi, sh)], 1u);
+                    } else if (c == 0 || argmax_better(conf, best[k])) {
+                        best[k] = conf;
+                        bcls[k] = c;
+                    }
+                }
+            }
+        }
+        if (!f.multi_label) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (((pass >> k) & 1u) && best[k] > f.conf_thres && class_allowed(f, bcls[k]))
+                    atomicAdd(&sh_hist[cut_bin(conf_key(best[k]), lo_hi, sh)], 1u);
+        }
+    }
+    cluster.sync();                                  // every CTA's histogram is complete and visible cluster-wide
+    if (rank == 0) {
+        // prefix sum over the bins (best confidences first), summed over the cluster, scaled by the sampling stride
+        constexpr int per = kCutBins / kCutThreads;
+        static_assert(per * kCutThreads == kCutBins, "bins must split evenly over the CTA");
+        unsigned int h[per], mine = 0;
+#pragma unroll
+        for (int j = 0; j < per; ++j) h[j] = sh_hist[threadIdx.x * per + j];
+        for (int r = 1; r < csize; ++r) {
+            const unsigned int *remote = cluster.map_shared_rank(sh_hist, r);      // DSMEM read
+#pragma unroll
+            for (int j = 0; j < per; ++j) h[j] += remote[threadIdx.x * per + j];
+        }
+#pragma unroll
+        for (int j = 0; j < per; ++j) { h[j] *= kCutStride; mine += h[j]; }
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        unsigned int incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned int up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += up;
+        }
+        if (lane == 31) warp_sum[warp] = incl;
+        __syncthreads();
+        unsigned int pre = incl - mine;
+        for (int w = 0; w < warp; ++w) pre += warp_sum[w];
+#pragma unroll
+        for (int j = 0; j < per; ++j) {
+            pre += h[j];
+            if (pre >= want) { atomicMin(&chosen, (unsigned)(threadIdx.x * per + j)); break; }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            // keys in bins <= chosen pass; boundary in the confidence half of the key: lo_hi + ((chosen+1) << sh) - 1
+            unsigned int c = 0xFFFFFFFFu;
+            if (chosen != 0xFFFFFFFFu) {
+                const unsigned long long edge = (unsigned long long)lo_hi + (((unsigned long long)chosen + 1ull) << sh) - 1ull;
+                c = edge > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned int)edge;
+            }
+            cut_hi[b] = c;
+            cut_dropped[b] = c != 0xFFFFFFFFu;        // a cut is in force: the filter may drop candidates of this image
+        }
+    }
+    cluster.sync();                                  // keep the other CTAs' shared memory alive until CTA 0 has read it
 }
 
 // ---- from a decoded prediction (bs, A, no): lane = one row ---------------------------------------
@@ -207,12 +499,83 @@ extern "C" __attribute__((visibility("default"))) int dsn_detect_decode(const fl
 extern "C" __attribute__((visibility("default"))) int dsn_filter_levels(const float *const *raw, const int *ny, const int *nx, int nl, int bs, int na, int no,
                                  float conf_thres, int multi_label, const uint64_t *class_mask, uint64_t *keys,
                                  int64_t cap, int *counts, void *stream) {
+    return dsn_filter_levels_cut(raw, ny, nx, nl, bs, na, no, conf_thres, multi_label, class_mask, keys, cap, counts, nullptr,
+                                 stream);
+}
+
+// confidence half of a key for a confidence value / the histogram geometry shared by sampler, cut and filter
+static inline unsigned int host_conf_key(float conf) {
+    uint32_t b;
+    memcpy(&b, &conf, 4);
+    return ~b;
+}
+static inline void cut_geometry(float conf_thres, unsigned int &lo_hi, int &sh) {
+    lo_hi = host_conf_key(1.0f);                                  // confidences above 1.0 fall into bin 0
+    const unsigned int hi_hi = host_conf_key(conf_thres > 0.f ? conf_thres : 0.f);
+    const unsigned int width = hi_hi > lo_hi ? hi_hi - lo_hi : 1u;
+    sh = 0;
+    while ((width >> sh) >= (unsigned)kCutBins) ++sh;
+}
+
+extern "C" __attribute__((visibility("default"))) int dsn_conf_cut_levels(const float *const *raw, const int *ny, const int *nx, int nl,
+                                                                          int bs, int na, int no, float conf_thres, int multi_label,
+                                                                          const uint64_t *class_mask, int target,
+                                                                          unsigned int *hist_ws, unsigned int *cut_hi,
+                                                                          int *cut_dropped, void *stream) {
+    HeadGeom g;
+    int rc = make_geom(g, raw, ny, nx, nullptr, nullptr, nl, bs, na, no);
+    if (rc) return rc;
+    (void)hist_ws;                              // reserved (the histogram lives in shared memory)
+    if (!cut_hi || !cut_dropped || target < 1 || target > (1 << 28)) return DSN_E_INVALID;
+    FilterOut f;
+    uint64_t dummy_keys;
+    int dummy_counts;
+    rc = make_filter_out(f, conf_thres, multi_label, no - 5, class_mask, &dummy_keys, 1, &dummy_counts);
+    if (rc) return rc;
+    if (bs == 0) return DSN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int l = 0; l < nl; ++l)
+        if (g.plane[l] % 4 != 0 || (((uintptr_t)raw[l]) & 15) != 0) return DSN_E_UNSUPPORTED;   // caller: run without a cut
+    int units = 0;
+    for (int l = 0; l < nl; ++l) {
+        g.unit_off[l] = units;
+        units += na * g.plane[l] / 4;
+    }
+    g.unit_off[nl] = units;
+    unsigned int lo_hi;
+    int sh;
+    cut_geometry(conf_thres, lo_hi, sh);
+    // cluster size from the amount of sampled work: one CTA per image when a single pass of its threads covers it
+    const int sampled = (units + kCutStride - 1) / kCutStride;
+    const int tasks = sampled * (f.multi_label ? (no - 5 + 7) / 8 : 1);
+    int csize = 1;
+    while (csize < kCutCluster && tasks > csize * kCutThreads) csize <<= 1;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)(bs * csize));
+    lc.blockDim = dim3(kCutThreads);
+    lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    DSN_CUDA(cudaLaunchKernelEx(&lc, conf_cut_kernel, g, f, obj_logit_lower_bound(conf_thres), lo_hi, sh,
+                                (unsigned)kCutFactor * (unsigned)target, cut_hi, cut_dropped));
+    return DSN_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int dsn_filter_levels_cut(const float *const *raw, const int *ny, const int *nx, int nl, int bs, int na, int no,
+                                 float conf_thres, int multi_label, const uint64_t *class_mask, uint64_t *keys,
+                                 int64_t cap, int *counts, const unsigned int *cut_hi, void *stream) {
     HeadGeom g;
     int rc = make_geom(g, raw, ny, nx, nullptr, nullptr, nl, bs, na, no);
     if (rc) return rc;
     FilterOut f;
     rc = make_filter_out(f, conf_thres, multi_label, no - 5, class_mask, keys, cap, counts);
     if (rc) return rc;
+    f.cut_hi = cut_hi;
     if (bs == 0) return DSN_OK;
     cudaStream_t st = (cudaStream_t)stream;
     DSN_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)bs, st));
@@ -227,6 +590,20 @@ extern "C" __attribute__((visibility("default"))) int dsn_filter_levels(const fl
     }
     g.cta_off[nl] = ctas;
     const float lo = obj_logit_lower_bound(conf_thres);
+    if (vec && f.multi_label) {                // dense multi-label path: every class plane is streamed
+        ctas = 0;
+        for (int l = 0; l < nl; ++l) {
+            g.cta_off[l] = ctas;
+            g.ctas_per_plane[l] = (g.plane[l] + kDenseCells - 1) / kDenseCells;
+            ctas += na * g.ctas_per_plane[l];
+        }
+        g.cta_off[nl] = ctas;
+        static DeviceOnce once;
+        if (int rc2 = raise_dynamic_smem(once, filter_dense_kernel, (int)sizeof(DenseSmem))) return rc2;
+        filter_dense_kernel<<<dim3(ctas, bs), kDenseThreads, sizeof(DenseSmem), st>>>(g, f, lo, obj_logit_upper_bound(conf_thres));
+        DSN_CHECK_LAUNCH();
+        return DSN_OK;
+    }
     dim3 grid(ctas, bs);
     if (vec) filter_levels_kernel<4><<<grid, kFilterThreads, 0, st>>>(g, f, lo);
     else filter_levels_kernel<1><<<grid, kFilterThreads, 0, st>>>(g, f, lo);

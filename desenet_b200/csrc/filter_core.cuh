@@ -19,6 +19,9 @@ struct FilterOut {
     int multi_label;
     unsigned long long cmask[4];
     int use_cmask;
+    // optional confidence cut (dsn_conf_cut_levels): candidates whose key's confidence half exceeds cut_hi[b] are not
+    // emitted (they can only matter beyond the max_nms best)
+    const unsigned int *cut_hi;
 };
 
 __device__ __forceinline__ bool class_allowed(const FilterOut &f, int cls) {
@@ -62,9 +65,12 @@ struct KeySinkGlobal {
 
 template <class Cls, class Sink>
 __device__ __forceinline__ void filter_emit(const FilterOut &f, unsigned int row, int nc, float obj, bool valid,
-                                            const Cls &cls, int *counter, const Sink &sink) {
+                                            const Cls &cls, int *counter, const Sink &sink,
+                                            const unsigned int *cut_ptr = nullptr) {
     const bool pass = valid && obj > f.conf_thres;                                       // general.py:668,687
     if (!__any_sync(0xffffffffu, pass)) return;
+    const bool cut_on = cut_ptr != nullptr;
+    const unsigned int cut = cut_on ? *cut_ptr : 0xFFFFFFFFu;
     float best = 0.f;
     int bcls = 0;
     if (!f.multi_label && nc <= kClsChunk) {
@@ -95,7 +101,8 @@ __device__ __forceinline__ void filter_emit(const FilterOut &f, unsigned int row
                 }
             }
         }
-        const bool emit = exact && best > f.conf_thres && class_allowed(f, bcls);            // general.py:714,717
+        bool emit = exact && best > f.conf_thres && class_allowed(f, bcls);                  // general.py:714,717
+        if (cut_on) emit = emit && conf_key(best) <= cut;
         const int slot = warp_alloc(counter, emit ? 1 : 0);
         if (emit) sink(slot, ((unsigned long long)conf_key(best) << 32) | (unsigned long long)(row * (unsigned)nc + bcls), bcls);
         return;
@@ -136,6 +143,13 @@ __device__ __forceinline__ void filter_emit(const FilterOut &f, unsigned int row
                         if (!class_allowed(f, c0 + ci)) emit &= ~(1u << ci);
                 }
             }
+            if (cut_on) {                                     // confidence cut: keep only keys that can reach the top max_nms
+                unsigned int keep = 0;
+#pragma unroll
+                for (int ci = 0; ci < kClsChunk; ++ci)
+                    if (((emit >> ci) & 1u) && conf_key(cf[ci]) <= cut) keep |= 1u << ci;
+                emit = keep;
+            }
             if (!__any_sync(0xffffffffu, emit != 0)) continue;
             int slot = warp_alloc(counter, __popc(emit));
             const unsigned int ref0 = row * (unsigned)nc + (unsigned)c0;
@@ -148,7 +162,8 @@ __device__ __forceinline__ void filter_emit(const FilterOut &f, unsigned int row
         }
     }
     if (!f.multi_label) {
-        const bool emit = pass && best > f.conf_thres && class_allowed(f, bcls);             // general.py:714,717
+        bool emit = pass && best > f.conf_thres && class_allowed(f, bcls);                   // general.py:714,717
+        if (cut_on) emit = emit && conf_key(best) <= cut;
         const int slot = warp_alloc(counter, emit ? 1 : 0);
         if (emit) sink(slot, ((unsigned long long)conf_key(best) << 32) | (unsigned long long)(row * (unsigned)nc + bcls), bcls);
     }
@@ -193,6 +208,7 @@ static inline int make_filter_out(FilterOut &f, float conf_thres, int multi_labe
     f.multi_label = (multi_label && nc > 1) ? 1 : 0;                          // general.py:679
     f.use_cmask = class_mask != nullptr;
     for (int i = 0; i < 4; ++i) f.cmask[i] = class_mask ? class_mask[i] : ~0ull;
+    f.cut_hi = nullptr;
     return DSN_OK;
 }
 

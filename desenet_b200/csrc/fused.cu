@@ -282,7 +282,7 @@ extern "C" __attribute__((visibility("default"))) int dsn_detect_nms_levels(
         rc = dsn_filter_levels(raw, ny, nx, nl, bs, na, no, conf_thres, multi_label, class_mask, keys, cap, counts, stream);
         if (rc) return rc;
         return dsn_nms_levels(raw, ny, nx, stride, anchor_grid, nl, bs, na, no, keys, cap, counts, conf_thres, iou_thres,
-                              agnostic, max_nms, max_det, max_wh, det, det_count, stream);
+                              agnostic, max_nms, max_det, max_wh, nullptr, det, det_count, stream);
     }
     const float lo = obj_logit_lower_bound(conf_thres);
     const size_t smem = sizeof(FusedSmem);

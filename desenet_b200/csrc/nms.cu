@@ -30,7 +30,8 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams p, con
         return;
     }
     if (total <= 0 || p.max_det <= 0 || p.max_nms <= 0) {
-        if (threadIdx.x == 0) p.det_count[b] = 0;
+        const bool starved = total <= 0 && p.max_det > 0 && p.max_nms > 0 && p.cut_dropped && p.cut_dropped[b];
+        if (threadIdx.x == 0) p.det_count[b] = starved ? -2 : 0;
         return;
     }
     nms_image(s, p, src, b, p.keys + (size_t)b * p.cap, total);
@@ -55,7 +56,8 @@ using namespace dsn;
 extern "C" __attribute__((visibility("default"))) int dsn_nms_levels(const float *const *raw, const int *ny, const int *nx, const float *stride,
                               const float *anchor_grid, int nl, int bs, int na, int no, const uint64_t *keys,
                               int64_t cap, const int *counts, float conf_thres, double iou_thres, int agnostic,
-                              int max_nms, int max_det, float max_wh, float *det, int *det_count, void *stream) {
+                              int max_nms, int max_det, float max_wh, const int *cut_dropped, float *det, int *det_count,
+                              void *stream) {
     if (!stride || !anchor_grid) return DSN_E_INVALID;
     BoxFromLevels src;
     int rc = make_geom(src.g, raw, ny, nx, stride, anchor_grid, nl, bs, na, no);
@@ -63,6 +65,7 @@ extern "C" __attribute__((visibility("default"))) int dsn_nms_levels(const float
     NmsParams p;
     rc = make_nms_params(p, keys, cap, counts, bs, no - 5, conf_thres, iou_thres, agnostic, max_nms, max_det, max_wh, det, det_count);
     if (rc) return rc;
+    p.cut_dropped = cut_dropped;
     return launch_nms(p, src, bs, (cudaStream_t)stream);
 }
 

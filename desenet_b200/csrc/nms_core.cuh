@@ -26,6 +26,7 @@ struct NmsParams {
     int max_nms, max_det;
     unsigned long long key_lo_hint;   // keys of conf <= 1.0 are >= this (hint, not required)
     unsigned long long key_hi;        // every key is <= this (conf > conf_thres)
+    const int *cut_dropped;           // optional (bs): the filter dropped candidates below a confidence cut
     float *det;
     int *det_count;
 };
@@ -276,6 +277,7 @@ __device__ void nms_image(NmsSmem &s, const NmsParams &p, const BoxSrc &src, int
     int seen = 0;                   // keys gathered so far
     unsigned long long cur = 0ull;
     bool first = true;
+    bool done = false;              // max_det survivors found
     __syncthreads();
     DSN_LAP_START();
 
@@ -364,7 +366,6 @@ __device__ void nms_image(NmsSmem &s, const NmsParams &p, const BoxSrc &src, int
                           (((double)s.ext[2] - (double)s.ext[0]) <= cull_lim || ((double)s.ext[3] - (double)s.ext[1]) <= cull_lim);
         DSN_LAP(36);   // extent
         // ---- 4. resolve the chunk in rounds of kRound candidates ---------------------------------
-        bool done = false;
         for (int s0 = 0; s0 < m && !done; s0 += kRound) {
             const int cnt = min(kRound, m - s0);
             const int nkept0 = s.nkept;
@@ -509,7 +510,11 @@ __device__ void nms_image(NmsSmem &s, const NmsParams &p, const BoxSrc &src, int
     }
     __syncthreads();
     DSN_MARK(16);
-    if (threadIdx.x == 0) p.det_count[b] = s.nkept;
+    // Confidence cut (dsn_conf_cut_levels): the emitted keys are exactly the best candidates of the image, so the
+    // result is the reference's whenever the greedy pass stopped by itself (max_det survivors, or max_nms candidates
+    // consumed).  Running out of emitted keys first means dropped candidates could still have mattered: -2.
+    const bool starved = !done && consumed < p.max_nms && p.cut_dropped != nullptr && p.cut_dropped[b] != 0;
+    if (threadIdx.x == 0) p.det_count[b] = starved ? -2 : s.nkept;
 }
 
 static inline int make_nms_params(NmsParams &p, const uint64_t *keys, int64_t cap, const int *counts, int bs, int nc,
@@ -533,6 +538,7 @@ static inline int make_nms_params(NmsParams &p, const uint64_t *keys, int64_t ca
     const float ct = conf_thres > 0.f ? conf_thres : 0.f;
     memcpy(&tb, &ct, 4);
     p.key_hi = ((unsigned long long)(~tb) << 32) | 0xFFFFFFFFull;   // conf > conf_thres  =>  key <= this
+    p.cut_dropped = nullptr;
     p.det = det;
     p.det_count = det_count;
     return DSN_OK;

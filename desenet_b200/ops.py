@@ -98,8 +98,34 @@ def detect_decode(head: Head, want_z: bool = True, want_x: bool = True):
     return z, xs
 
 
+class ConfCut:
+    """Workspace + result of ``conf_cut_levels``: per-image confidence-key bound and the filter's dropped flags."""
+
+    def __init__(self, bs: int, device):
+        self.cut_hi = torch.empty((bs,), dtype=torch.int32, device=device)
+        self.dropped = torch.zeros((bs,), dtype=torch.int32, device=device)
+
+
+def conf_cut_levels(head: Head, conf_thres: float, multi_label: bool, classes=None, target: int = 8192,
+                    cut: Optional[ConfCut] = None) -> Optional[ConfCut]:
+    """Sampled per-image confidence cut for huge candidate sets (see include/desenet_b200.h).  Returns None when
+    the head layout does not allow it (the filter then simply runs without a cut)."""
+    lib = _lib.load()
+    ml = bool(multi_label) and head.nc > 1
+    with torch.cuda.device(head.device):
+        if cut is None:
+            cut = ConfCut(head.bs, head.device)
+        rc = lib.dsn_conf_cut_levels(head.c_raw, head.c_ny, head.c_nx, head.nl, head.bs, head.na, head.no, float(conf_thres),
+                                     int(ml), class_mask(classes, head.nc), int(target), None, _ptr(cut.cut_hi),
+                                     _ptr(cut.dropped), _stream(head.device))
+    if rc == -2:
+        return None
+    _lib.check(rc, "dsn_conf_cut_levels")
+    return cut
+
+
 def filter_levels(head: Head, conf_thres: float, multi_label: bool, classes=None, cap: Optional[int] = None,
-                  keys: Optional[torch.Tensor] = None, counts: Optional[torch.Tensor] = None):
+                  keys: Optional[torch.Tensor] = None, counts: Optional[torch.Tensor] = None, cut: Optional[ConfCut] = None):
     """Fused decode + candidate filter (yolo.py:259-277 + general.py:668-718) -> (keys, counts)."""
     lib = _lib.load()
     ml = bool(multi_label) and head.nc > 1
@@ -110,10 +136,10 @@ def filter_levels(head: Head, conf_thres: float, multi_label: bool, classes=None
             keys = torch.empty((head.bs, cap), dtype=torch.int64, device=head.device)
         if counts is None:
             counts = torch.empty((head.bs,), dtype=torch.int32, device=head.device)
-        rc = lib.dsn_filter_levels(head.c_raw, head.c_ny, head.c_nx, head.nl, head.bs, head.na, head.no,
-                                   float(conf_thres), int(ml), class_mask(classes, head.nc), _ptr(keys), cap,
-                                   _ptr(counts), _stream(head.device))
-    _lib.check(rc, "dsn_filter_levels")
+        rc = lib.dsn_filter_levels_cut(head.c_raw, head.c_ny, head.c_nx, head.nl, head.bs, head.na, head.no,
+                                       float(conf_thres), int(ml), class_mask(classes, head.nc), _ptr(keys), cap,
+                                       _ptr(counts), _ptr(cut.cut_hi if cut else None), _stream(head.device))
+    _lib.check(rc, "dsn_filter_levels_cut")
     return keys, counts
 
 
@@ -137,7 +163,7 @@ def filter_z(z: torch.Tensor, conf_thres: float, multi_label: bool, classes=None
 
 def nms_levels(head: Head, keys: torch.Tensor, counts: torch.Tensor, conf_thres: float, iou_thres: float,
                agnostic: bool, max_det: int, max_nms: int = MAX_NMS, max_wh: float = MAX_WH,
-               det: Optional[torch.Tensor] = None, det_count: Optional[torch.Tensor] = None):
+               det: Optional[torch.Tensor] = None, det_count: Optional[torch.Tensor] = None, cut: Optional[ConfCut] = None):
     lib = _lib.load()
     with torch.cuda.device(head.device):
         if det is None:
@@ -147,7 +173,7 @@ def nms_levels(head: Head, keys: torch.Tensor, counts: torch.Tensor, conf_thres:
         rc = lib.dsn_nms_levels(head.c_raw, head.c_ny, head.c_nx, head.c_stride, head.c_anchor, head.nl, head.bs,
                                 head.na, head.no, _ptr(keys), int(keys.shape[1]), _ptr(counts), float(conf_thres),
                                 float(iou_thres), int(bool(agnostic)), int(max_nms), int(max_det), float(max_wh),
-                                _ptr(det), _ptr(det_count), _stream(head.device))
+                                _ptr(cut.dropped if cut else None), _ptr(det), _ptr(det_count), _stream(head.device))
     _lib.check(rc, "dsn_nms_levels")
     return det, det_count
 

@@ -15,7 +15,8 @@ class PostProcessor:
     def __init__(self, bs: int, size, nc: int, n_segcls: int, anchor_grid, stride, *, conf_thres=0.25,
                  iou_thres=0.45, classes=None, agnostic=False, multi_label=False, max_det=300, mode="detect",
                  nclass: Optional[int] = None, mask_dtype=torch.float32, device=None, overlap_streams=True,
-                 na: int = 3, fused_det: bool = False, scale_params: Optional[torch.Tensor] = None, round_boxes: bool = False):
+                 na: int = 3, fused_det: bool = False, scale_params: Optional[torch.Tensor] = None, round_boxes: bool = False,
+                 conf_cut: Optional[bool] = None):
         assert mode in ("detect", "eval", "det_only")
         assert 0 <= conf_thres <= 1 and 0 <= iou_thres <= 1
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -46,7 +47,16 @@ class PostProcessor:
             self.side = torch.cuda.Stream(device=d, priority=-1) if (overlap_streams and mode != "det_only") else None
             self.ev_in = torch.cuda.Event()
             self.ev_seg = torch.cuda.Event()
-        self.kernels_per_step = (1 if fused_det else 2) + (0 if mode == "det_only" else 1)
+        # sampled confidence cut (ops.conf_cut_levels): worth it when an image can emit far more than the max_nms
+        # candidates non_max_suppression ever looks at (general.py:728-729), i.e. multi-label at a low threshold
+        # candidates the greedy NMS is expected to consume before max_det survive; the cut keeps about twice as many
+        self.cut_target = min(ops.MAX_NMS, max(8192, 16 * int(max_det)))
+        self.conf_cut = (self.kw["multi_label"] and cap >= 8 * self.cut_target) if conf_cut is None else bool(conf_cut)
+        self.conf_cut = self.conf_cut and not fused_det
+        with torch.cuda.device(d):
+            self.cut = ops.ConfCut(bs, d) if self.conf_cut else None
+        self._last_head = None
+        self.kernels_per_step = (1 if fused_det else (3 if self.conf_cut else 2)) + (0 if mode == "det_only" else 1)
         self._graphs = {}
 
     # ---- enqueue-only device path --------------------------------------------------------------
@@ -79,17 +89,22 @@ class PostProcessor:
                 self._seg(seg_low, target)
         return self.det, self.det_count, (self.mask if self.mode == "detect" else self.cm)
 
-    def _det(self, head):
+    def _det(self, head, allow_cut: bool = True):
         kw = self.kw
+        self._last_head = head
         if self.fused_det:
             ops.detect_nms_levels(head, kw["conf_thres"], kw["iou_thres"], kw["classes"], kw["agnostic"], kw["multi_label"],
                                   kw["max_det"], keys=self.keys, counts=self.counts, det=self.det, det_count=self.det_count)
             self._scale()
             return
+        cut = None
+        if self.conf_cut and allow_cut:
+            cut = ops.conf_cut_levels(head, kw["conf_thres"], kw["multi_label"], kw["classes"], target=self.cut_target,
+                                      cut=self.cut)
         ops.filter_levels(head, kw["conf_thres"], kw["multi_label"], kw["classes"], cap=int(self.keys.shape[1]),
-                          keys=self.keys, counts=self.counts)
+                          keys=self.keys, counts=self.counts, cut=cut)
         ops.nms_levels(head, self.keys, self.counts, kw["conf_thres"], kw["iou_thres"], kw["agnostic"], kw["max_det"],
-                       det=self.det, det_count=self.det_count)
+                       det=self.det, det_count=self.det_count, cut=cut)
         self._scale()
 
     def _scale(self):
@@ -124,6 +139,11 @@ class PostProcessor:
     def detections(self) -> List[torch.Tensor]:
         """Host-synchronising: list of (n_i, 6) tensors like the reference's non_max_suppression."""
         n = self.det_count.cpu().tolist()
+        if any(v == -2 for v in n) and self._last_head is not None:
+            # the sampled confidence cut left an image with fewer than max_nms candidates: results would not be
+            # guaranteed identical to the reference, so the detection chain is redone without the cut (rare)
+            self._det(self._last_head, allow_cut=False)
+            n = self.det_count.cpu().tolist()
         if any(v < 0 for v in n):
             raise RuntimeError("desenet_b200: candidate buffer overflow (internal capacity error)")
         return [self.det[i, :n[i]].clone() for i in range(self.bs)]

@@ -74,6 +74,27 @@ int dsn_filter_levels(const float *const *raw, const int *ny, const int *nx, int
                       int no, float conf_thres, int multi_label, const uint64_t *class_mask,
                       uint64_t *keys, int64_t cap, int *counts, void *stream);
 
+/* Confidence cut for huge candidate sets (conf 0.001 + multi_label: up to A*nc candidates per image, while the
+ * greedy NMS stops after max_det survivors and never looks past the max_nms best, general.py:728-736).
+ * dsn_conf_cut_levels histograms the confidences of a 1/64 sample of every image (one thread-block cluster per
+ * image, histograms merged over distributed shared memory) and writes, per image, the confidence-key bound
+ * cut_hi[b] above which about 2*target candidates are expected, and cut_dropped[b] = 1 when such a bound exists
+ * (0: the image is expected to have fewer candidates, cut_hi[b] = 0xFFFFFFFF keeps everything).
+ * dsn_filter_levels_cut then emits only candidates at or above that bound - exactly the best ones.  dsn_nms_levels
+ * takes cut_dropped: an image whose NMS runs out of emitted candidates before it stops by itself (max_det
+ * survivors or max_nms candidates consumed) although a cut was in force gets det_count = -2 (dropped candidates
+ * could have mattered) and the caller re-runs without the cut; every other result is exactly the uncut one.
+ * Needs 16-byte aligned planes with ny*nx % 4 == 0 (DSN_E_UNSUPPORTED otherwise: run without a cut).
+ *   target      candidates the NMS is expected to consume at most (e.g. 16*max_det), >= 1
+ *   hist_ws     reserved, may be NULL (the histograms live in shared memory)
+ *   cut_hi / cut_dropped   device (bs) uint32 / int32 */
+int dsn_conf_cut_levels(const float *const *raw, const int *ny, const int *nx, int nl, int bs, int na, int no,
+                        float conf_thres, int multi_label, const uint64_t *class_mask, int target,
+                        unsigned int *hist_ws, unsigned int *cut_hi, int *cut_dropped, void *stream);
+int dsn_filter_levels_cut(const float *const *raw, const int *ny, const int *nx, int nl, int bs, int na,
+                          int no, float conf_thres, int multi_label, const uint64_t *class_mask,
+                          uint64_t *keys, int64_t cap, int *counts, const unsigned int *cut_hi, void *stream);
+
 /* Same filter on an already decoded prediction (bs, A, no) — the input of the reference's
  * non_max_suppression(prediction, ...) (general.py:659). */
 int dsn_filter_z(const float *z, int bs, int64_t A, int no, float conf_thres, int multi_label,
@@ -89,14 +110,16 @@ int dsn_filter_z(const float *z, int bs, int64_t A, int no, float conf_thres, in
  *   iou_thres  compared as torchvision does: (double)iou_fp32 > iou_thres
  *   max_wh     class offset in pixels (4096, general.py:675); agnostic != 0 => offset 0
  *   det        (bs, max_det, 6) fp32, rows >= det_count[i] are left untouched
- *   det_count  (bs) int32; -1 when counts[i] > cap (keys were dropped: retry with a larger cap)
+ *   det_count  (bs) int32; -1 when counts[i] > cap (keys were dropped: retry with a larger cap); -2 when a
+ *              confidence cut was in force and the NMS ran out of emitted candidates (retry without the cut)
+ *   cut_dropped (dsn_nms_levels only) device (bs) int32 written by dsn_conf_cut_levels, or NULL
  * Box source is either the raw levels (dsn_nms_levels: decode on the fly, yolo.py:266-269 +
  * general.py:523-530) or a decoded prediction (dsn_nms_z). */
 int dsn_nms_levels(const float *const *raw, const int *ny, const int *nx, const float *stride,
                    const float *anchor_grid, int nl, int bs, int na, int no,
                    const uint64_t *keys, int64_t cap, const int *counts, float conf_thres,
                    double iou_thres, int agnostic, int max_nms, int max_det, float max_wh,
-                   float *det, int *det_count, void *stream);
+                   const int *cut_dropped, float *det, int *det_count, void *stream);
 
 int dsn_nms_z(const float *z, int bs, int64_t A, int no,
               const uint64_t *keys, int64_t cap, const int *counts, float conf_thres,

@@ -108,3 +108,75 @@ def test_postprocessor_scale_option(env):
         w = w.clone()
         w[:, :4] = port.scale_coords((S, S), w[:, :4], (333, 517), do_round=True)
         assert torch.equal(g.cpu(), w)
+
+
+def test_conf_cut_is_exact(env):
+    """Sampled confidence cut (dsn_conf_cut_levels + dsn_filter_levels_cut): far fewer keys are emitted, the
+    detections are identical to the run without a cut and to the oracle (> max_nms candidates per image)."""
+    api, ops, pipeline = env
+    bs, S, nc, C = 2, 256, 80, 2
+    kw = dict(conf_thres=0.001, iou_thres=0.6, multi_label=True, max_det=300)
+    levels, _, _ = port.synth_head_outputs(bs, S, nc, C, seed=50, with_target=False)
+    dl = [l.cuda() for l in levels]
+    mk = lambda cut: pipeline.PostProcessor(bs, S, nc, C, port.DEFAULT_ANCHORS, port.DEFAULT_STRIDES, mode="det_only",
+                                            conf_cut=cut, **kw)
+    a, b = mk(False), mk(None)
+    assert b.conf_cut and not a.conf_cut            # auto: multi-label and cap = A*nc >= 8 * cut_target
+    a.run(dl)
+    b.run(dl)
+    torch.cuda.synchronize()
+    ca, cb = a.counts.cpu(), b.counts.cpu()
+    assert (ca > 2 * ops.MAX_NMS).all() and (cb >= b.cut_target).all() and (cb < 4 * b.cut_target).all()
+    assert (b.det_count.cpu() >= 0).all()
+    for x, y in zip(a.detections(), b.detections()):
+        assert torch.equal(x, y)
+    ho = api.HeadOutputs(dl, port.DEFAULT_ANCHORS, port.DEFAULT_STRIDES)
+    want = port.non_max_suppression(ho.z[:1].cpu(), nms_impl="c", **kw)
+    assert torch.equal(b.detections()[0].cpu(), want[0])
+    # graph replay with the cut
+    first = b.det.clone()
+    b.det.zero_()
+    b.capture(dl)
+    b.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(b.det, first)
+
+
+def test_conf_cut_fallback_when_sample_misleads(env):
+    """Adversarial input: only the SAMPLED cells (every 64th unit of 4 cells) are confident, so the histogram
+    over-estimates 64x and the cut lands above almost everything; with agnostic NMS the few emitted candidates
+    (same box for all classes of a cell) cannot give max_det survivors, the NMS runs out of emitted candidates
+    -> det_count -2 -> detections() redoes the batch without the cut."""
+    api, ops, pipeline = env
+    bs, S, nc = 2, 256, 80
+    kw = dict(conf_thres=0.001, iou_thres=0.6, multi_label=True, max_det=300, agnostic=True)
+    g = torch.Generator().manual_seed(7)
+    levels = []
+    for s in (8, 16, 32):
+        n = S // s
+        x = torch.randn((bs, 3, nc + 5, n * n), generator=g)
+        x[:, :, 4] = -5.0 + 0.1 * torch.randn((bs, 3, n * n), generator=g)          # passes 0.001, low
+        x[:, :, 5:] = -1.0 + 0.5 * torch.randn((bs, 3, nc, n * n), generator=g)
+        levels.append(x)
+    # sampled units: unit index u = 64*k over the concatenated (level, anchor, cell/4) units of one image
+    off = 0
+    for x in levels:
+        plane = x.shape[-1]
+        for a in range(3):
+            for u in range(plane // 4):
+                if (off + u) % 64 == 0:
+                    x[:, a, 4, 4 * u:4 * u + 4] = 6.0
+                    x[:, a, 5:, 4 * u:4 * u + 4] += 4.0
+            off += plane // 4
+    levels = [x.reshape(bs, 3 * (nc + 5), int(x.shape[-1] ** 0.5), -1).contiguous() for x in levels]
+    dl = [l.cuda() for l in levels]
+    mk = lambda cut: pipeline.PostProcessor(bs, S, nc, 2, port.DEFAULT_ANCHORS, port.DEFAULT_STRIDES, mode="det_only",
+                                            conf_cut=cut, **kw)
+    a, b = mk(False), mk(True)
+    a.run(dl)
+    b.run(dl)
+    torch.cuda.synchronize()
+    assert (b.det_count.cpu() == -2).all()
+    for x, y in zip(a.detections(), b.detections()):
+        assert torch.equal(x, y)
+    assert (b.det_count.cpu() >= 0).all()
