@@ -20,7 +20,7 @@
 namespace dsn {
 
 template <class BoxSrc>
-__global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams p, const BoxSrc src) {
+__global__ void __launch_bounds__(kNmsThreads, 1024 / kNmsThreads) nms_kernel(const NmsParams p, const BoxSrc src) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmsSmem &s = *reinterpret_cast<NmsSmem *>(smem_raw);
     const int b = blockIdx.x;

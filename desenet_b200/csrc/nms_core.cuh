@@ -10,7 +10,10 @@
 
 namespace dsn {
 
-constexpr int kNmsThreads = 1024;
+#ifndef DSN_NMS_THREADS
+#define DSN_NMS_THREADS 512
+#endif
+constexpr int kNmsThreads = DSN_NMS_THREADS;
 constexpr int kChunk = 2048;        // candidates sorted / resolved per round
 constexpr int kBins = 2048;         // histogram bins per refinement level (11 bits)
 constexpr int kBinBits = 11;
@@ -377,8 +380,9 @@ __device__ void nms_image(NmsSmem &s, const NmsParams &p, const BoxSrc &src, int
                 s.roff[threadIdx.x] = threadIdx.x < cnt ? s.off[s0 + threadIdx.x] : 0.f;
             }
             if (threadIdx.x < kRound / 32) { s.dead[threadIdx.x] = 0u; s.nz[threadIdx.x] = 0u; }
-            static_assert(kRound * kWords == kNmsThreads, "one mask word per thread");
-            (&s.mask[0][0])[threadIdx.x] = 0ull;
+            static_assert((kRound * kWords) % kNmsThreads == 0, "mask words split evenly over the CTA");
+#pragma unroll
+            for (int i = 0; i < kRound * kWords / kNmsThreads; ++i) (&s.mask[0][0])[threadIdx.x + i * kNmsThreads] = 0ull;
             __syncthreads();
             DSN_LAP(37);   // round setup
             // (a) against the survivors so far: candidate = tid % kRound, the thread groups stride the kept list
