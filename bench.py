@@ -223,7 +223,7 @@ def main():
     ap.add_argument("--prewarm-ms", type=float, default=600.0)
     ap.add_argument("--two-kernel-det", action="store_true", help="filter + NMS as two launches instead of the fused kernel")
     ap.add_argument("--fused-det", action="store_true", help="use the fused single-launch detection kernel")
-    ap.add_argument("--in-flight", type=int, default=2, help="independent batches in flight (one CUDA stream + workspace each)")
+    ap.add_argument("--in-flight", type=int, default=3, help="independent batches in flight (one CUDA stream + workspace each)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -23,6 +23,7 @@ __all__ = [
     "HeadOutputs", "SegLogits", "detect_forward", "non_max_suppression", "segoutput_to_target",
     "batch_pix_accuracy", "batch_intersection_union", "seg_confusion_matrix", "seg_stats_from_cm",
     "seg_validation", "xywh2xyxy", "scale_coords", "clip_coords", "box_iou", "process_batch",
+    "ap_per_class", "compute_ap", "ConfusionMatrix",
 ]
 
 
@@ -183,6 +184,86 @@ def process_batch(detections, labels, iouv):
     off = torch.tensor([0, m], dtype=torch.int32, device=detections.device)
     c = ops.process_batch(detections, None, labels.float().contiguous(), off, iouv.float().contiguous(), m)
     return c[0].bool()
+
+
+# ------------------------------------------------------------------------------------------------
+# f3  ap_per_class / compute_ap / ConfusionMatrix   core/utils/metrics.py:31-170
+# ------------------------------------------------------------------------------------------------
+def _to_device(a, dtype, device):
+    t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+    return t.to(device=device, dtype=dtype, non_blocking=True)
+
+
+def _stats_device(*arrays):
+    for a in arrays:
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            return a.device
+    if not torch.cuda.is_available():
+        raise RuntimeError("desenet_b200: ap_per_class needs a CUDA device; this package has no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def ap_per_class(tp, conf, pred_cls, target_cls, plot=False, save_dir='.', names=()):
+    """Same signature and result as the reference (metrics.py:31-92): ``(p, r, ap, f1, unique_classes)`` as numpy
+    arrays.  Inputs may be numpy arrays (what val.py:282 hands over) or torch tensors; the sort, the cumulative
+    counts, the AP integration and the 1000-point precision / recall curves run on the device, bit-identical to the
+    reference's numpy float64 arithmetic.  The (ncls, 1000) F1 tail (metrics.py:85-91) is evaluated here from the
+    device curves.  ``plot`` is not supported (plotting is out of scope); equal confidences keep their input order."""
+    if plot:
+        raise NotImplementedError("desenet_b200.ap_per_class: plotting (metrics.py:82-88) is out of scope")
+    dev = _stats_device(tp, conf, pred_cls, target_cls)
+    conf_d = _to_device(conf, torch.float32, dev).reshape(-1)
+    n = int(conf_d.shape[0])
+    tp_d = tp if isinstance(tp, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(tp))
+    tp_d = (tp_d != 0).to(dev).reshape(n, int(tp_d.shape[1]) if tp_d.dim() == 2 else 1)
+    pred_d = _to_device(pred_cls, torch.float32, dev).reshape(-1)
+    tgt_d = _to_device(target_cls, torch.float32, dev).reshape(-1)
+    classes, n_labels = torch.unique(tgt_d, return_counts=True)                    # metrics.py:52,59 (sorted ascending)
+    ap, p, r = ops.ap_per_class_device(tp_d, conf_d, pred_d, classes, n_labels)
+    ap, p, r = ap.cpu().numpy(), p.cpu().numpy(), r.cpu().numpy()
+    f1 = 2 * p * r / (p + r + 1e-16)                                               # metrics.py:85
+    i = f1.mean(0).argmax() if f1.shape[0] else 0                                  # metrics.py:90
+    return p[:, i], r[:, i], ap, f1[:, i], classes.cpu().numpy().astype('int32')
+
+
+def compute_ap(recall, precision):
+    """metrics.py:95-121: ``(ap, mpre, mrec)`` for one recall / precision curve (numpy in, numpy out; the envelope,
+    the 101-point interpolation and the trapezoid sum run on the device)."""
+    dev = _stats_device(recall, precision)
+    rec = _to_device(recall, torch.float64, dev).reshape(-1)
+    pre = _to_device(precision, torch.float64, dev).reshape(-1)
+    ap, env = ops.compute_ap_device(rec, pre)
+    n = int(rec.shape[0])
+    e = env[:n].cpu().numpy()
+    mpre = np.concatenate(([max(1.0, float(e[0])) if n else 1.0], e, [0.0]))
+    mrec = np.concatenate(([0.0], rec.cpu().numpy(), [1.0]))
+    return float(ap.item()), mpre, mrec
+
+
+class ConfusionMatrix:
+    """Detection confusion matrix with the reference's interface (metrics.py:124-172; plot / print out of scope).
+    ``process_batch(detections, labels)`` takes one image like the reference; ``process_images`` takes the batched
+    NMS output buffers so that a whole batch is one launch and nothing is copied to the host."""
+
+    def __init__(self, nc, conf=0.25, iou_thres=0.45, device=None):
+        self.nc, self.conf, self.iou_thres = int(nc), conf, iou_thres
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._m = torch.zeros((self.nc + 1, self.nc + 1), dtype=torch.int64, device=self.device)
+
+    def process_batch(self, detections, labels):
+        det = detections.to(self.device, torch.float32)
+        lab = labels.to(self.device, torch.float32).reshape(-1, 5)
+        off = torch.tensor([0, lab.shape[0]], dtype=torch.int32, device=self.device)
+        det = det.contiguous() if det.numel() else det.new_zeros((0, 6))
+        ops.det_confusion_matrix_(self._m, det, None, lab, off, int(lab.shape[0]), self.nc, self.conf, self.iou_thres)
+
+    def process_images(self, det, det_count, labels, label_off, max_labels_per_image):
+        ops.det_confusion_matrix_(self._m, det, det_count, labels, label_off, max_labels_per_image, self.nc, self.conf,
+                                  self.iou_thres)
+
+    def matrix(self):
+        """(nc+1, nc+1) float64 numpy array like the reference's ``self.matrix`` (metrics.py:127)."""
+        return self._m.cpu().numpy().astype(np.float64)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -7,6 +7,7 @@ import ctypes
 from ctypes import c_float, c_int, c_uint64, c_void_p
 from typing import List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -384,3 +385,88 @@ def process_batch(det: torch.Tensor, det_count: Optional[torch.Tensor], labels: 
                                    _stream(det.device))
     _lib.check(rc, "dsn_process_batch")
     return correct
+
+
+# ------------------------------------------------------------------------------------------------
+# ap_per_class / compute_ap / detection ConfusionMatrix     core/utils/metrics.py:31-170
+# ------------------------------------------------------------------------------------------------
+_LINSPACE = {}
+
+
+def _linspace_f64(num: int, device) -> torch.Tensor:
+    """np.linspace(0, 1, num) exactly as numpy produces it (the grids metrics.py:56,114 interpolate on)."""
+    key = (num, str(device))
+    if key not in _LINSPACE:
+        _LINSPACE[key] = torch.from_numpy(np.linspace(0, 1, num)).to(device)
+    return _LINSPACE[key]
+
+
+def ap_per_class_device(tp: torch.Tensor, conf: torch.Tensor, pred_cls: torch.Tensor, classes: torch.Tensor,
+                        n_labels: torch.Tensor, npx: int = 1000):
+    """metrics.py:47-79 on the device -> (ap (ncls, niou), p (ncls, npx), r (ncls, npx)) float64 CUDA tensors."""
+    lib = _lib.load()
+    dev = conf.device
+    if not conf.is_cuda:
+        raise RuntimeError("desenet_b200: ap_per_class_device needs CUDA tensors; this package has no CPU path")
+    n = int(conf.shape[0])
+    tp = tp.reshape(n, int(tp.shape[1]) if tp.dim() == 2 else 1)
+    tp = (tp if tp.dtype in (torch.uint8, torch.bool) else (tp != 0)).contiguous().view(torch.uint8)
+    niou = int(tp.shape[1])
+    conf = _require_cuda(conf.reshape(-1), "conf")
+    pred_cls = _require_cuda(pred_cls.reshape(-1), "pred_cls")
+    classes = _require_cuda(classes.reshape(-1), "classes")
+    n_labels = _require_cuda(n_labels.reshape(-1), "n_labels", torch.int64)
+    ncls = int(classes.shape[0])
+    with torch.cuda.device(dev):
+        ap = torch.zeros((ncls, niou), dtype=torch.float64, device=dev)
+        p = torch.zeros((ncls, npx), dtype=torch.float64, device=dev)
+        r = torch.zeros((ncls, npx), dtype=torch.float64, device=dev)
+        if ncls == 0:
+            return ap, p, r
+        nbytes = int(lib.dsn_ap_workspace_bytes(n, niou, ncls))
+        if nbytes < 0:
+            raise ValueError(f"ap_per_class: unsupported sizes n={n} niou={niou} ncls={ncls}")
+        ws = torch.empty((nbytes + 255,), dtype=torch.uint8, device=dev)
+        base = (ws.data_ptr() + 255) // 256 * 256
+        rc = lib.dsn_ap_per_class(_ptr(tp), _ptr(conf), _ptr(pred_cls), n, niou, _ptr(classes), _ptr(n_labels), ncls,
+                                  _ptr(_linspace_f64(101, dev)), _ptr(_linspace_f64(npx, dev)), npx, c_void_p(base), nbytes,
+                                  _ptr(ap), _ptr(p), _ptr(r), _stream(dev))
+        _lib.check(rc, "dsn_ap_per_class")
+        ws.record_stream(torch.cuda.current_stream(dev))
+    return ap, p, r
+
+
+def compute_ap_device(recall: torch.Tensor, precision: torch.Tensor) -> torch.Tensor:
+    """metrics.py:95-121 for one curve -> (1,) float64 CUDA tensor."""
+    lib = _lib.load()
+    recall = _require_cuda(recall.reshape(-1), "recall", torch.float64)
+    precision = _require_cuda(precision.reshape(-1), "precision", torch.float64)
+    dev = recall.device
+    n = int(recall.shape[0])
+    with torch.cuda.device(dev):
+        env = torch.empty((max(n, 1),), dtype=torch.float64, device=dev)
+        ap = torch.zeros((1,), dtype=torch.float64, device=dev)
+        rc = lib.dsn_compute_ap(_ptr(recall), _ptr(precision), n, _ptr(_linspace_f64(101, dev)), _ptr(env), _ptr(ap), _stream(dev))
+    _lib.check(rc, "dsn_compute_ap")
+    return ap, env
+
+
+def det_confusion_matrix_(matrix: torch.Tensor, det: torch.Tensor, det_count: Optional[torch.Tensor], labels: torch.Tensor,
+                          label_off: torch.Tensor, max_labels_per_image: int, nc: int, conf: float = 0.25,
+                          iou_thres: float = 0.45) -> torch.Tensor:
+    """metrics.py:132-170 for a batch, accumulating into ``matrix`` ((nc+1, nc+1) int64 CUDA tensor)."""
+    lib = _lib.load()
+    det = det if det.dim() == 3 else det.unsqueeze(0)
+    if not det.is_cuda or det.dtype != torch.float32 or (det.numel() and det.stride(2) != 1):
+        raise RuntimeError("desenet_b200: det must be a float32 CUDA tensor with contiguous rows; there is no CPU path")
+    bs, rows = int(det.shape[0]), int(det.shape[1])
+    labels = _require_cuda(labels.reshape(-1, 5), "labels")
+    label_off = _require_cuda(label_off, "label_off", torch.int32)
+    matrix = _require_cuda(matrix, "matrix", torch.int64)
+    assert tuple(matrix.shape) == (nc + 1, nc + 1)
+    with torch.cuda.device(det.device):
+        rc = lib.dsn_det_confusion_matrix(_ptr(det), int(det.stride(0)), int(det.stride(1)) if rows else 6, _ptr(det_count), bs,
+                                          rows, _ptr(labels), _ptr(label_off), int(max_labels_per_image), int(nc),
+                                          float(np.float32(conf)), float(np.float32(iou_thres)), _ptr(matrix), _stream(det.device))
+    _lib.check(rc, "dsn_det_confusion_matrix")
+    return matrix

@@ -203,6 +203,39 @@ int dsn_process_batch(const float *det, int64_t det_image_stride, int64_t det_ro
                       int bs, int max_rows, const float *labels, const int *label_off, int max_labels_per_image,
                       const float *iouv, int niou, unsigned char *correct, void *stream);
 
+/* ---- end-of-eval detection statistics ------------------------------------------------
+ * ap_per_class (core/utils/metrics.py:31-92) over ALL detections of an evaluation, on the device:
+ *   tp          device (n, niou) uint8/bool: detection i is a true positive at IoU threshold j (val.py:121,263)
+ *   conf        device (n) fp32 confidences; pred_cls device (n) fp32 predicted classes
+ *   classes     device (ncls) fp32: the unique TARGET classes, ascending (np.unique(target_cls), metrics.py:52)
+ *   n_labels    device (ncls) int64: labels per class (metrics.py:59)
+ *   x101, px    device float64: np.linspace(0, 1, 101) and np.linspace(0, 1, npx) (npx = 1000, metrics.py:56,114)
+ *   workspace   device, 256-byte aligned, dsn_ap_workspace_bytes(n, niou, ncls) bytes
+ *   ap          device (ncls, niou) float64 = metrics.py:79;  p, r device (ncls, npx) float64 = metrics.py:71,75
+ * Bit-identical to the reference's numpy float64 results (np.interp / np.trapz restated operation by operation);
+ * equal confidences keep their input order where the reference's quicksort (metrics.py:48) leaves it open.
+ * Limits: n < 2^24, ncls < 255, niou <= 16.  The F1 curve / its argmax (metrics.py:85-91) are a (ncls, npx)
+ * elementwise tail the host mirror evaluates from p and r. */
+int64_t dsn_ap_workspace_bytes(int64_t n, int niou, int ncls);
+int dsn_ap_per_class(const uint8_t *tp, const float *conf, const float *pred_cls, int64_t n, int niou,
+                     const float *classes, const int64_t *n_labels, int ncls, const double *x101, const double *px,
+                     int npx, void *workspace, int64_t workspace_bytes, double *ap, double *p, double *r, void *stream);
+
+/* compute_ap (metrics.py:95-121, 'interp' method) of one recall / precision curve (device float64 arrays of n
+ * points): precision envelope into env_ws (n doubles), 101-point interpolation, trapezoid sum -> ap[0]. */
+int dsn_compute_ap(const double *recall, const double *precision, int64_t n, const double *x101, double *env_ws,
+                   double *ap, void *stream);
+
+/* ConfusionMatrix.process_batch (metrics.py:132-170) for a whole batch, one CTA per image; det / det_count / labels /
+ * label_off as for dsn_process_batch.  matrix: device (nc+1, nc+1) uint64, rows = predicted class (nc = background),
+ * columns = true class, ACCUMULATED.  Detections with conf <= `conf` are ignored, pairs need IoU > iou_thres (both
+ * compared in fp32 as torch does); equal IoUs resolve to the lowest index (the reference's order there depends on
+ * numpy's unstable argsort); classes outside [0, nc] are skipped (the reference would raise or wrap). */
+int dsn_det_confusion_matrix(const float *det, int64_t det_image_stride, int64_t det_row_stride, const int *det_count,
+                             int bs, int max_rows, const float *labels, const int *label_off,
+                             int max_labels_per_image, int nc, float conf, float iou_thres, uint64_t *matrix,
+                             void *stream);
+
 #ifdef __cplusplus
 }
 #endif

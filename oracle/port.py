@@ -439,6 +439,137 @@ def process_batch(detections: torch.Tensor, labels: torch.Tensor, iouv: torch.Te
 
 
 # --------------------------------------------------------------------------------------------
+# ap_per_class / compute_ap (metrics.py:31-121) and the detection ConfusionMatrix
+# (metrics.py:124-170).  The float64 arithmetic of np.interp / np.trapz is restated operation by operation (plain
+# Python floats = IEEE binary64, no FMA) so that the CUDA kernels have a bit-level specification; the restatement is
+# pinned against fixtures generated by the reference itself (tests/golden/make_golden_stats.py).
+# --------------------------------------------------------------------------------------------
+def interp_scalar(x: float, xp, fp, left: float, right: float) -> float:
+    """numpy's arr_interp for one x: j = last index with xp[j] <= x; slope form with the NaN retries."""
+    n = len(xp)
+    if x != x:
+        return x
+    if x > xp[n - 1]:
+        return right
+    if x < xp[0]:
+        return left
+    j = int(np.searchsorted(xp, x, side="right")) - 1
+    if j == n - 1:
+        return float(fp[j])
+    if xp[j] == x:
+        return float(fp[j])
+    slope = (float(fp[j + 1]) - float(fp[j])) / (float(xp[j + 1]) - float(xp[j]))
+    res = slope * (x - float(xp[j])) + float(fp[j])
+    if res != res:
+        res = slope * (x - float(xp[j + 1])) + float(fp[j + 1])
+        if res != res and fp[j] == fp[j + 1]:
+            res = float(fp[j])
+    return res
+
+
+def pairwise_sum_small(a) -> float:
+    """numpy's pairwise add.reduce for a contiguous float64 vector of fewer than 128 elements."""
+    n = len(a)
+    a = [float(v) for v in a]
+    if n < 8:
+        res = 0.0 if n == 0 else a[0]          # numpy starts from the first element
+        for v in a[1:]:
+            res += v
+        return res
+    assert n <= 128
+    r = a[:8]
+    i = 8
+    while i < n - (n % 8):
+        for k in range(8):
+            r[k] += a[i + k]
+        i += 8
+    res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]))
+    while i < n:
+        res += a[i]
+        i += 1
+    return res
+
+
+def compute_ap(recall, precision) -> float:
+    """metrics.py:95-121 ('interp' method): sentinels, precision envelope, 101-point interpolation, trapezoid sum."""
+    mrec = np.concatenate(([0.0], np.asarray(recall, dtype=np.float64), [1.0]))
+    mpre = np.concatenate(([1.0], np.asarray(precision, dtype=np.float64), [0.0]))
+    mpre = np.maximum.accumulate(mpre[::-1])[::-1]
+    x = np.linspace(0, 1, 101)
+    y = [interp_scalar(float(v), mrec, mpre, float(mpre[0]), float(mpre[-1])) for v in x]
+    terms = [(float(x[k + 1]) - float(x[k])) * (y[k + 1] + y[k]) / 2.0 for k in range(100)]
+    return pairwise_sum_small(terms)
+
+
+def ap_per_class(tp, conf, pred_cls, target_cls):
+    """metrics.py:31-92 without the plots.  Equal confidences keep their input order (stable sort) where the
+    reference's default quicksort leaves the order implementation-defined.  Returns (p, r, ap, f1, classes)."""
+    tp = np.asarray(tp)
+    tp = tp.reshape(len(conf), tp.shape[1] if tp.ndim == 2 else 1)
+    order = np.argsort(-np.asarray(conf), kind="stable")
+    tp, conf, pred_cls = tp[order], np.asarray(conf)[order], np.asarray(pred_cls)[order]
+    classes = np.unique(target_cls)
+    nc, niou = classes.shape[0], tp.shape[1]
+    px = np.linspace(0, 1, 1000)
+    ap, p, r = np.zeros((nc, niou)), np.zeros((nc, 1000)), np.zeros((nc, 1000))
+    for ci, c in enumerate(classes):
+        sel = pred_cls == c
+        n_l, n_p = int((np.asarray(target_cls) == c).sum()), int(sel.sum())
+        if n_p == 0 or n_l == 0:
+            continue
+        tpc = tp[sel].astype(np.int64).cumsum(0)
+        cnt = np.arange(1, n_p + 1, dtype=np.int64)[:, None]            # tpc + fpc
+        recall = tpc / (n_l + 1e-16)
+        precision = tpc / cnt
+        xp = -conf[sel].astype(np.float64)
+        r[ci] = [interp_scalar(-float(v), xp, recall[:, 0], 0.0, float(recall[-1, 0])) for v in px]
+        p[ci] = [interp_scalar(-float(v), xp, precision[:, 0], 1.0, float(precision[-1, 0])) for v in px]
+        for j in range(niou):
+            ap[ci, j] = compute_ap(recall[:, j], precision[:, j])
+    f1 = 2 * p * r / (p + r + 1e-16)
+    i = f1.mean(0).argmax()
+    return p[:, i], r[:, i], ap, f1[:, i], classes.astype("int32")
+
+
+def det_confusion_matrix(matrix: np.ndarray, detections: torch.Tensor, labels: torch.Tensor, nc: int, conf: float = 0.25,
+                         iou_thres: float = 0.45) -> np.ndarray:
+    """Canonical restatement of ConfusionMatrix.process_batch (metrics.py:132-170) without the numpy sorts: every
+    detection above `conf` picks its best-IoU label (IoU > iou_thres; ties: lowest label), every label keeps its
+    best-IoU such detection (ties: lowest detection); matched label -> matrix[det class, gt class], unmatched label
+    -> matrix[nc, gt class]; detections left over -> matrix[det class, nc], but only if the image had any match
+    (metrics.py:165-168).  Updates and returns `matrix` ((nc+1, nc+1), rows = predicted)."""
+    det = detections[detections[:, 4] > conf]
+    gt = labels[:, 0].int().tolist()
+    dc = det[:, 5].int().tolist()
+    n, m = det.shape[0], labels.shape[0]
+    match_of_label = {}
+    if n and m:
+        iou = box_iou(labels[:, 1:], det[:, :4])
+        thr = torch.tensor(iou_thres, dtype=torch.float32)
+        best = {}
+        for d in range(n):
+            cand = [(float(iou[l, d]), -l) for l in range(m) if iou[l, d] > thr]
+            if cand:
+                v, negl = max(cand)
+                best[d] = (-negl, v)
+        for d, (l, v) in best.items():
+            if l not in match_of_label or (v, -d) > (match_of_label[l][1], -match_of_label[l][0]):
+                match_of_label[l] = (d, v)
+    any_match = len(match_of_label) > 0
+    for l, gc in enumerate(gt):
+        if l in match_of_label:
+            matrix[dc[match_of_label[l][0]], gc] += 1
+        else:
+            matrix[nc, gc] += 1
+    if any_match:
+        used = {d for d, _ in match_of_label.values()}
+        for d, c in enumerate(dc):
+            if d not in used:
+                matrix[c, nc] += 1
+    return matrix
+
+
+# --------------------------------------------------------------------------------------------
 # Synthetic inputs (SURVEY §8d): family T (throughput) — seeded, device-independent (CPU RNG)
 # --------------------------------------------------------------------------------------------
 def synth_head_outputs(bs: int, S: int, nc: int, C: int = 2, seed: int = 0, obj_mean: float = -4.0,
