@@ -144,6 +144,33 @@ def install(model: Optional[nn.Module] = None, fused: bool = True, modules: Opti
 
         scale_coords._dsn_dispatch = True
         h._set(mod, "scale_coords", scale_coords)
+    # detection metrics: CUDA tensors go to the kernels; ap_per_class takes the device path whenever
+    # a GPU is present and no plot is requested (plotting stays with the reference)
+    def _cuda_f32(*ts):
+        return all(isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 for t in ts)
+
+    for name in (modules or _MODULES):
+        mod = sys.modules.get(name)
+        if mod is None:
+            continue
+        for fn in ("box_iou", "process_batch", "ap_per_class"):
+            orig = getattr(mod, fn, None)
+            if orig is None or getattr(orig, "_dsn_dispatch", False):
+                continue
+            if fn == "box_iou":
+                def repl(box1, box2, _orig=orig):
+                    return api.box_iou(box1, box2) if _cuda_f32(box1, box2) else _orig(box1, box2)
+            elif fn == "process_batch":
+                def repl(detections, labels, iouv, _orig=orig):
+                    return api.process_batch(detections, labels, iouv) if _cuda_f32(detections, labels, iouv) else _orig(detections, labels, iouv)
+            else:
+                def repl(tp, conf, pred_cls, target_cls, plot=False, save_dir='.', names=(), _orig=orig):
+                    if plot or not torch.cuda.is_available():
+                        return _orig(tp, conf, pred_cls, target_cls, plot=plot, save_dir=save_dir, names=names)
+                    return api.ap_per_class(tp, conf, pred_cls, target_cls)
+            repl._dsn_dispatch = True
+            repl.__name__ = fn
+            h._set(mod, fn, repl)
     if model is not None:
         patched_classes = set()
         for m in model.modules():

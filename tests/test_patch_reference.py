@@ -20,6 +20,7 @@ def test_install_and_uninstall(ref):
     from desenet_b200 import api, patch
     import core.models.common as common
     orig_nms = ref.general.non_max_suppression
+    orig_box_iou = ref.general.box_iou
     torch.manual_seed(0)
     model = ref_shim.build_desenet_s(n_segcls=2)
     det, seg = model.model[-1], model.model[-2]
@@ -43,7 +44,12 @@ def test_install_and_uninstall(ref):
         assert torch.equal(z0, z1) and torch.equal(s0, s1) and all(torch.equal(a, b) for a, b in zip(x0, x1))
         with pytest.raises(RuntimeError, match="CUDA"):
             ref.general.non_max_suppression(z1)
+        # detection-metric dispatchers: CPU tensors still reach the reference's own code
+        assert getattr(ref.metrics.ap_per_class, "_dsn_dispatch", False) and getattr(ref.general.box_iou, "_dsn_dispatch", False)
+        b = torch.tensor([[0., 0., 10., 10.], [5., 5., 15., 15.]])
+        assert torch.equal(ref.general.box_iou(b, b), orig_box_iou(b, b))
     finally:
         h.uninstall()
     assert ref.general.non_max_suppression is orig_nms and common.non_max_suppression is orig_nms
+    assert ref.general.box_iou is orig_box_iou
     assert type(det).forward is orig_forward and seg.out[4] is orig_up
