@@ -430,7 +430,8 @@ def main():
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(f"cfg{args.config}", {}).get(dom)
+            traffic = json.load(f).get(f"cfg{args.config}", {}).get(dom)          # bytes per image (profiles/summarize.py)
+            traffic = traffic * bs if traffic is not None else None
     except Exception:
         pass
     roofline = {
