@@ -223,6 +223,7 @@ def main():
     ap.add_argument("--prewarm-ms", type=float, default=600.0)
     ap.add_argument("--two-kernel-det", action="store_true", help="filter + NMS as two launches instead of the fused kernel")
     ap.add_argument("--fused-det", action="store_true", help="use the fused single-launch detection kernel")
+    ap.add_argument("--time-fused", action="store_true", help="also time the fused detection kernel alone (kernels_us.det_fused)")
     ap.add_argument("--in-flight", type=int, default=3, help="independent batches in flight (one CUDA stream + workspace each)")
     args = ap.parse_args()
 
@@ -416,7 +417,8 @@ def main():
         kern_us["filter"] = time_alone(k_filter, reps)
     k_filter(0)
     kern_us["nms"] = time_alone(k_nms, reps)
-    kern_us["det_fused"] = time_alone(k_det_fused, reps)
+    if args.time_fused or pp.fused_det:      # the opt-in single-launch detection kernel, for comparison (not part of the step)
+        kern_us["det_fused"] = time_alone(k_det_fused, reps)
     if mode != "det_only":
         kern_us["seg"] = time_alone(k_seg, reps)
 
@@ -435,7 +437,7 @@ def main():
     except Exception:
         pass
     roofline = {
-        "bound": "hbm", "kernel": {"seg": "seg_fused_tile_kernel", "filter": "filter_levels_kernel"}[dom],
+        "bound": "hbm", "kernel": {"seg": "seg_fused_rows_kernel", "filter": "filter_dense_kernel" if kw["multi_label"] else "filter_levels_kernel"}[dom],
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
         "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "us_per_launch": kern_us[dom],
         "kernels_us": kern_us,

@@ -86,16 +86,13 @@ __global__ void __launch_bounds__(kFilterThreads) filter_levels_kernel(const Hea
     __shared__ unsigned int list_cell[kFilterThreads * kFilterUnroll * V];
     __shared__ float list_obj[kFilterThreads * kFilterUnroll * V];
     __shared__ unsigned int list_n;
-    const int b = blockIdx.y;
-    int l = 0;
-    while (l + 1 < g.nl && (int)blockIdx.x >= g.cta_off[l + 1]) ++l;
-    const int cp = blockIdx.x - g.cta_off[l];
-    const int a = cp / g.ctas_per_plane[l];
-    const int tile = cp - a * g.ctas_per_plane[l];
-    const int plane = g.plane[l];
+    const int b = blockIdx.z, a = blockIdx.y;
+    const TileGeom tg = tile_geom(g, (int)blockIdx.x);
+    const int tile = tg.tile;
+    const int plane = tg.plane;
     const int units = plane / V;
-    const float *pbase = g.raw[l] + ((size_t)(b * g.na + a) * g.no) * plane;
-    const unsigned int prow0 = (unsigned)(g.row_off[l] + a * plane);
+    const float *pbase = tg.raw + ((size_t)(b * g.na + a) * g.no) * plane;
+    const unsigned int prow0 = (unsigned)(tg.row_off + a * plane);
     const int u0 = tile * (kFilterThreads * kFilterUnroll) + threadIdx.x;
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) list_n = 0u;
@@ -189,19 +186,16 @@ __global__ void __launch_bounds__(kDenseThreads, 3) filter_dense_kernel(const He
                                                                                    const float obj_logit_hi) {
     extern __shared__ __align__(16) unsigned char dense_smem_raw[];
     DenseSmem &sm = *reinterpret_cast<DenseSmem *>(dense_smem_raw);
-    const int b = blockIdx.y;
-    int l = 0;
-    while (l + 1 < g.nl && (int)blockIdx.x >= g.cta_off[l + 1]) ++l;
-    const int cp = blockIdx.x - g.cta_off[l];
-    const int a = cp / g.ctas_per_plane[l];
-    const int tile = cp - a * g.ctas_per_plane[l];
-    const int plane = g.plane[l];
+    const int b = blockIdx.z, a = blockIdx.y;
+    const TileGeom tg = tile_geom(g, (int)blockIdx.x);
+    const int tile = tg.tile;
+    const int plane = tg.plane;
     const int nc = g.no - 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cell0 = tile * kDenseCells + threadIdx.x * 4;       // plane % 4 == 0: the 4 cells are all in or all out
     const bool in = cell0 < plane;
-    const float *pbase = g.raw[l] + ((size_t)(b * g.na + a) * g.no) * plane + (in ? cell0 : 0);
-    const unsigned int row0 = (unsigned)(g.row_off[l] + a * plane + tile * kDenseCells + warp * 128);   // warp's first row
+    const float *pbase = tg.raw + ((size_t)(b * g.na + a) * g.no) * plane + (in ? cell0 : 0);
+    const unsigned int row0 = (unsigned)(tg.row_off + a * plane + tile * kDenseCells + warp * 128);   // warp's first row
     const unsigned int cut = f.cut_hi ? f.cut_hi[b] : 0xFFFFFFFFu;
     const float cut_conf = __uint_as_float(~cut);                 // keys <= cut  <=>  conf >= cut_conf  (0 when no cut)
     const float t_lo = fmaxf(f.conf_thres, cut_conf) * 0.999f;
@@ -586,7 +580,7 @@ extern "C" __attribute__((visibility("default"))) int dsn_filter_levels_cut(cons
     for (int l = 0; l < nl; ++l) {
         g.cta_off[l] = ctas;
         g.ctas_per_plane[l] = (g.plane[l] / V + kFilterThreads * kFilterUnroll - 1) / (kFilterThreads * kFilterUnroll);
-        ctas += na * g.ctas_per_plane[l];
+        ctas += g.ctas_per_plane[l];
     }
     g.cta_off[nl] = ctas;
     const float lo = obj_logit_lower_bound(conf_thres);
@@ -595,16 +589,16 @@ extern "C" __attribute__((visibility("default"))) int dsn_filter_levels_cut(cons
         for (int l = 0; l < nl; ++l) {
             g.cta_off[l] = ctas;
             g.ctas_per_plane[l] = (g.plane[l] + kDenseCells - 1) / kDenseCells;
-            ctas += na * g.ctas_per_plane[l];
+            ctas += g.ctas_per_plane[l];
         }
         g.cta_off[nl] = ctas;
         static DeviceOnce once;
         if (int rc2 = raise_dynamic_smem(once, filter_dense_kernel, (int)sizeof(DenseSmem))) return rc2;
-        filter_dense_kernel<<<dim3(ctas, bs), kDenseThreads, sizeof(DenseSmem), st>>>(g, f, lo, obj_logit_upper_bound(conf_thres));
+        filter_dense_kernel<<<dim3(ctas, na, bs), kDenseThreads, sizeof(DenseSmem), st>>>(g, f, lo, obj_logit_upper_bound(conf_thres));
         DSN_CHECK_LAUNCH();
         return DSN_OK;
     }
-    dim3 grid(ctas, bs);
+    dim3 grid(ctas, na, bs);
     if (vec) filter_levels_kernel<4><<<grid, kFilterThreads, 0, st>>>(g, f, lo);
     else filter_levels_kernel<1><<<grid, kFilterThreads, 0, st>>>(g, f, lo);
     DSN_CHECK_LAUNCH();

@@ -25,7 +25,10 @@ struct FilterOut {
 };
 
 __device__ __forceinline__ bool class_allowed(const FilterOut &f, int cls) {
-    return !f.use_cmask || ((f.cmask[(cls >> 6) & 3] >> (cls & 63)) & 1ull);
+    if (!f.use_cmask) return true;
+    const int w = (cls >> 6) & 3;            // static indices: a dynamic one would put the by-value parameter in local memory
+    const unsigned long long m = w == 0 ? f.cmask[0] : (w == 1 ? f.cmask[1] : (w == 2 ? f.cmask[2] : f.cmask[3]));
+    return (m >> (cls & 63)) & 1ull;
 }
 
 // Warp-aggregated slot allocation: every lane passes its emission count; returns the lane's first

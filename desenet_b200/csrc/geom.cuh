@@ -9,8 +9,8 @@ struct HeadGeom {
     int ny[DSN_MAX_LEVELS], nx[DSN_MAX_LEVELS], plane[DSN_MAX_LEVELS];
     int row_off[DSN_MAX_LEVELS + 1];    // first row of the level inside z (per image); [nl] = A
     int unit_off[DSN_MAX_LEVELS + 1];   // fused kernel: first work unit (V cells) of the level
-    int cta_off[DSN_MAX_LEVELS + 1];    // filter kernel: first CTA of the level (per image)
-    int ctas_per_plane[DSN_MAX_LEVELS]; // filter kernel: CTAs covering one (level, anchor) plane
+    int cta_off[DSN_MAX_LEVELS + 1];    // filter kernels: first blockIdx.x of the level (grid = tiles x anchors x images)
+    int ctas_per_plane[DSN_MAX_LEVELS]; // filter kernels: CTAs covering one (level, anchor) plane
     int tile_off[DSN_MAX_LEVELS + 1];   // decode kernel: first tile of the level
     float stride[DSN_MAX_LEVELS];
     float anchor_w[DSN_MAX_LEVELS][DSN_MAX_ANCHORS], anchor_h[DSN_MAX_LEVELS][DSN_MAX_ANCHORS];
@@ -50,6 +50,25 @@ static inline int make_geom(HeadGeom &g, const float *const *raw, const int *ny,
     g.row_off[nl] = (int)rows;
     g.A = (int)rows;
     return DSN_OK;
+}
+
+// Level of a filter CTA from blockIdx.x, with STATIC indices into the by-value kernel parameter (dynamic indexing would
+// make the compiler copy the arrays to local memory) and no integer division: the anchor is blockIdx.y.
+struct TileGeom {
+    const float *raw;
+    int plane, row_off, tile;
+};
+__device__ __forceinline__ TileGeom tile_geom(const HeadGeom &g, int x) {
+    TileGeom t{g.raw[0], g.plane[0], g.row_off[0], x};
+#pragma unroll
+    for (int i = 1; i < DSN_MAX_LEVELS; ++i)
+        if (i < g.nl && x >= g.cta_off[i]) {
+            t.raw = g.raw[i];
+            t.plane = g.plane[i];
+            t.row_off = g.row_off[i];
+            t.tile = x - g.cta_off[i];
+        }
+    return t;
 }
 
 // (level, anchor, cell) of a row index inside one image, without integer division (nl, na are small).
