@@ -43,12 +43,13 @@ SIGNATURES = {
     "dsn_box_iou": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "dsn_process_batch": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                   c_int, c_void_p, c_void_p]),
+    "dsn_labels_to_native": (c_int, [c_void_p, c_int64, c_float, c_float, c_void_p, c_int, c_void_p, c_void_p]),
     "dsn_ap_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
     "dsn_ap_per_class": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                  c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dsn_compute_ap": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dsn_det_confusion_matrix": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
-                                         c_float, c_float, c_void_p, c_void_p]),
+                                         c_float, c_float, c_int, c_void_p, c_void_p]),
     "dsn_scale_coords": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
 }
 

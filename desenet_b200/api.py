@@ -257,9 +257,10 @@ class ConfusionMatrix:
         det = det.contiguous() if det.numel() else det.new_zeros((0, 6))
         ops.det_confusion_matrix_(self._m, det, None, lab, off, int(lab.shape[0]), self.nc, self.conf, self.iou_thres)
 
-    def process_images(self, det, det_count, labels, label_off, max_labels_per_image):
+    def process_images(self, det, det_count, labels, label_off, max_labels_per_image, skip_empty=False):
+        """``skip_empty``: images without detections contribute nothing (what val.run's loop does, val.py:241-244)."""
         ops.det_confusion_matrix_(self._m, det, det_count, labels, label_off, max_labels_per_image, self.nc, self.conf,
-                                  self.iou_thres)
+                                  self.iou_thres, skip_empty=skip_empty)
 
     def matrix(self):
         """(nc+1, nc+1) float64 numpy array like the reference's ``self.matrix`` (metrics.py:127)."""

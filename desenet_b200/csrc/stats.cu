@@ -343,11 +343,12 @@ __global__ void __launch_bounds__(256) det_confusion_kernel(const float *__restr
                                                             long long det_row_stride, const int *__restrict__ det_count,
                                                             int max_rows, const float *__restrict__ labels,
                                                             const int *__restrict__ label_off, int nc, float conf, float iou_thres,
-                                                            unsigned long long *__restrict__ matrix) {
+                                                            int skip_empty, unsigned long long *__restrict__ matrix) {
     extern __shared__ unsigned long long win[];     // per label: (iou bits << 32) | ~detection of its best detection
     __shared__ int any_match;
     const int b = blockIdx.x;
     const int n = det_count ? min(det_count[b], max_rows) : max_rows;
+    if (skip_empty && n <= 0) return;               // val.py:241-244: images without detections never reach process_batch
     const int l0 = label_off[b], m = label_off[b + 1] - l0;
     const float *lab = labels + (size_t)l0 * 5;
     const float *d0 = det + (size_t)b * det_image_stride;
@@ -505,14 +506,15 @@ extern "C" __attribute__((visibility("default"))) int dsn_det_confusion_matrix(c
                                                                                int64_t det_row_stride, const int *det_count, int bs,
                                                                                int max_rows, const float *labels, const int *label_off,
                                                                                int max_labels_per_image, int nc, float conf,
-                                                                               float iou_thres, uint64_t *matrix, void *stream) {
+                                                                               float iou_thres, int skip_empty, uint64_t *matrix,
+                                                                               void *stream) {
     if (bs < 0 || max_rows < 0 || nc < 1 || max_labels_per_image < 0 || det_row_stride < 6) return DSN_E_INVALID;
     if (bs == 0) return DSN_OK;
     if (!label_off || !matrix || (max_rows > 0 && !det) || (max_labels_per_image > 0 && !labels)) return DSN_E_INVALID;
     if (max_rows > 8 * 256 || max_labels_per_image > 6000) return DSN_E_UNSUPPORTED;
     const size_t smem = sizeof(unsigned long long) * (size_t)(max_labels_per_image > 0 ? max_labels_per_image : 1);
     det_confusion_kernel<<<bs, 256, smem, (cudaStream_t)stream>>>(det, det_image_stride, det_row_stride, det_count, max_rows, labels,
-                                                                  label_off, nc, conf, iou_thres, (unsigned long long *)matrix);
+                                                                  label_off, nc, conf, iou_thres, skip_empty, (unsigned long long *)matrix);
     DSN_CHECK_LAUNCH();
     return DSN_OK;
 }

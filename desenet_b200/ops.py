@@ -453,7 +453,7 @@ def compute_ap_device(recall: torch.Tensor, precision: torch.Tensor) -> torch.Te
 
 def det_confusion_matrix_(matrix: torch.Tensor, det: torch.Tensor, det_count: Optional[torch.Tensor], labels: torch.Tensor,
                           label_off: torch.Tensor, max_labels_per_image: int, nc: int, conf: float = 0.25,
-                          iou_thres: float = 0.45) -> torch.Tensor:
+                          iou_thres: float = 0.45, skip_empty: bool = False) -> torch.Tensor:
     """metrics.py:132-170 for a batch, accumulating into ``matrix`` ((nc+1, nc+1) int64 CUDA tensor)."""
     lib = _lib.load()
     det = det if det.dim() == 3 else det.unsqueeze(0)
@@ -467,6 +467,22 @@ def det_confusion_matrix_(matrix: torch.Tensor, det: torch.Tensor, det_count: Op
     with torch.cuda.device(det.device):
         rc = lib.dsn_det_confusion_matrix(_ptr(det), int(det.stride(0)), int(det.stride(1)) if rows else 6, _ptr(det_count), bs,
                                           rows, _ptr(labels), _ptr(label_off), int(max_labels_per_image), int(nc),
-                                          float(np.float32(conf)), float(np.float32(iou_thres)), _ptr(matrix), _stream(det.device))
+                                          float(np.float32(conf)), float(np.float32(iou_thres)), int(bool(skip_empty)), _ptr(matrix),
+                                          _stream(det.device))
     _lib.check(rc, "dsn_det_confusion_matrix")
     return matrix
+
+
+def labels_to_native(targets: torch.Tensor, width: float, height: float, params: torch.Tensor) -> torch.Tensor:
+    """val.py:227,243-255 for a whole batch: ``targets`` (n, 6) [image, cls, normalised xywh] -> ``labelsn`` (n, 5)
+    [cls, native-space xyxy], with per-image ``params`` (bs, 5) as for ``scale_coords_``."""
+    lib = _lib.load()
+    targets = _require_cuda(targets.reshape(-1, 6), "targets")
+    params = _require_cuda(params, "params").reshape(-1, 5)
+    n = int(targets.shape[0])
+    with torch.cuda.device(targets.device):
+        out = torch.empty((n, 5), dtype=torch.float32, device=targets.device)
+        rc = lib.dsn_labels_to_native(_ptr(targets), n, float(width), float(height), _ptr(params), int(params.shape[0]), _ptr(out),
+                                      _stream(targets.device))
+    _lib.check(rc, "dsn_labels_to_native")
+    return out

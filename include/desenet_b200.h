@@ -203,6 +203,15 @@ int dsn_process_batch(const float *det, int64_t det_image_stride, int64_t det_ro
                       int bs, int max_rows, const float *labels, const int *label_off, int max_labels_per_image,
                       const float *iouv, int niou, unsigned char *correct, void *stream);
 
+/* All labels of a batch into native image space in one launch (scripts/val.py:227,243-255):
+ *   targets   device (n, 6) fp32 rows [image, cls, x, y, w, h], xywh normalised to the network input
+ *   width, height   network input size (val.py:227: targets[:, 2:] *= (width, height, width, height))
+ *   params    device (bs, 5) fp32 per image: pad_x, pad_y, gain, w0, h0 (as dsn_scale_coords)
+ *   labelsn   device (n, 5) fp32 rows [cls, x1, y1, x2, y2]: xywh2xyxy (general.py:523-530), then scale_coords +
+ *             clip_coords (general.py:598-623) with the row's image parameters */
+int dsn_labels_to_native(const float *targets, int64_t n, float width, float height, const float *params, int bs,
+                         float *labelsn, void *stream);
+
 /* ---- end-of-eval detection statistics ------------------------------------------------
  * ap_per_class (core/utils/metrics.py:31-92) over ALL detections of an evaluation, on the device:
  *   tp          device (n, niou) uint8/bool: detection i is a true positive at IoU threshold j (val.py:121,263)
@@ -230,11 +239,13 @@ int dsn_compute_ap(const double *recall, const double *precision, int64_t n, con
  * label_off as for dsn_process_batch.  matrix: device (nc+1, nc+1) uint64, rows = predicted class (nc = background),
  * columns = true class, ACCUMULATED.  Detections with conf <= `conf` are ignored, pairs need IoU > iou_thres (both
  * compared in fp32 as torch does); equal IoUs resolve to the lowest index (the reference's order there depends on
- * numpy's unstable argsort); classes outside [0, nc] are skipped (the reference would raise or wrap). */
+ * numpy's unstable argsort); classes outside [0, nc] are skipped (the reference would raise or wrap).
+ * skip_empty != 0: images without detections contribute nothing, as in val.run, whose loop `continue`s before
+ * process_batch for them (val.py:241-244); 0: their labels count as background FP, as a direct call would. */
 int dsn_det_confusion_matrix(const float *det, int64_t det_image_stride, int64_t det_row_stride, const int *det_count,
                              int bs, int max_rows, const float *labels, const int *label_off,
-                             int max_labels_per_image, int nc, float conf, float iou_thres, uint64_t *matrix,
-                             void *stream);
+                             int max_labels_per_image, int nc, float conf, float iou_thres, int skip_empty,
+                             uint64_t *matrix, void *stream);
 
 #ifdef __cplusplus
 }
