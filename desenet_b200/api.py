@@ -133,8 +133,19 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
     assert 0 <= iou_thres <= 1, f'Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0'
     has_labels = bool(labels) and any(len(l) for l in labels)
     if isinstance(prediction, HeadOutputs) and not has_labels:
-        det, det_count, _ = ops.detect_nms_levels(prediction.head, conf_thres, iou_thres, classes, agnostic, multi_label,
-                                                  int(max_det))
+        head = prediction.head
+        ml = bool(multi_label) and head.nc > 1
+        target = min(ops.MAX_NMS, max(8192, 16 * int(max_det)))
+        cut = None
+        if ml and head.A * head.nc >= 8 * target:          # eval setting: sampled confidence cut (exact, see ops.conf_cut_levels)
+            cut = ops.conf_cut_levels(head, conf_thres, ml, classes, target=target)
+        if cut is not None:
+            keys, counts = ops.filter_levels(head, conf_thres, ml, classes, cut=cut)
+            det, det_count = ops.nms_levels(head, keys, counts, conf_thres, iou_thres, agnostic, int(max_det), cut=cut)
+            if bool((det_count == -2).any()):              # the NMS ran out of emitted candidates somewhere: redo without the cut
+                cut = None
+        if cut is None:
+            det, det_count, _ = ops.detect_nms_levels(head, conf_thres, iou_thres, classes, agnostic, multi_label, int(max_det))
     else:
         z = prediction.z if isinstance(prediction, HeadOutputs) else prediction
         if has_labels:

@@ -133,6 +133,9 @@ def test_conf_cut_is_exact(env):
     ho = api.HeadOutputs(dl, port.DEFAULT_ANCHORS, port.DEFAULT_STRIDES)
     want = port.non_max_suppression(ho.z[:1].cpu(), nms_impl="c", **kw)
     assert torch.equal(b.detections()[0].cpu(), want[0])
+    got = api.non_max_suppression(ho, **kw)               # the reference-facing call takes the cut path as well
+    for x, y in zip(got, a.detections()):
+        assert torch.equal(x, y)
     # graph replay with the cut
     first = b.det.clone()
     b.det.zero_()
@@ -180,3 +183,6 @@ def test_conf_cut_fallback_when_sample_misleads(env):
     for x, y in zip(a.detections(), b.detections()):
         assert torch.equal(x, y)
     assert (b.det_count.cpu() >= 0).all()
+    ho = api.HeadOutputs(dl, port.DEFAULT_ANCHORS, port.DEFAULT_STRIDES)
+    for x, y in zip(api.non_max_suppression(ho, **kw), a.detections()):      # same fallback inside the API call
+        assert torch.equal(x, y)
