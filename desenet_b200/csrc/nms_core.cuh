@@ -86,6 +86,7 @@ __device__ __forceinline__ float4 offset_box(const float4 &b, float off) {
 constexpr int kRound = 256;          // candidates resolved per bitmask round
 constexpr int kRankSortMax = 256;    // O(m^2) rank sort below, bitonic sort above
 constexpr int kWords = kRound / 64;
+constexpr int kChainClasses = 256;
 
 struct NmsSmem {
     unsigned long long key[kChunk];
@@ -108,6 +109,12 @@ struct NmsSmem {
     unsigned int dead[kRound / 32];
     unsigned int nz[kRound / 32];
     unsigned long long keptbits[kWords];
+    // class chains (used while the class-aware culling holds and nc <= kChainClasses): survivors / round candidates of
+    // one class are linked newest-to-oldest, so a candidate only meets the boxes that can overlap it
+    int khead[kChainClasses];         // newest survivor slot of the class (-1: none); slots < kKeptSmem only
+    short knext[kKeptSmem];           // next older survivor of the same class
+    short rprev[kRound];              // previous (better-scored) candidate of the same class inside the round
+    unsigned short rcls[kRound];      // class of the round's candidates
     unsigned int m;                   // gathered count
     unsigned int below;
     unsigned int red_sum, red_max, red_min;
@@ -276,6 +283,8 @@ __device__ void nms_image(NmsSmem &s, const NmsParams &p, const BoxSrc &src, int
         s.ext[2] = s.ext[3] = -INFINITY;
         s.ext_bad = 0;
     }
+    const bool chainable = p.nc <= kChainClasses;
+    for (int i = threadIdx.x; i < kChainClasses; i += kNmsThreads) s.khead[i] = -1;
     int consumed = 0;               // candidates taken in sorted order so far (max_nms cut)
     int seen = 0;                   // keys gathered so far
     unsigned long long cur = 0ull;
@@ -378,6 +387,7 @@ __device__ void nms_image(NmsSmem &s, const NmsParams &p, const BoxSrc &src, int
                 s.rbox[threadIdx.x] = ob;
                 s.rarea[threadIdx.x] = box_area(ob);
                 s.roff[threadIdx.x] = threadIdx.x < cnt ? s.off[s0 + threadIdx.x] : 0.f;
+                s.rcls[threadIdx.x] = threadIdx.x < cnt ? (unsigned short)((unsigned int)s.key[s0 + threadIdx.x] % (unsigned)p.nc) : 0;
             }
             if (threadIdx.x < kRound / 32) { s.dead[threadIdx.x] = 0u; s.nz[threadIdx.x] = 0u; }
             static_assert((kRound * kWords) % kNmsThreads == 0, "mask words split evenly over the CTA");
@@ -385,6 +395,57 @@ __device__ void nms_image(NmsSmem &s, const NmsParams &p, const BoxSrc &src, int
             for (int i = 0; i < kRound * kWords / kNmsThreads; ++i) (&s.mask[0][0])[threadIdx.x + i * kNmsThreads] = 0ull;
             __syncthreads();
             DSN_LAP(37);   // round setup
+            // class chains: previous candidate of the same class inside the round (built for every round so that the
+            // survivor chains stay complete; used for the pair tests only while the class-aware culling holds)
+            const bool use_chain = chainable && cull;
+            if (chainable) {
+                if (threadIdx.x < cnt) {
+                    const unsigned short c = s.rcls[threadIdx.x];
+                    int j = (int)threadIdx.x - 1;
+                    while (j >= 0 && s.rcls[j] != c) --j;
+                    s.rprev[threadIdx.x] = (short)j;
+                }
+                __syncthreads();
+            }
+            static_assert(kNmsThreads >= 2 * kRound, "the chain path runs (a) and (b) on disjoint halves of the CTA");
+            if (use_chain) {
+                if (threadIdx.x < kRound) {
+                    // (a) against the survivors of the candidate's own class (newest first), then any survivors beyond
+                    //     the shared-memory cache
+                    const int j = threadIdx.x;
+                    bool dead = false;
+                    if (j < cnt && nkept0 > 0) {
+                        const float4 bj = s.rbox[j];
+                        const float aj = s.rarea[j], oj = s.roff[j];
+                        // no early exit: the tests of successive hops are independent, only the hop itself (one LDS) is serial
+#pragma unroll 4
+                        for (int k = s.khead[s.rcls[j]]; k >= 0; k = s.knext[k]) dead = suppresses(s.kbox[k], s.karea[k], bj, aj, p.thr_f) || dead;
+                        for (int k = kKeptSmem; k < nkept0 && !dead; ++k) {
+                            const float *r = det + (size_t)k * 6;
+                            const float ok = __fmul_rn(r[5], p.off_mul);
+                            if (ok != oj) continue;
+                            const float4 bk = offset_box(make_float4(r[0], r[1], r[2], r[3]), ok);
+                            dead = suppresses(bk, box_area(bk), bj, aj, p.thr_f);
+                        }
+                    }
+                    const unsigned int bal = __ballot_sync(0xffffffffu, dead);
+                    if (lane == 0 && bal) atomicOr(&s.dead[warp], bal);
+                } else if (threadIdx.x < 2 * kRound) {
+                    // (b) inside the round: candidate i against the better-scored candidates of its class
+                    const int i = threadIdx.x - kRound;
+                    if (i < cnt) {
+                        const float4 bi = s.rbox[i];
+                        const float ai = s.rarea[i];
+#pragma unroll 4
+                        for (int j = s.rprev[i]; j >= 0; j = s.rprev[j]) {
+                            if (suppresses(s.rbox[j], s.rarea[j], bi, ai, p.thr_f)) {
+                                atomicOr(&s.mask[j][i >> 6], 1ull << (i & 63));
+                                atomicOr(&s.nz[j >> 5], 1u << (j & 31));
+                            }
+                        }
+                    }
+                }
+            } else {
             // (a) against the survivors so far: candidate = tid % kRound, the thread groups stride the kept list
             if (nkept0 > 0) {
                 const int j = threadIdx.x & (kRound - 1), part = threadIdx.x / kRound;
@@ -438,6 +499,7 @@ __device__ void nms_image(NmsSmem &s, const NmsParams &p, const BoxSrc &src, int
                     }
                 }
             }
+            }   // !use_chain
             __syncthreads();
             DSN_MARK(14);
             DSN_LAP(39);   // (b) pairs + sync
@@ -484,6 +546,7 @@ __device__ void nms_image(NmsSmem &s, const NmsParams &p, const BoxSrc &src, int
             DSN_MARK(15);
             DSN_LAP(40);   // (c) scan
             // (d) append survivors                                               general.py:745
+            int my_slot = -1;
             if (threadIdx.x < cnt) {
                 const int w = threadIdx.x >> 6, bit = threadIdx.x & 63;
                 const unsigned long long kb = s.keptbits[w];
@@ -501,8 +564,27 @@ __device__ void nms_image(NmsSmem &s, const NmsParams &p, const BoxSrc &src, int
                         s.kbox[slot] = s.rbox[threadIdx.x];
                         s.karea[slot] = s.rarea[threadIdx.x];
                         s.koff[slot] = s.roff[threadIdx.x];
+                        if (chainable) {
+                            // link behind the previous survivor of the class: the nearest kept one up the round's chain,
+                            // else the class's newest survivor of earlier rounds
+                            int j = s.rprev[threadIdx.x];
+                            while (j >= 0 && !((s.keptbits[j >> 6] >> (j & 63)) & 1ull)) j = s.rprev[j];
+                            int prev;
+                            if (j >= 0) {
+                                prev = nkept0 + __popcll(s.keptbits[j >> 6] & ((1ull << (j & 63)) - 1ull));
+                                for (int v = 0; v < (j >> 6); ++v) prev += __popcll(s.keptbits[v]);
+                            } else {
+                                prev = s.khead[s.rcls[threadIdx.x]];
+                            }
+                            s.knext[slot] = (short)prev;
+                            my_slot = slot;
+                        }
                     }
                 }
+            }
+            if (chainable) {
+                __syncthreads();                                   // every knext is written before a head moves
+                if (my_slot >= 0) atomicMax(&s.khead[s.rcls[threadIdx.x]], my_slot);
             }
             __syncthreads();
             DSN_LAP(41);   // (d) append
