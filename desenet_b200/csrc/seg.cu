@@ -145,12 +145,29 @@ __device__ __forceinline__ SrcCols<C> load_src_row(const float *img, int plane, 
 // inner loop is branch-free: two LDS for the row's (l0, l1), C x 4 FMUL+FFMA, the compares, one
 // 16 B streaming store.  Between segments T/B swap roles and the stale one is rebuilt from raw
 // values prefetched one source row ahead.
-template <int C, bool HAS_TGT, int MASK, typename W>
+// RING (eval mode without a mask): the int64 target does not pass through registers on its way in.  Every thread
+// streams its own 32 B of each row into a private shared-memory ring with cp.async (LDGSTS, 16 B, L2 only), kRingAhead
+// rows ahead of the row it is working on, and reads it back with two LDS.128 when the row's predictions are done.
+// Registers bound the bytes a thread can keep in flight with plain loads, and those were consumed right after they
+// were issued (nothing in flight during the arithmetic); with the ring the next rows' bytes are in flight all the time.
+constexpr int kRingSlots = 8;      // rows per thread in the ring (power of two)
+constexpr int kRingAhead = 4;      // rows in flight beyond the group being consumed
+constexpr int kRingPrefetch = 12;  // rows ahead of the issue pointer that are prefetched into L2
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int C, bool HAS_TGT, int MASK, typename W, bool RING = false>
 __global__ void __maxnreg__(HAS_TGT ? 96 : 128) seg_fused_rows_kernel(const SegParams p, const int rows_per_cta) {
     extern __shared__ __align__(16) unsigned char seg_smem[];
     float2 *lam = reinterpret_cast<float2 *>(seg_smem);                    // [H]   (l0, l1) of output row Y
     int *y0_of = reinterpret_cast<int *>(lam + p.H);                       // [H]   source row y0 of output row Y
     int *seg_start = y0_of + p.H;                                          // [h+1] first output row whose y0 is the index
+    // [RING] target ring: slot s, half q of thread t at ((s * 2 + q) * blockDim.x + t) * 16 bytes (conflict-free LDS.128)
+    unsigned char *ring = seg_smem + (((sizeof(float2) + sizeof(int)) * (size_t)p.H + sizeof(int) * (size_t)(p.h + 1) + 15) & ~(size_t)15);
     __shared__ unsigned int cm_smem[DSN_MAX_CM_ROWS * kMaxPackedC];
     const int G = p.W >> 2;
     const int plane = p.h * p.w;
@@ -211,6 +228,35 @@ __global__ void __maxnreg__(HAS_TGT ? 96 : 128) seg_fused_rows_kernel(const SegP
         const long long *tgt_end = HAS_TGT ? p.target + (size_t)total_rows * p.W : nullptr;
         int since_flush = 0;
         bool finite = true;
+        // [RING] stream state: next row to issue, rows of the run still to issue, issue / consume counters
+        const long long *tp_iss = tp;
+        long long iss_left = r_end - r_begin;
+        unsigned int iss = 0, con = 0;
+        auto ring_issue = [&]() {
+            // the row kRingPrefetch rows further down is pulled into L2 (one prefetch per 128 B line = every fourth lane),
+            // so that the cp.async of a row finds it there
+            if (iss_left > kRingPrefetch && active && (threadIdx.x & 3) == 0)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(tp_iss + (size_t)kRingPrefetch * p.W));
+            if (iss_left > 0 && active) {
+                unsigned char *d = ring + ((size_t)((iss & (kRingSlots - 1)) * 2) * blockDim.x + threadIdx.x) * 16;
+                cp_async16(d, tp_iss);
+                cp_async16(d + (size_t)blockDim.x * 16, tp_iss + 2);
+            }
+            cp_async_commit();
+            ++iss;
+            tp_iss += p.W;
+            --iss_left;
+        };
+        auto ring_read = [&](unsigned int slot, long long (&tv)[4]) {
+            const unsigned char *d = ring + ((size_t)((slot & (kRingSlots - 1)) * 2) * blockDim.x + threadIdx.x) * 16;
+            const longlong2 ta = *reinterpret_cast<const longlong2 *>(d);
+            const longlong2 tb = *reinterpret_cast<const longlong2 *>(d + (size_t)blockDim.x * 16);
+            tv[0] = ta.x; tv[1] = ta.y; tv[2] = tb.x; tv[3] = tb.y;
+        };
+        if constexpr (RING) {
+#pragma unroll
+            for (int q = 0; q < kRingAhead; ++q) ring_issue();
+        }
 
         // one output row from the row pair (top, bot)
         auto row_body = [&](const float2 lm, const float (&top)[C][4], const float (&bot)[C][4], const long long (&tv)[4]) {
@@ -264,6 +310,24 @@ __global__ void __maxnreg__(HAS_TGT ? 96 : 128) seg_fused_rows_kernel(const SegP
         // output rows [Y, ye) of one segment; the target loads of 4 rows are issued together (8 x 16 B in flight)
         auto segment = [&](int Y, const int ye, const float (&top)[C][4], const float (&bot)[C][4]) {
             for (; Y + 4 <= ye; Y += 4) {
+                if constexpr (RING) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) ring_issue();
+                    cp_async_wait<kRingAhead>();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        long long t4[4] = {0, 0, 0, 0};
+                        if (active) ring_read(con + q, t4);
+                        row_body(lam[Y + q], top, bot, t4);
+                    }
+                    con += 4;
+                    since_flush += 4;
+                    if (since_flush >= 60) {
+                        acc.flush(cm_smem, p.cm_rows);
+                        since_flush = 0;
+                    }
+                    continue;
+                }
                 long long tv[4][4];
                 if (HAS_TGT) {
                     // Registers bound the bytes a thread can have in flight (8 x 16 B here), and a dependent DRAM round
@@ -299,7 +363,13 @@ __global__ void __maxnreg__(HAS_TGT ? 96 : 128) seg_fused_rows_kernel(const SegP
             }
             for (; Y < ye; ++Y) {
                 long long tv[4] = {0, 0, 0, 0};
-                if (HAS_TGT) {
+                if constexpr (RING) {
+                    ring_issue();
+                    cp_async_wait<kRingAhead>();
+                    if (active) ring_read(con, tv);
+                    ++con;
+                    ++since_flush;
+                } else if (HAS_TGT) {
                     if (active) {
                         const longlong2 ta = ldg_stream_ll2(tp);
                         const longlong2 tb = ldg_stream_ll2(tp + 2);
@@ -347,6 +417,7 @@ __global__ void __maxnreg__(HAS_TGT ? 96 : 128) seg_fused_rows_kernel(const SegP
             }
         }
         if (HAS_TGT) acc.flush(cm_smem, p.cm_rows);
+        if constexpr (RING) cp_async_wait<0>();
     }
     if (HAS_TGT) {
         __syncthreads();
@@ -783,15 +854,16 @@ static inline int G_of(const SegParams &p) { return p.W / 4; }
 
 static int sm_count() { return sm_count_current_device(); }
 
-template <int C, bool T, int M, typename W>
+template <int C, bool T, int M, typename W, bool RING = false>
 static int launch_rows_w(const SegParams &p, cudaStream_t st) {
     const int G = p.W / 4;
     const int threads = std::min(512, (G + 31) / 32 * 32);
-    const size_t smem = (sizeof(float2) + sizeof(int)) * (size_t)p.H + sizeof(int) * (size_t)(p.h + 1);
+    size_t smem = (sizeof(float2) + sizeof(int)) * (size_t)p.H + sizeof(int) * (size_t)(p.h + 1);
+    if (RING) smem = ((smem + 15) & ~(size_t)15) + (size_t)kRingSlots * 32 * threads;
     static DeviceOnce once;                   // per template instantiation
-    if (int rc = raise_dynamic_smem(once, seg_fused_rows_kernel<C, T, M, W>, 200 * 1024)) return rc;
+    if (int rc = raise_dynamic_smem(once, seg_fused_rows_kernel<C, T, M, W, RING>, 200 * 1024)) return rc;
     int occ = 0;
-    DSN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seg_fused_rows_kernel<C, T, M, W>, threads, smem));
+    DSN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seg_fused_rows_kernel<C, T, M, W, RING>, threads, smem));
     if (occ < 1) occ = 1;
     const long long total_rows = (long long)p.bs * p.H;
     long long grid = std::min<long long>((long long)sm_count() * occ, (total_rows + 7) / 8);
@@ -803,7 +875,7 @@ static int launch_rows_w(const SegParams &p, cudaStream_t st) {
     }
     if (forced > 0) rows_per_cta = forced;
     grid = (total_rows + rows_per_cta - 1) / rows_per_cta;
-    seg_fused_rows_kernel<C, T, M, W><<<(unsigned)grid, threads, smem, st>>>(p, rows_per_cta);
+    seg_fused_rows_kernel<C, T, M, W, RING><<<(unsigned)grid, threads, smem, st>>>(p, rows_per_cta);
     DSN_CHECK_LAUNCH();
     return DSN_OK;
 }
@@ -833,6 +905,19 @@ static int launch_eval_tma_w(const SegParams &p, cudaStream_t st) {
 
 template <int C, bool T, int M>
 static int launch_rows_one(const SegParams &p, cudaStream_t st) {
+    if constexpr (T && M == 0) {
+        // pure eval, opt-in (DSN_SEG_RING=1): target streamed through a per-thread cp.async ring.  Measured on B200
+        // (cfg 3, bs 512): the kernel ALONE is slower than the plain-load variant (463 vs 363 us: 4 rows ahead do not
+        // cover a DRAM round trip and 8 slots x 32 B x threads of shared memory cap the ring depth), while the whole
+        // step with 3 batches in flight is ~6 % faster (the ring CTAs share the SMs better with the detection chain);
+        // at 1280 px it loses both ways.  The default stays the variant with the higher stand-alone bandwidth.
+        static int ring = -1;
+        if (ring < 0) { const char *e = getenv("DSN_SEG_RING"); ring = (e && atoi(e)) ? 1 : 0; }
+        if (ring && (size_t)kRingSlots * 32 * std::min(512, (p.W / 4 + 31) / 32 * 32) <= 160 * 1024) {
+            if (p.cm_rows <= 4) return launch_rows_w<C, T, M, unsigned int, true>(p, st);
+            return launch_rows_w<C, T, M, unsigned long long, true>(p, st);
+        }
+    }
     if (!T || p.cm_rows <= 4) return launch_rows_w<C, T, M, unsigned int>(p, st);
     return launch_rows_w<C, T, M, unsigned long long>(p, st);
 }
