@@ -218,6 +218,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-graph", action="store_true", help="launch kernels directly instead of CUDA-graph replay")
+    ap.add_argument("--python-loop", action="store_true", help="replay the step graphs one by one from Python instead of one native burst")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--prewarm-ms", type=float, default=600.0)
@@ -335,11 +336,20 @@ def main():
         for q in pps:
             q.cm.zero_()
         torch.cuda.synchronize(dev)
+    # the K timed steps are enqueued by ONE native call (ops.GraphBurst -> dsn_graph_launch_many): step i = graph of input
+    # set i % NBUF of batch slot i % in_flight, on that slot's stream - the same sequence step(i) launches from Python
+    burst = None
+    if use_graph and not args.python_loop:
+        burst = ops.GraphBurst([pps[i % n_fl]._graphs[i % NBUF][0] for i in range(args.steps)],
+                               [streams[i % n_fl] for i in range(args.steps)])
     t_wall0 = time.perf_counter()
     ev0.record()
     fork()
-    for i in range(args.steps):
-        step(i)
+    if burst is not None:
+        burst.launch()
+    else:
+        for i in range(args.steps):
+            step(i)
     join()
     cm_total = None
     if eval_mode:
@@ -488,7 +498,8 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak" if not cfg.get("total") else "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["name"], "images_per_gpu": bs, "l2": f"rotating {NBUF} input sets (working set > 126 MB L2 between reuses)",
-                       "launch": "cuda-graph replay" if use_graph else "direct launches",
+                       "launch": ("cuda-graph replay, K steps enqueued by one native call" if burst is not None else
+                                  "cuda-graph replay from Python") if use_graph else "direct launches",
                        "det_path": "fused single launch" if pp.fused_det else
                        ("confidence cut + filter + NMS (3 launches)" if pp.conf_cut else "filter + NMS (2 launches)"),
                        "in_flight_batches": n_fl,

@@ -17,6 +17,7 @@ _FLOATPP = POINTER(c_void_p)
 SIGNATURES = {
     "dsn_version": (c_int, []),
     "dsn_error_string": (c_char_p, [c_int]),
+    "dsn_graph_launch_many": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int]),
     "dsn_detect_decode": (c_int, [_FLOATPP, POINTER(c_int), POINTER(c_int), POINTER(c_float), POINTER(c_float),
                                   c_int, c_int, c_int, c_int, c_void_p, _FLOATPP, c_void_p]),
     "dsn_filter_levels": (c_int, [_FLOATPP, POINTER(c_int), POINTER(c_int), c_int, c_int, c_int, c_int, c_float, c_int,

@@ -15,6 +15,18 @@ extern "C" __attribute__((visibility("default"))) const char *dsn_error_string(i
     return "unknown desenet_b200 error code";
 }
 
+// Native serving loop: launches n captured post-process steps back to back (step i = graph_execs[i] on streams[i]).
+// One Python call per burst instead of one per step: at ~30 us per step the host side of a per-step Python replay
+// (stream context + graph launch) is the bottleneck as soon as several ranks share the host cores.
+extern "C" __attribute__((visibility("default"))) int dsn_graph_launch_many(void *const *graph_execs, void *const *streams, int n) {
+    if (n < 0 || (n > 0 && (!graph_execs || !streams))) return DSN_E_INVALID;
+    for (int i = 0; i < n; ++i) {
+        if (!graph_execs[i]) return DSN_E_INVALID;
+        DSN_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_execs[i], (cudaStream_t)streams[i]));
+    }
+    return DSN_OK;
+}
+
 #ifdef DSN_TIMING
 namespace dsn { __device__ unsigned long long dsn_timing[64]; }
 extern "C" __attribute__((visibility("default"))) int dsn_debug_timing(unsigned long long *host_out) {

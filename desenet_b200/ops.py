@@ -486,3 +486,19 @@ def labels_to_native(targets: torch.Tensor, width: float, height: float, params:
                                       _stream(targets.device))
     _lib.check(rc, "dsn_labels_to_native")
     return out
+
+
+class GraphBurst:
+    """A fixed sequence of captured steps (``torch.cuda.CUDAGraph`` objects) and the streams they run on, launched
+    by one native call (``dsn_graph_launch_many``): the serving loop of a rank without per-step Python overhead."""
+
+    def __init__(self, graphs: Sequence[torch.cuda.CUDAGraph], streams: Sequence[torch.cuda.Stream]):
+        assert len(graphs) == len(streams)
+        self.n = len(graphs)
+        self._keep = (list(graphs), list(streams))
+        self._execs = (c_void_p * self.n)(*[int(g.raw_cuda_graph_exec()) for g in graphs])
+        self._streams = (c_void_p * self.n)(*[int(s.cuda_stream) for s in streams])
+
+    def launch(self, n: Optional[int] = None):
+        rc = _lib.load().dsn_graph_launch_many(self._execs, self._streams, self.n if n is None else int(n))
+        _lib.check(rc, "dsn_graph_launch_many")

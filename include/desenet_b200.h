@@ -38,6 +38,11 @@ int dsn_version(void);
 /* Static string for a return code of any function below (cudaGetErrorString for codes > 0). */
 const char *dsn_error_string(int code);
 
+/* Native serving loop: launch n captured steps back to back, step i = cudaGraphExec_t graph_execs[i] on cudaStream_t
+ * streams[i] (handles of graphs the caller captured from the enqueue-only entry points below, e.g.
+ * torch.cuda.CUDAGraph.raw_cuda_graph_exec()).  Enqueue-only. */
+int dsn_graph_launch_many(void *const *graph_execs, void *const *streams, int n);
+
 /* ------------------------------------------------------------------------------------------
  * Detection head geometry, shared by the calls below.
  *   raw[l]      device pointer, level l conv output, NCHW fp32 (bs, na*no, ny[l], nx[l]);
