@@ -340,7 +340,7 @@ def main():
     # set i % NBUF of batch slot i % in_flight, on that slot's stream - the same sequence step(i) launches from Python
     burst = None
     if use_graph and not args.python_loop:
-        burst = ops.GraphBurst([pps[i % n_fl]._graphs[i % NBUF][0] for i in range(args.steps)],
+        burst = ops.GraphBurst([pps[i % n_fl].graph(i % NBUF) for i in range(args.steps)],
                                [streams[i % n_fl] for i in range(args.steps)])
     t_wall0 = time.perf_counter()
     ev0.record()

@@ -135,6 +135,10 @@ class PostProcessor:
     def replay(self, key=0):
         self._graphs[key][0].replay()
 
+    def graph(self, key=0) -> torch.cuda.CUDAGraph:
+        """The captured step graph (for ``ops.GraphBurst``: many steps enqueued by one native call)."""
+        return self._graphs[key][0]
+
     # ---- results ---------------------------------------------------------------------------------
     def detections(self) -> List[torch.Tensor]:
         """Host-synchronising: list of (n_i, 6) tensors like the reference's non_max_suppression."""

@@ -186,3 +186,32 @@ def test_conf_cut_fallback_when_sample_misleads(env):
     ho = api.HeadOutputs(dl, port.DEFAULT_ANCHORS, port.DEFAULT_STRIDES)
     for x, y in zip(api.non_max_suppression(ho, **kw), a.detections()):      # same fallback inside the API call
         assert torch.equal(x, y)
+
+
+def test_graph_burst_native_serving_loop(env):
+    """ops.GraphBurst / dsn_graph_launch_many: several captured steps on two streams enqueued by one native call give the
+    same results as replaying them one by one."""
+    api, ops, pipeline = env
+    bs, S, nc, C = 3, 160, 6, 2
+    kw = dict(conf_thres=0.25, iou_thres=0.45, max_det=100)
+    sets = [port.synth_head_outputs(bs, S, nc, C, seed=60 + k, with_target=False) for k in range(2)]
+    pps = [pipeline.PostProcessor(bs, S, nc, C, port.DEFAULT_ANCHORS, port.DEFAULT_STRIDES, mode="detect", **kw) for _ in range(2)]
+    dev_sets = [([l.cuda() for l in lv], seg.cuda()) for lv, seg, _ in sets]
+    for q, (lv, seg) in zip(pps, dev_sets):
+        q.capture(lv, seg)
+    want = []
+    for q in pps:
+        q.replay()
+        torch.cuda.synchronize()
+        want.append((q.det.clone(), q.det_count.clone(), q.mask.clone()))
+        q.det.zero_(); q.det_count.zero_(); q.mask.zero_()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for st in streams:
+        st.wait_stream(torch.cuda.current_stream())
+    burst = ops.GraphBurst([pps[i % 2].graph() for i in range(6)], [streams[i % 2] for i in range(6)])
+    burst.launch()
+    torch.cuda.synchronize()
+    for q, (d, c, m) in zip(pps, want):
+        assert torch.equal(q.det_count, c) and torch.equal(q.mask, m)
+        for i in range(bs):
+            assert torch.equal(q.det[i, :int(c[i])], d[i, :int(c[i])])
