@@ -179,6 +179,9 @@ def time_cpu(cfg, seed, repeats, n=None, stages=None):
     return n, times
 
 
+_JSON_OUT = sys.stdout
+
+
 def run_reference_arm(args, cfg, rank, world):
     """--impl reference: the reference's CPU path (oracle port), all host threads, rank 0 only.  Each
     step is a bounded sample of the batch, sized from a 1-image probe so that W+K steps take ~2 min."""
@@ -205,7 +208,7 @@ def run_reference_arm(args, cfg, rank, world):
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -227,6 +230,13 @@ def main():
     ap.add_argument("--time-fused", action="store_true", help="also time the fused detection kernel alone (kernels_us.det_fused)")
     ap.add_argument("--in-flight", type=int, default=3, help="independent batches in flight (one CUDA stream + workspace each)")
     args = ap.parse_args()
+
+    # stdout carries exactly ONE line (the JSON): everything else a library prints there (NCCL prints its version banner
+    # to stdout) is sent to stderr by pointing fd 1 at fd 2 for the duration of the run
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -512,7 +522,7 @@ def main():
             line["config"]["cm_total"] = cm_total.cpu().tolist()
             line["config"]["collectives"] = ("int64 confusion-matrix all_reduce + detection all_gather (NCCL), once at the end of "
                                              "the timed region" if world > 1 else "none (1 GPU)")
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -5,6 +5,7 @@ R=${1:-r1}
 O=gpurun_out
 mkdir -p $O
 python -m pytest tests -m gpu -x -q > $O/${R}_pytest_gpu.log 2>&1; tail -2 $O/${R}_pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" > $O/${R}_smoke.log 2>&1; tail -1 $O/${R}_smoke.log
 python bench.py --impl reference --steps 3 --warmup 1 > $O/${R}_bench_cfg2_reference_arm.json 2> $O/${R}_ref.err
 python bench.py > $O/${R}_bench_cfg2.json 2> $O/${R}_bench_cfg2.err
 for c in 3 4 5; do python bench.py --config $c --steps 50 --warmup 10 > $O/${R}_bench_cfg$c.json 2> $O/${R}_bench_cfg$c.err; done
