@@ -224,6 +224,7 @@ def main():
     ap.add_argument("--python-loop", action="store_true", help="replay the step graphs one by one from Python instead of one native burst")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-depth", type=int, default=2, help="slots (streams) of the host pipeline that e2e measures")
     ap.add_argument("--prewarm-ms", type=float, default=600.0)
     ap.add_argument("--two-kernel-det", action="store_true", help="filter + NMS as two launches instead of the fused kernel")
     ap.add_argument("--fused-det", action="store_true", help="use the fused single-launch detection kernel")
@@ -466,10 +467,9 @@ def main():
     }
 
     # ---- e2e: host buffers in, host results out, copies inside the timed region -----------------------
-    e2e = None
-    if not args.no_e2e:
-        hp = HostPipeline(make_pp, [tuple(l.shape) for l in levels0], tuple(seg0.shape) if mode != "det_only" else None,
-                          tuple(tgt0.shape) if eval_mode else None, depth=2, device=dev)
+    def time_e2e(make):
+        hp = HostPipeline(make, [tuple(l.shape) for l in levels0], tuple(seg0.shape) if mode != "det_only" else None,
+                          tuple(tgt0.shape) if eval_mode else None, depth=args.e2e_depth, device=dev)
         e_steps = max(3, min(args.steps, 50))
         for i in range(3):
             s = h_sets[i % NBUF]
@@ -485,10 +485,21 @@ def main():
         e_t = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
-        e2e = {"value": bs * world * e_steps / float(e_t.item()), "unit": "images/s", "h2d_bytes_per_step": hp.h2d_bytes,
-               "d2h_bytes_per_step": hp.d2h_bytes, "steps": e_steps, "ms_per_step": 1e3 * float(e_t.item()) / e_steps,
-               "note": "pinned host inputs -> H2D -> kernels -> D2H of detections+counts and mask/CM every step; "
-                       "2 slots on 2 streams; wall clock incl. final synchronize"}
+        return {"value": bs * world * e_steps / float(e_t.item()), "unit": "images/s", "h2d_bytes_per_step": hp.h2d_bytes,
+                "d2h_bytes_per_step": hp.d2h_bytes, "steps": e_steps, "ms_per_step": 1e3 * float(e_t.item()) / e_steps}
+
+    e2e = None
+    if not args.no_e2e:
+        e2e = time_e2e(make_pp)
+        e2e["note"] = ("pinned host inputs -> H2D -> kernels -> D2H of detections+counts and mask/CM every step; "
+                       f"{args.e2e_depth} slots on {args.e2e_depth} streams; wall clock incl. final synchronize")
+        if mode == "detect":
+            # the same call with the mask returned as uint8 class ids instead of the reference's float32 (an option of the
+            # host API, NOT the reference contract): shows how much of e2e is the PCIe cost of the fp32 mask
+            u8 = time_e2e(lambda: PostProcessor(bs, S, nc, C, DEFAULT_ANCHORS, DEFAULT_STRIDES, conf_thres=cfg["conf"],
+                                                iou_thres=cfg["iou"], multi_label=cfg["multi_label"], max_det=cfg["max_det"],
+                                                mode=mode, nclass=max(C, 2), device=dev, mask_dtype=torch.uint8))
+            e2e["uint8_mask_variant"] = {k: u8[k] for k in ("value", "d2h_bytes_per_step", "ms_per_step")}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
