@@ -272,6 +272,27 @@ def test_nms_eval_setting_multilabel_full_size(dsn):
     assert all(o.shape[0] == 300 for o in out)
 
 
+def test_nms_nc80_full_size_cut_vs_uncut_and_oracle(dsn):
+    """BASELINE config 5 setting (nc 80, 640x640, conf .001 / iou .6 / multi_label): 1.28 M candidates per image.  The
+    reference-facing call (sampled confidence cut + dense filter) equals the uncut kernels on every image and the oracle
+    on one; with max_det = 5000 the NMS runs until max_nms candidates are consumed, which the cut must also survive."""
+    from desenet_b200 import ops
+    levels, _, _ = port.synth_head_outputs(3, 640, 80, seed=2, with_target=False)
+    ho = dsn.HeadOutputs([l.cuda() for l in levels], port.DEFAULT_ANCHORS, port.DEFAULT_STRIDES)
+    for max_det in (300, 5000):
+        kw = dict(conf_thres=0.001, iou_thres=0.6, multi_label=True, max_det=max_det)
+        out = dsn.non_max_suppression(ho, **kw)
+        det, cnt, counts = ops.detect_nms_levels(ho.head, 0.001, 0.6, None, False, True, max_det)       # no cut
+        assert (counts.cpu() > 1_000_000).all()
+        n = cnt.cpu().tolist()
+        for i, o in enumerate(out):
+            assert o.shape[0] == n[i] and torch.equal(o, det[i, :n[i]])
+        if max_det == 300:
+            want = port.non_max_suppression(ho.z.cpu()[:1], nms_impl="c", **kw)
+            assert_dets_equal(out[:1], [w.numpy() for w in want])
+            assert all(o.shape[0] == 300 for o in out)
+
+
 # ------------------------------------------------------------------------------------------------
 # a5-a8  segmentation tail
 # ------------------------------------------------------------------------------------------------
