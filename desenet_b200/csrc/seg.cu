@@ -87,6 +87,15 @@ struct CmAcc {
     }
 };
 
+// XOR of the HIGH words of four int64 targets.  Only the low words carry information (clamp_target_row), but with the
+// high words dead ptxas narrows each 16-byte target load into two 4-byte loads of the used words: twice the requests,
+// each pulling a whole 32-byte sector for 4 useful bytes.  Folding the high words into a sink that a never-true branch
+// stores keeps the loads 128 bits wide: eval seg kernel 375 -> 288 us at bs 512 / 640 px (0.69 -> 0.90 of the measured
+// HBM peak), 101 -> 80 us at bs 32 / 1280 px.
+__device__ __forceinline__ unsigned int hi_words(const longlong2 &a, const longlong2 &b) {
+    return (unsigned int)(a.x >> 32) ^ (unsigned int)(a.y >> 32) ^ (unsigned int)(b.x >> 32) ^ (unsigned int)(b.y >> 32);
+}
+
 __device__ __forceinline__ int clamp_target_row(long long t, int rows) {
     // metrics.py:359,380 wrap the int64 target to int32 (`astype('int32')`); negatives are neither
     // "labeled" (target > 0) nor inside any histogram range -> same statistics as row 0.
@@ -228,6 +237,7 @@ __global__ void __maxnreg__(HAS_TGT ? 96 : 128) seg_fused_rows_kernel(const SegP
         const long long *tgt_end = HAS_TGT ? p.target + (size_t)total_rows * p.W : nullptr;
         int since_flush = 0;
         bool finite = true;
+        unsigned int hi_sink = 0;
         // [RING] stream state: next row to issue, rows of the run still to issue, issue / consume counters
         const long long *tp_iss = tp;
         long long iss_left = r_end - r_begin;
@@ -258,6 +268,29 @@ __global__ void __maxnreg__(HAS_TGT ? 96 : 128) seg_fused_rows_kernel(const SegP
             for (int q = 0; q < kRingAhead; ++q) ring_issue();
         }
 
+        // predictions of one output row only (no mask, no target): used by the pure-eval group path
+        auto row_pred = [&](const float2 lm, const float (&top)[C][4], const float (&bot)[C][4], int (&pred)[4]) {
+            if (C == 2 && finite) {
+                float v0[4], v1[4];
+                vlerp4(lm, top[0], bot[0], v0);
+                vlerp4(lm, top[C - 1], bot[C - 1], v1);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) pred[k] = v1[k] > v0[k] ? 1 : 0;
+            } else {
+                float vals[C][4];
+#pragma unroll
+                for (int c = 0; c < C; ++c) vlerp4(lm, top[c], bot[c], vals[c]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float best = vals[0][k];
+                    int bi = 0;
+#pragma unroll
+                    for (int c = 1; c < C; ++c)
+                        if (argmax_better(vals[c][k], best)) { best = vals[c][k]; bi = c; }
+                    pred[k] = bi;
+                }
+            }
+        };
         // one output row from the row pair (top, bot)
         auto row_body = [&](const float2 lm, const float (&top)[C][4], const float (&bot)[C][4], const long long (&tv)[4]) {
             int pred[4];
@@ -347,12 +380,34 @@ __global__ void __maxnreg__(HAS_TGT ? 96 : 128) seg_fused_rows_kernel(const SegP
                             const longlong2 ta = ldg_stream_ll2(tp + (size_t)q * p.W);
                             const longlong2 tb = ldg_stream_ll2(tp + (size_t)q * p.W + 2);
                             tv[q][0] = ta.x; tv[q][1] = ta.y; tv[q][2] = tb.x; tv[q][3] = tb.y;
+                            hi_sink ^= hi_words(ta, tb);          // keeps the loads 128 bits wide, see hi_words
                         }
                     }
                     tp += (size_t)4 * p.W;
                 }
+                if constexpr (HAS_TGT && MASK == 0 && C <= 4) {
+                    // pure eval: the predictions of all four rows (independent of the target) are computed FIRST, packed
+                    // two bits per pixel, so that ~300 instructions separate the target loads from their first use and
+                    // the DRAM / L2 round trip overlaps this thread's own arithmetic; only then are the targets consumed
+                    unsigned int packed = 0;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) row_body(lam[Y + q], top, bot, tv[q]);
+                    for (int q = 0; q < 4; ++q) {
+                        int pr[4];
+                        row_pred(lam[Y + q], top, bot, pr);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) packed |= (unsigned)pr[k] << (2 * (q * 4 + k));
+                    }
+                    if (active) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                acc.add((int)((packed >> (2 * (q * 4 + k))) & 3u), clamp_target_row(tv[q][k], p.cm_rows));
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) row_body(lam[Y + q], top, bot, tv[q]);
+                }
                 if (HAS_TGT) {
                     since_flush += 4;
                     if (since_flush >= 60) {              // 4 px per row: an 8-bit field holds at most 255
@@ -374,6 +429,7 @@ __global__ void __maxnreg__(HAS_TGT ? 96 : 128) seg_fused_rows_kernel(const SegP
                         const longlong2 ta = ldg_stream_ll2(tp);
                         const longlong2 tb = ldg_stream_ll2(tp + 2);
                         tv[0] = ta.x; tv[1] = ta.y; tv[2] = tb.x; tv[3] = tb.y;
+                        hi_sink ^= hi_words(ta, tb);
                     }
                     tp += p.W;
                     ++since_flush;
@@ -417,6 +473,7 @@ __global__ void __maxnreg__(HAS_TGT ? 96 : 128) seg_fused_rows_kernel(const SegP
             }
         }
         if (HAS_TGT) acc.flush(cm_smem, p.cm_rows);
+        if (HAS_TGT && hi_sink == 0x9E3779B9u && p.bs < 0) p.cm[0] = hi_sink;      // never true: see hi_sink above
         if constexpr (RING) cp_async_wait<0>();
     }
     if (HAS_TGT) {
@@ -765,6 +822,7 @@ __global__ void __launch_bounds__(256) seg_fullres_vec_kernel(const SegParams p)
         __syncthreads();
     }
     const size_t q0 = (size_t)blockIdx.x * blockDim.x * kQuadsPerThread;
+    unsigned int hi_sink = 0;
 #pragma unroll 2
     for (int j = 0; j < kQuadsPerThread; ++j) {
         const size_t q = q0 + (size_t)j * blockDim.x + threadIdx.x;
@@ -795,6 +853,7 @@ __global__ void __launch_bounds__(256) seg_fullres_vec_kernel(const SegParams p)
                 const longlong2 ta = ldg_stream_ll2(p.target + pix);
                 const longlong2 tb = ldg_stream_ll2(p.target + pix + 2);
                 tv[0] = ta.x; tv[1] = ta.y; tv[2] = tb.x; tv[3] = tb.y;
+                hi_sink ^= hi_words(ta, tb);              // keeps the loads 128 bits wide, see hi_words
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -802,6 +861,7 @@ __global__ void __launch_bounds__(256) seg_fullres_vec_kernel(const SegParams p)
         }
     }
     if (HAS_TGT) {
+        if (hi_sink == 0x9E3779B9u && p.bs < 0) p.cm[0] = hi_sink;      // never true: see hi_words
         __syncthreads();
         for (int i = threadIdx.x; i < nb; i += blockDim.x)
             if (cm_smem[i]) atomicAdd(p.cm + (size_t)(b % p.cm_slots) * nb + i, (unsigned long long)cm_smem[i]);

@@ -23,6 +23,26 @@ __global__ void runs(const long long *t, long long total_rows, int rows_per_cta,
     }
     if (acc == 0x123456789LL) out[0] = acc;
 }
+// same as runs<4>, but only the LOW 32 bits of every int64 are used (what the seg kernel needs): ptxas then narrows
+// each 16-byte load into two 4-byte loads of the used words
+__global__ void runs_low(const long long *t, long long total_rows, int rows_per_cta, int W, unsigned long long *out) {
+    const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(total_rows, r0 + rows_per_cta);
+    unsigned int acc = 0;
+    for (int g = threadIdx.x; g < W / 4; g += blockDim.x) {
+        const long long *p = t + r0 * W + g * 4;
+        long long r = r0;
+        for (; r + 4 <= r1; r += 4) {
+            longlong2 a[4], b[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { a[q] = ld2(p + (size_t)q * W); b[q] = ld2(p + (size_t)q * W + 2); }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc += (unsigned)a[q].x + (unsigned)a[q].y + (unsigned)b[q].x + (unsigned)b[q].y;
+            p += (size_t)4 * W;
+        }
+        for (; r < r1; ++r) { longlong2 a = ld2(p), b = ld2(p + 2); acc += (unsigned)a.x + (unsigned)a.y + (unsigned)b.x + (unsigned)b.y; p += W; }
+    }
+    if (acc == 0x12345678u) out[0] = acc;
+}
 // mode 1: flat grid-stride over 16 B units, U loads in flight
 template <int U>
 __global__ void flat(const long long *t, long long n16, unsigned long long *out) {
@@ -60,6 +80,8 @@ int main() {
         char nm[96];
         snprintf(nm, 96, "runs  %4d CTAs x160, 4 rows in flight", ctas);
         time([&](int i) { runs<4><<<ctas, 160>>>(buf[i % 4], rows, rpc, W, out); }, nm);
+        snprintf(nm, 96, "runs  %4d CTAs x160, 4 rows, LOW words only", ctas);
+        time([&](int i) { runs_low<<<ctas, 160>>>(buf[i % 4], rows, rpc, W, out); }, nm);
         snprintf(nm, 96, "runs  %4d CTAs x160, 8 rows in flight", ctas);
         time([&](int i) { runs<8><<<ctas, 160>>>(buf[i % 4], rows, rpc, W, out); }, nm);
     }
