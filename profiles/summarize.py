@@ -69,6 +69,14 @@ for c in (2, 3, 5):
     for r in rows[2:]:
         if len(r) > ki:
             seen[r[ki]] = r                      # last capture of each kernel (the first is the cold one)
+    # a later capture of single kernels of the same config (e.g. after a kernel change) overrides those rows
+    for extra in sorted(f for f in os.listdir(O) if f.startswith(f"{R}_ncu_full_cfg{c}_") and f.endswith("_raw.csv") and f != os.path.basename(raw)):
+        erows = list(csv.reader(open(os.path.join(O, extra), errors="replace")))
+        if len(erows) > 2 and erows[0] == hdr:
+            shutil.copy(os.path.join(O, extra), os.path.join(P, extra))
+            for r in erows[2:]:
+                if len(r) > ki:
+                    seen[r[ki]] = r
     out = []
     for k, r in seen.items():
         e = OrderedDict(kernel=k)
