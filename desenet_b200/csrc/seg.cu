@@ -925,6 +925,15 @@ static int launch_rows_w(const SegParams &p, cudaStream_t st) {
     int occ = 0;
     DSN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seg_fused_rows_kernel<C, T, M, W, RING>, threads, smem));
     if (occ < 1) occ = 1;
+    static int occ_cap = -1;                 // experiment knob: DSN_SEG_OCC=<resident CTAs per SM the persistent grid is sized for>
+    if (occ_cap < 0) {
+        const char *e = getenv("DSN_SEG_OCC");
+        occ_cap = e ? atoi(e) : 0;
+    }
+    // detect mode is a pure store stream: two 160-thread CTAs per SM already saturate it (21.8 vs 22.1 us), and the
+    // register file they leave free lets an NMS CTA of a batch in flight share the SM (step 29.85 -> 29.3 us at cfg 2)
+    if (!T && occ_cap == 0 && occ > 2) occ = 2;
+    if (occ_cap > 0 && occ > occ_cap) occ = occ_cap;
     const long long total_rows = (long long)p.bs * p.H;
     long long grid = std::min<long long>((long long)sm_count() * occ, (total_rows + 7) / 8);
     int rows_per_cta = (int)((total_rows + grid - 1) / grid);
