@@ -3,7 +3,6 @@ all arithmetic happens in the hand-written sm_100a kernels behind ``include/dese
 Every function enqueues on the current CUDA stream of the input's device and does not synchronise."""
 from __future__ import annotations
 
-import ctypes
 from ctypes import c_float, c_int, c_uint64, c_void_p
 from typing import List, Optional, Sequence, Tuple
 

@@ -16,7 +16,7 @@ Two levels:
 from __future__ import annotations
 
 import sys
-from typing import Iterable, List, Optional
+from typing import Iterable, Optional
 
 import torch
 import torch.nn as nn
