@@ -34,6 +34,9 @@ SIGNATURES = {
     "dsn_detect_nms_levels": (c_int, [_FLOATPP, POINTER(c_int), POINTER(c_int), POINTER(c_float), POINTER(c_float), c_int,
                                       c_int, c_int, c_int, c_float, c_int, POINTER(c_uint64), c_double, c_int, c_int,
                                       c_int, c_float, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dsn_detect_nms_redo_levels": (c_int, [_FLOATPP, POINTER(c_int), POINTER(c_int), POINTER(c_float), POINTER(c_float), c_int,
+                                           c_int, c_int, c_int, c_float, c_int, POINTER(c_uint64), c_double, c_int, c_int,
+                                           c_int, c_float, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dsn_nms_z": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int64, c_void_p, c_float, c_double, c_int, c_int,
                           c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "dsn_seg_fused": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,

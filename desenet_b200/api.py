@@ -27,14 +27,104 @@ __all__ = [
 ]
 
 
-class HeadOutputs:
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    """Kernels compute in fp32, like the reference's fp32 path; fp16 / bf16 head outputs (``--half``, val.py:144,178-179)
+    are upcast on load — the results are those of the fp32 path on ``t.float()``."""
+    return t if t.dtype == torch.float32 else t.float()
+
+
+class _TensorLike:
+    """Shared behaviour of ``HeadOutputs`` / ``SegLogits``: anything the kernels do not take over falls back to the
+    materialised reference tensor (``torch.*`` functions through ``__torch_function__``, indexing, unknown attributes),
+    so code that treats the object as the tensor the reference would have returned keeps working."""
+
+    def _materialise(self) -> torch.Tensor:          # pragma: no cover - overridden
+        raise NotImplementedError
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        def conv(a):
+            if isinstance(a, _TensorLike):
+                return a._materialise()
+            if isinstance(a, (list, tuple)):
+                return type(a)(conv(v) for v in a)
+            return a
+        return func(*conv(tuple(args)), **{k: conv(v) for k, v in (kwargs or {}).items()})
+
+    def __getitem__(self, idx):
+        return self._materialise()[idx]
+
+    def __setitem__(self, idx, value):              # Model._descale_pred (yolo.py:360-366) writes into the prediction
+        self._materialise()[idx] = value
+
+    def __len__(self):
+        return int(self.shape[0])
+
+    def __getattr__(self, name):
+        # only reached for attributes the class does not define: tensor methods such as .argmax / .softmax / .numpy
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self._materialise(), name)
+
+    def dim(self):
+        return len(self.shape)
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    def size(self, dim=None):
+        shp = torch.Size(self.shape)
+        return shp if dim is None else shp[dim]
+
+    def detach(self):
+        return self
+
+    def contiguous(self):
+        return self
+
+    def float(self):
+        return self.to(torch.float32)
+
+    def half(self):
+        return self.to(torch.float16)
+
+    def cpu(self):
+        return self.to(torch.device("cpu"))
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda", torch.cuda.current_device()) if device is None else device)
+
+    def type_as(self, other):
+        return self.to(other.dtype)
+
+
+def _parse_to(args, kwargs, device, dtype):
+    """(device, dtype) after ``Tensor.to(*args, **kwargs)``."""
+    for a in list(args) + [kwargs.get("device"), kwargs.get("dtype"), kwargs.get("other")]:
+        if a is None:
+            continue
+        if isinstance(a, torch.dtype):
+            dtype = a
+        elif isinstance(a, (torch.device, str, int)):
+            device = torch.device("cuda", a) if isinstance(a, int) else torch.device(a)
+        elif isinstance(a, torch.Tensor):
+            device, dtype = a.device, a.dtype
+    return device, dtype
+
+
+class HeadOutputs(_TensorLike):
     """Raw outputs of the three ``Detect.m[i]`` convs (core/models/yolo.py:258) + the head's
     ``anchor_grid`` / ``stride`` buffers.  ``.z`` / ``.x`` materialise what ``Detect.forward`` returns
-    (yolo.py:277) on demand; ``non_max_suppression`` accepts the object directly (fused path)."""
+    (yolo.py:277) on demand; ``non_max_suppression`` accepts the object directly (fused path).
+    ``out_dtype`` is the dtype the reference's ``z`` would have had (fp16 under ``--half``); everything is computed in
+    fp32 and only a materialised ``z`` is cast to it."""
 
-    def __init__(self, levels: Sequence[torch.Tensor], anchor_grid, stride):
-        self.head = ops.Head(levels, anchor_grid, stride)
+    def __init__(self, levels: Sequence[torch.Tensor], anchor_grid, stride=None, out_dtype=None):
+        self._out_dtype = out_dtype if out_dtype is not None else levels[0].dtype
+        self.head = ops.Head([_f32(l) for l in levels], anchor_grid, stride)
         self._z = None
+        self._zc = None
         self._x = None
 
     @property
@@ -44,6 +134,10 @@ class HeadOutputs:
     @property
     def device(self):
         return self.head.device
+
+    @property
+    def dtype(self):
+        return self._out_dtype
 
     @property
     def z(self) -> torch.Tensor:
@@ -57,26 +151,71 @@ class HeadOutputs:
             _, self._x = ops.detect_decode(self.head, want_z=False, want_x=True)
         return self._x
 
+    def _materialise(self):
+        # cached, so that in-place edits (augmented inference de-scales the prediction in place) are kept
+        if self._out_dtype == torch.float32:
+            return self.z
+        if self._zc is None:
+            self._zc = self.z.to(self._out_dtype)
+        return self._zc
 
-class SegLogits:
+    def to(self, *args, **kwargs):
+        device, dtype = _parse_to(args, kwargs, self.device, self._out_dtype)
+        if device.type != "cuda":
+            return self.z.to(device=device, dtype=dtype)       # leaves the device: hand over the reference tensor
+        if device != self.device:
+            return self.z.to(device=device, dtype=dtype)
+        ho = HeadOutputs.__new__(HeadOutputs)
+        ho.head, ho._z, ho._zc, ho._x, ho._out_dtype = self.head, self._z, None, self._x, dtype
+        return ho
+
+
+class SegLogits(_TensorLike):
     """Low-res seg logits (bs, C, h, w) — the input of the head's final
     ``nn.Upsample(scale_factor=8, mode='bilinear', align_corners=True)`` (core/models/yolo.py:183) —
-    plus the size that Upsample would produce.  ``.full()`` materialises the reference tensor."""
+    plus the size that Upsample would produce.  ``.full()`` materialises the reference tensor.
 
-    def __init__(self, low: torch.Tensor, scale_factor: int = 8, size: Optional[Tuple[int, int]] = None):
+    The object stands in for the full-resolution logits the reference model returns, so it answers ``.shape`` /
+    ``.device`` / ``.dtype`` as that tensor would, and ``.cpu()`` / ``.to()`` / ``.float()`` / ``.half()`` return a
+    ``SegLogits`` that remembers where the caller wants results (scripts/detect.py:198 calls
+    ``segoutput_to_target(seg_pred.cpu(), size=...)``): the low-res logits stay on the GPU, the kernels run there,
+    and only the RESULT (the mask) is moved to the requested device — 1.6 MB per image instead of a 13 MB logit D2H
+    plus a CPU argmax."""
+
+    def __init__(self, low: torch.Tensor, scale_factor: int = 8, size: Optional[Tuple[int, int]] = None,
+                 out_device=None, out_dtype=None):
         self.low = low
-        self.size = (int(low.shape[2]) * scale_factor, int(low.shape[3]) * scale_factor) if size is None else tuple(size)
+        self.full_hw = (int(low.shape[2]) * scale_factor, int(low.shape[3]) * scale_factor) if size is None else \
+            (int(size[0]), int(size[1]))
+        self.out_device = torch.device(out_device) if out_device is not None else low.device
+        self.out_dtype = out_dtype if out_dtype is not None else low.dtype
 
     @property
     def shape(self):
-        return (int(self.low.shape[0]), int(self.low.shape[1])) + tuple(self.size)
+        return (int(self.low.shape[0]), int(self.low.shape[1])) + tuple(self.full_hw)
 
     @property
     def device(self):
-        return self.low.device
+        return self.out_device
+
+    @property
+    def dtype(self):
+        return self.out_dtype
+
+    @property
+    def low_f32(self) -> torch.Tensor:
+        return _f32(self.low)
 
     def full(self) -> torch.Tensor:
-        return ops.upsample_bilinear_ac(self.low, self.size)
+        """The full-resolution fp32 logits on the GPU (bit-identical to ATen's CPU upsample of the fp32 logits)."""
+        return ops.upsample_bilinear_ac(self.low_f32, self.full_hw)
+
+    def _materialise(self):
+        return self.full().to(device=self.out_device, dtype=self.out_dtype)
+
+    def to(self, *args, **kwargs):
+        device, dtype = _parse_to(args, kwargs, self.out_device, self.out_dtype)
+        return SegLogits(self.low, size=self.full_hw, out_device=device, out_dtype=dtype)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -142,12 +281,12 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
         if cut is not None:
             keys, counts = ops.filter_levels(head, conf_thres, ml, classes, cut=cut)
             det, det_count = ops.nms_levels(head, keys, counts, conf_thres, iou_thres, agnostic, int(max_det), cut=cut)
-            if bool((det_count == -2).any()):              # the NMS ran out of emitted candidates somewhere: redo without the cut
-                cut = None
-        if cut is None:
+            # images whose NMS ran out of emitted candidates (det_count == -2) are redone uncut on the device
+            ops.detect_nms_redo_levels(head, conf_thres, iou_thres, classes, agnostic, ml, int(max_det), keys, counts, det, det_count)
+        else:
             det, det_count, _ = ops.detect_nms_levels(head, conf_thres, iou_thres, classes, agnostic, multi_label, int(max_det))
     else:
-        z = prediction.z if isinstance(prediction, HeadOutputs) else prediction
+        z = prediction.z if isinstance(prediction, HeadOutputs) else _f32(prediction)
         if has_labels:
             z = _append_label_rows(z, labels)
         if z.shape[0] == 0:
@@ -163,18 +302,38 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
 # ------------------------------------------------------------------------------------------------
 # f1  scale_coords / clip_coords        core/utils/general.py:598-623
 # ------------------------------------------------------------------------------------------------
+_PARAM_CACHE = {}
+
+
+def _letterbox_params_device(img1_shape, img0_shape, ratio_pad, device) -> torch.Tensor:
+    """(1, 5) fp32 device tensor of ``ops.letterbox_params``, cached per (shapes, ratio_pad, device): callers run
+    scale_coords once per image (val.py:250, detect.py:218), almost always with the same few shapes, and building a
+    device tensor from Python floats costs a pageable H2D copy each time."""
+    try:
+        key = (tuple(int(v) for v in img1_shape[:2]), tuple(int(v) for v in img0_shape[:2]),
+               None if ratio_pad is None else (float(ratio_pad[0][0]), float(ratio_pad[1][0]), float(ratio_pad[1][1])), str(device))
+    except (TypeError, ValueError, IndexError):
+        key = None
+    t = _PARAM_CACHE.get(key) if key is not None else None
+    if t is None:
+        t = torch.tensor([ops.letterbox_params(img1_shape, img0_shape, ratio_pad)], dtype=torch.float32, device=device)
+        if key is not None:
+            if len(_PARAM_CACHE) > 4096:
+                _PARAM_CACHE.clear()
+            _PARAM_CACHE[key] = t
+    return t
+
+
 def scale_coords(img1_shape, coords, img0_shape, ratio_pad=None):
     """Same signature and in-place behaviour as the reference: rescale ``coords`` (n, 4) xyxy (any row-strided
     view, e.g. ``det[:, :4]``) from ``img1_shape`` to ``img0_shape`` and clip; returns ``coords``."""
-    params = torch.tensor([ops.letterbox_params(img1_shape, img0_shape, ratio_pad)], dtype=torch.float32,
-                          device=coords.device)
-    return ops.scale_coords_(coords, params)
+    return ops.scale_coords_(coords, _letterbox_params_device(img1_shape, img0_shape, ratio_pad, coords.device))
 
 
 def clip_coords(boxes, shape):
     """general.py:614-623 on a CUDA tensor (n, 4), in place: clamp to the image ``shape`` (h, w)."""
-    params = torch.tensor([[0.0, 0.0, 1.0, float(shape[1]), float(shape[0])]], dtype=torch.float32, device=boxes.device)
-    ops.scale_coords_(boxes, params)
+    ops.scale_coords_(boxes, _letterbox_params_device((int(shape[0]), int(shape[1])), (int(shape[0]), int(shape[1])),
+                                                      ((1.0,), (0.0, 0.0)), boxes.device))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -283,12 +442,14 @@ class ConfusionMatrix:
 # ------------------------------------------------------------------------------------------------
 def segoutput_to_target(output, size=None) -> torch.Tensor:
     """argmax over classes -> float -> nearest resize to ``size`` -> (bs, size[0], size[1]) float32.
-    ``output``: full-res logits (bs, C, H, W) as in the reference, or ``SegLogits`` (fused path)."""
+    ``output``: full-res logits (bs, C, H, W) as in the reference (fp16 / bf16 are upcast), or ``SegLogits`` (fused
+    path; the mask is returned on the device the ``SegLogits`` stands for, e.g. the CPU after ``.cpu()``)."""
     if isinstance(output, SegLogits):
-        full = output.size
+        full = output.full_hw
         msize = full if size is None else tuple(int(v) for v in size)[-2:]
-        mask, _ = ops.seg_fused(output.low, full, mask_dtype=torch.float32, mask_size=msize)
-        return mask
+        mask, _ = ops.seg_fused(output.low_f32, full, mask_dtype=torch.float32, mask_size=msize)
+        return mask if output.out_device == mask.device else mask.to(output.out_device)
+    output = _f32(output)
     H, W = int(output.shape[2]), int(output.shape[3])
     msize = (H, W) if size is None else tuple(int(v) for v in size)[-2:]
     mask, _ = ops.seg_fullres(output, mask_dtype=torch.float32, mask_size=msize)
@@ -300,13 +461,20 @@ def segoutput_to_target(output, size=None) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 def seg_confusion_matrix(output, target: torch.Tensor, nclass: int, cm: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Target-clamped confusion matrix CM[r][p] (device int64, shape (slots, rows, C); sum over
-    slots) of argmax(output) against ``target`` — the sufficient statistic of metrics.py:350-388."""
+    slots) of argmax(output) against ``target`` — the sufficient statistic of metrics.py:350-388.
+    ``target`` may have any integer / float dtype and live on any device (the reference takes it through
+    ``.cpu().numpy().astype('int32')``, metrics.py:359,380); fp16 / bf16 logits are upcast."""
     C = int(output.shape[1])
     rows = ops.cm_rows_for(C, nclass)
+    dev = output.low.device if isinstance(output, SegLogits) else output.device
+    if not isinstance(target, torch.Tensor):
+        target = torch.as_tensor(target)
+    if target.device != dev or target.dtype != torch.int64:
+        target = target.to(device=dev, dtype=torch.int64)
     if isinstance(output, SegLogits):
-        _, cm = ops.seg_fused(output.low, output.size, target=target, cm=cm, cm_rows=rows)
+        _, cm = ops.seg_fused(output.low_f32, output.full_hw, target=target, cm=cm, cm_rows=rows)
     else:
-        _, cm = ops.seg_fullres(output, target=target, cm=cm, cm_rows=rows)
+        _, cm = ops.seg_fullres(_f32(output), target=target, cm=cm, cm_rows=rows)
     return cm
 
 
@@ -387,11 +555,8 @@ def seg_validation(model, n_segcls, valloader, half_precision=True, device=None,
             image = image / 255.0                                                  # val.py:64
             target = target.to(device, non_blocking=True)
             pred = model(image)[1]                                                 # val.py:45
-            if isinstance(pred, SegLogits):
-                if tuple(pred.size) != tuple(target.shape[1:]):
-                    pred = pred.full()
-                elif pred.low.dtype != torch.float32:
-                    pred = SegLogits(pred.low.float(), size=pred.size)
+            if isinstance(pred, SegLogits) and tuple(pred.full_hw) != tuple(target.shape[1:]):
+                pred = pred.full()
             if not isinstance(pred, SegLogits):
                 pred = pred.float()
                 if tuple(pred.shape[2:]) != tuple(target.shape[1:]):               # val.py:47
@@ -399,8 +564,9 @@ def seg_validation(model, n_segcls, valloader, half_precision=True, device=None,
             C = int(pred.shape[1])
             if cm is None:
                 rows = ops.cm_rows_for(C, n_segcls)
-                cm = torch.zeros((64, rows, C), dtype=torch.int64, device=target.device)
-            seg_confusion_matrix(pred, target.long(), n_segcls, cm=cm)             # val.py:48-49
+                cm_dev = pred.low.device if isinstance(pred, SegLogits) else pred.device
+                cm = torch.zeros((64, rows, C), dtype=torch.int64, device=cm_dev)
+            seg_confusion_matrix(pred, target, n_segcls, cm=cm)                    # val.py:48-49
     if cm is None:
         return 0.0
     correct, labeled, inter, union = seg_stats_from_cm(cm.sum(0).cpu().numpy(), n_segcls)

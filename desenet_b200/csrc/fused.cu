@@ -171,11 +171,14 @@ __device__ __forceinline__ void fused_scan_range(FusedSmem &s, int lo, int hi, f
     }
 }
 
+// only_flagged: the on-device redo of the confidence cut (dsn_detect_nms_redo_levels) - only images whose NMS reported
+// det_count == -2 are processed, every other CTA leaves at once.
 __global__ void __launch_bounds__(kNmsThreads) detect_fused_kernel(const HeadGeom g, const FilterOut f, const NmsParams p,
-                                                                   const float obj_logit_lo) {
+                                                                   const float obj_logit_lo, const int only_flagged) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FusedSmem &s = *reinterpret_cast<FusedSmem *>(smem_raw);
     const int b = blockIdx.x;
+    if (only_flagged && p.det_count[b] != -2) return;
     DSN_MARK(0);
     if (threadIdx.x == 0) {
         s.list_n = 0u;
@@ -257,11 +260,11 @@ __global__ void __launch_bounds__(kNmsThreads) detect_fused_kernel(const HeadGeo
 
 using namespace dsn;
 
-extern "C" __attribute__((visibility("default"))) int dsn_detect_nms_levels(
+static int detect_nms_levels_impl(
     const float *const *raw, const int *ny, const int *nx, const float *stride, const float *anchor_grid, int nl, int bs,
     int na, int no, float conf_thres, int multi_label, const uint64_t *class_mask, double iou_thres, int agnostic,
     int max_nms, int max_det, float max_wh, uint64_t *keys, int64_t cap, int *counts, float *det, int *det_count,
-    void *stream) {
+    void *stream, int only_flagged) {
     if (!stride || !anchor_grid) return DSN_E_INVALID;
     HeadGeom g;
     int rc = make_geom(g, raw, ny, nx, stride, anchor_grid, nl, bs, na, no);
@@ -279,6 +282,7 @@ extern "C" __attribute__((visibility("default"))) int dsn_detect_nms_levels(
     bool vec = true;
     for (int l = 0; l < nl; ++l) vec = vec && (g.plane[l] % 4 == 0) && (((uintptr_t)raw[l] & 15) == 0);
     if (!vec) {
+        if (only_flagged) return DSN_OK;       // no confidence cut exists for such layouts: nothing can be flagged
         rc = dsn_filter_levels(raw, ny, nx, nl, bs, na, no, conf_thres, multi_label, class_mask, keys, cap, counts, stream);
         if (rc) return rc;
         return dsn_nms_levels(raw, ny, nx, stride, anchor_grid, nl, bs, na, no, keys, cap, counts, conf_thres, iou_thres,
@@ -289,7 +293,25 @@ extern "C" __attribute__((visibility("default"))) int dsn_detect_nms_levels(
     static DeviceOnce once;
     rc = raise_dynamic_smem(once, detect_fused_kernel, (int)smem);
     if (rc) return rc;
-    detect_fused_kernel<<<bs, kNmsThreads, smem, st>>>(g, f, p, lo);
+    detect_fused_kernel<<<bs, kNmsThreads, smem, st>>>(g, f, p, lo, only_flagged);
     DSN_CHECK_LAUNCH();
     return DSN_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int dsn_detect_nms_levels(
+    const float *const *raw, const int *ny, const int *nx, const float *stride, const float *anchor_grid, int nl, int bs,
+    int na, int no, float conf_thres, int multi_label, const uint64_t *class_mask, double iou_thres, int agnostic,
+    int max_nms, int max_det, float max_wh, uint64_t *keys, int64_t cap, int *counts, float *det, int *det_count,
+    void *stream) {
+    return detect_nms_levels_impl(raw, ny, nx, stride, anchor_grid, nl, bs, na, no, conf_thres, multi_label, class_mask, iou_thres,
+                                  agnostic, max_nms, max_det, max_wh, keys, cap, counts, det, det_count, stream, 0);
+}
+
+extern "C" __attribute__((visibility("default"))) int dsn_detect_nms_redo_levels(
+    const float *const *raw, const int *ny, const int *nx, const float *stride, const float *anchor_grid, int nl, int bs,
+    int na, int no, float conf_thres, int multi_label, const uint64_t *class_mask, double iou_thres, int agnostic,
+    int max_nms, int max_det, float max_wh, uint64_t *keys, int64_t cap, int *counts, float *det, int *det_count,
+    void *stream) {
+    return detect_nms_levels_impl(raw, ny, nx, stride, anchor_grid, nl, bs, na, no, conf_thres, multi_label, class_mask, iou_thres,
+                                  agnostic, max_nms, max_det, max_wh, keys, cap, counts, det, det_count, stream, 1);
 }

@@ -34,15 +34,22 @@ class DetEvaluator:
         self._chunks = []          # (correct (bs, rows, niou) u8, det (bs, rows, 6), det_count (bs))
         self._tcls = []
 
-    def update(self, det: torch.Tensor, det_count: torch.Tensor, targets: torch.Tensor, img_hw, params: torch.Tensor):
+    def update(self, det: torch.Tensor, det_count: torch.Tensor, targets: torch.Tensor, img_hw, params: torch.Tensor,
+               max_labels_per_image: Optional[int] = None):
         """One batch.  ``det`` (bs, rows, 6) / ``det_count`` (bs): NMS output in network-input pixels; ``targets``
         (n, 6) [image, cls, normalised xywh] sorted by image (as the collate function builds them, val.py:213);
         ``img_hw`` = (height, width) of the network input; ``params`` (bs, 5) from ``ops.letterbox_params`` per image
-        (shapes[si] in val.py:239,250)."""
+        (shapes[si] in val.py:239,250).  ``max_labels_per_image``: an upper bound on the labels of one image (sizes the
+        kernels' shared memory); by default the true maximum of this batch — computed on the host for free when
+        ``targets`` arrives as a CPU tensor (the dataloader's collate output), with one sync when it is already on the
+        device."""
         bs, rows = int(det.shape[0]), int(det.shape[1])
         height, width = float(img_hw[0]), float(img_hw[1])
-        targets = targets.to(self.device, torch.float32).reshape(-1, 6)
-        n_lab = int(targets.shape[0])
+        targets = targets.reshape(-1, 6)
+        if max_labels_per_image is None:
+            max_labels_per_image = int(torch.bincount(targets[:, 0].long(), minlength=1).max()) if targets.shape[0] else 0
+        targets = targets.to(self.device, torch.float32)
+        n_lab = max(int(max_labels_per_image), 1)
         labelsn = ops.labels_to_native(targets, width, height, params)
         counts = torch.bincount(targets[:, 0].long(), minlength=bs)[:bs]
         label_off = torch.zeros(bs + 1, dtype=torch.int32, device=self.device)
@@ -50,9 +57,9 @@ class DetEvaluator:
         pred = det.clone() if not self.single_cls else det.clone().index_fill_(2, torch.tensor([5], device=det.device), 0.0)
         predn = pred.clone()                                                   # val.py:249
         ops.scale_coords_(predn, params, det_count)                            # val.py:250-251
-        correct = ops.process_batch(predn, det_count, labelsn, label_off, self.iouv, max(n_lab, 1))   # val.py:257
+        correct = ops.process_batch(predn, det_count, labelsn, label_off, self.iouv, n_lab)   # val.py:257
         if self.cm is not None:
-            self.cm.process_images(predn, det_count, labelsn, label_off, max(n_lab, 1), skip_empty=True)   # val.py:259
+            self.cm.process_images(predn, det_count, labelsn, label_off, n_lab, skip_empty=True)   # val.py:259
         self._chunks.append((correct, pred, det_count.clone()))
         self._tcls.append(targets[:, 1].clone())
         self.seen += bs

@@ -48,18 +48,68 @@ def class_mask(classes, nc: int):
     return (c_uint64 * 4)(*m)
 
 
-class Head:
-    """Raw Detect head outputs + geometry (the arguments of the ``*_levels`` entry points)."""
+class HeadSpec:
+    """Host copy of a Detect head's geometry buffers (``anchor_grid`` in pixels, ``stride``), built once per head:
+    on a real model both are CUDA buffers, and copying them to the host on every forward would cost two blocking
+    device syncs per batch."""
 
-    def __init__(self, levels: Sequence[torch.Tensor], anchor_grid, stride):
+    __slots__ = ("nl", "na", "anchors", "strides")
+
+    def __init__(self, anchor_grid, stride):
+        st = torch.as_tensor(stride, dtype=torch.float32).detach().cpu().reshape(-1)
+        self.nl = int(st.numel())
+        ag = torch.as_tensor(anchor_grid, dtype=torch.float32).detach().cpu().reshape(self.nl, -1, 2)
+        self.na = int(ag.shape[1])
+        self.anchors = ag
+        self.strides = st
+
+
+_SPEC_CACHE = {}
+
+
+def head_spec(anchor_grid, stride) -> HeadSpec:
+    """Cached ``HeadSpec``: keyed on (data_ptr, _version) of tensor arguments (an in-place update such as
+    ``check_anchor_order``'s flip, autoanchor.py:11-19, bumps the version) or on the value of plain sequences."""
+    if isinstance(anchor_grid, HeadSpec):
+        return anchor_grid
+
+    def key_of(v):
+        if isinstance(v, torch.Tensor):
+            return ("t", v.data_ptr(), v._version, tuple(v.shape), str(v.device))
+        try:
+            hash(v)
+            return ("v", v)
+        except TypeError:
+            return None
+
+    k1, k2 = key_of(anchor_grid), key_of(stride)
+    if k1 is None or k2 is None:
+        return HeadSpec(anchor_grid, stride)
+    spec = _SPEC_CACHE.get((k1, k2))
+    if spec is None:
+        if len(_SPEC_CACHE) > 256:
+            _SPEC_CACHE.clear()
+        spec = _SPEC_CACHE[(k1, k2)] = HeadSpec(anchor_grid, stride)
+    return spec
+
+
+class Head:
+    """Raw Detect head outputs + geometry (the arguments of the ``*_levels`` entry points).  ``anchor_grid`` may be a
+    ``HeadSpec`` (then ``stride`` is ignored)."""
+
+    def __init__(self, levels: Sequence[torch.Tensor], anchor_grid, stride=None):
         if len(levels) == 0:
             raise ValueError("no detection levels")
         self.levels: List[torch.Tensor] = [_require_cuda(l, f"levels[{i}]") for i, l in enumerate(levels)]
         self.device = self.levels[0].device
         self.nl = len(self.levels)
         self.bs = int(self.levels[0].shape[0])
-        ag = torch.as_tensor(anchor_grid, dtype=torch.float32).detach().cpu().reshape(self.nl, -1, 2)
-        self.na = int(ag.shape[1])
+        spec = head_spec(anchor_grid, stride)
+        self.spec = spec
+        if spec.nl != self.nl:
+            raise ValueError("one stride per level expected")
+        ag, st = spec.anchors, spec.strides
+        self.na = spec.na
         ch = int(self.levels[0].shape[1])
         if ch % self.na:
             raise ValueError(f"channels {ch} not divisible by na={self.na}")
@@ -68,9 +118,6 @@ class Head:
         for l in self.levels:
             if l.dim() != 4 or int(l.shape[0]) != self.bs or int(l.shape[1]) != ch or l.device != self.device:
                 raise ValueError("levels must be (bs, na*no, ny, nx) tensors on one device")
-        st = torch.as_tensor(stride, dtype=torch.float32).detach().cpu().reshape(-1)
-        if st.numel() != self.nl:
-            raise ValueError("one stride per level expected")
         self.ny = [int(l.shape[2]) for l in self.levels]
         self.nx = [int(l.shape[3]) for l in self.levels]
         self.A = self.na * sum(y * x for y, x in zip(self.ny, self.nx))
@@ -202,6 +249,23 @@ def detect_nms_levels(head: Head, conf_thres: float, iou_thres: float, classes=N
                                        _stream(head.device))
     _lib.check(rc, "dsn_detect_nms_levels")
     return det, det_count, counts
+
+
+def detect_nms_redo_levels(head: Head, conf_thres: float, iou_thres: float, classes, agnostic: bool, multi_label: bool,
+                           max_det: int, keys: torch.Tensor, counts: torch.Tensor, det: torch.Tensor, det_count: torch.Tensor,
+                           max_nms: int = MAX_NMS, max_wh: float = MAX_WH):
+    """On-device redo of the confidence cut: images whose ``det_count`` is -2 after ``nms_levels`` are redone without the
+    cut (one CTA per flagged image, all others exit at once).  No host round trip; capturable in a CUDA graph."""
+    lib = _lib.load()
+    ml = bool(multi_label) and head.nc > 1
+    with torch.cuda.device(head.device):
+        rc = lib.dsn_detect_nms_redo_levels(head.c_raw, head.c_ny, head.c_nx, head.c_stride, head.c_anchor, head.nl, head.bs,
+                                            head.na, head.no, float(conf_thres), int(ml), class_mask(classes, head.nc),
+                                            float(iou_thres), int(bool(agnostic)), int(max_nms), int(max_det), float(max_wh),
+                                            _ptr(keys), int(keys.shape[1]), _ptr(counts), _ptr(det), _ptr(det_count),
+                                            _stream(head.device))
+    _lib.check(rc, "dsn_detect_nms_redo_levels")
+    return det, det_count
 
 
 def nms_z(z: torch.Tensor, keys: torch.Tensor, counts: torch.Tensor, conf_thres: float, iou_thres: float,

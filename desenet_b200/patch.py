@@ -7,6 +7,12 @@ core/models/common.py:22-24; ``segoutput_to_target`` in val.py:38 / detect.py:32
 replacement has to be patched into every importing module, not only the defining one.  ``install()`` does
 that and returns a handle whose ``uninstall()`` restores the originals.
 
+Every installed callable is a DISPATCHER: CUDA tensors (fp32, or fp16 / bf16 as ``--half`` produces them,
+val.py:144,178-179) and the deferred head outputs (``HeadOutputs`` / ``SegLogits``) go to the sm_100a kernels;
+anything else — CPU tensors, numpy arrays, a model living on the CPU — goes to the reference's ORIGINAL function, exactly
+as before the patch (scripts/detect.py:198 hands ``seg_pred.cpu()`` to ``segoutput_to_target``; plots and dataset code
+call ``scale_coords`` on numpy arrays).  The kernels themselves have no CPU path; the reference keeps its own.
+
 Two levels:
   * ``install()``                     — function level (strict): same tensors in, same tensors out.
   * ``install(model=model, fused=True)`` — additionally swaps ``Detect.forward``'s post-conv part and the
@@ -21,21 +27,85 @@ from typing import Iterable, Optional
 import torch
 import torch.nn as nn
 
-from . import api
+from . import api, ops
 
-_FUNCS = {
-    "non_max_suppression": api.non_max_suppression,
-    "segoutput_to_target": api.segoutput_to_target,
-    "batch_pix_accuracy": api.batch_pix_accuracy,
-    "batch_intersection_union": api.batch_intersection_union,
-    "seg_validation": api.seg_validation,
+# names of the hot-path callables and the reference module that DEFINES each; every other module
+# holding the same function object imported it by name and is patched as well
+_DEFINED_IN = {
+    "non_max_suppression": ("core.utils.general",),
+    "scale_coords": ("core.utils.general",),
+    "box_iou": ("core.utils.general",),
+    "segoutput_to_target": ("core.utils.plots",),
+    "batch_pix_accuracy": ("core.utils.metrics",),
+    "batch_intersection_union": ("core.utils.metrics",),
+    "ap_per_class": ("core.utils.metrics",),
+    "seg_validation": ("scripts.val", "val"),
+    "process_batch": ("scripts.val", "val"),
 }
-# scale_coords / clip_coords are also called on CPU tensors and numpy arrays by the reference (plots, dataset
-# code), so they are patched with a dispatcher that only takes CUDA float32 tensors
 
-# modules of the reference that define or import those names
-_MODULES = ("core.utils.general", "core.utils.plots", "core.utils.metrics", "core.models.common",
-            "scripts.val", "scripts.detect", "scripts.show_seg_mIoU", "scripts.train", "val", "detect")
+
+def _is_cuda_tensor(t) -> bool:
+    return isinstance(t, torch.Tensor) and t.is_cuda and t.is_floating_point()
+
+
+def _ours(x) -> bool:
+    """True when the kernels take ``x``: a deferred head output or a floating-point CUDA tensor."""
+    return isinstance(x, (api.HeadOutputs, api.SegLogits)) or _is_cuda_tensor(x)
+
+
+def _make_dispatchers(orig):
+    """name -> dispatcher; ``orig[name]`` is the reference's own function (the fall-through for non-CUDA inputs)."""
+
+    def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False,
+                            labels=(), max_det=300):
+        fn = api.non_max_suppression if _ours(prediction) else orig["non_max_suppression"]
+        return fn(prediction, conf_thres, iou_thres, classes, agnostic, multi_label, labels, max_det)
+
+    def segoutput_to_target(output, size=None):
+        return (api.segoutput_to_target if _ours(output) else orig["segoutput_to_target"])(output, size)
+
+    def batch_pix_accuracy(output, target):
+        return (api.batch_pix_accuracy if _ours(output) else orig["batch_pix_accuracy"])(output, target)
+
+    def batch_intersection_union(output, target, nclass):
+        return (api.batch_intersection_union if _ours(output) else orig["batch_intersection_union"])(output, target, nclass)
+
+    def seg_validation(model, n_segcls, valloader, half_precision=True):
+        p = next(iter(model.parameters()), None) if hasattr(model, "parameters") else None
+        on_cuda = p is not None and p.is_cuda
+        return (api.seg_validation if on_cuda else orig["seg_validation"])(model, n_segcls, valloader, half_precision)
+
+    def scale_coords(img1_shape, coords, img0_shape, ratio_pad=None):
+        if _is_cuda_tensor(coords) and coords.dtype == torch.float32:
+            return api.scale_coords(img1_shape, coords, img0_shape, ratio_pad)
+        return orig["scale_coords"](img1_shape, coords, img0_shape, ratio_pad)
+
+    def _cuda_f32(*ts):
+        return all(_is_cuda_tensor(t) and t.dtype == torch.float32 for t in ts)
+
+    def box_iou(box1, box2):
+        return api.box_iou(box1, box2) if _cuda_f32(box1, box2) else orig["box_iou"](box1, box2)
+
+    def process_batch(detections, labels, iouv):
+        if _cuda_f32(detections, labels, iouv):
+            return api.process_batch(detections, labels, iouv)
+        return orig["process_batch"](detections, labels, iouv)
+
+    def ap_per_class(tp, conf, pred_cls, target_cls, plot=False, save_dir='.', names=()):
+        # plotting stays with the reference; without a GPU there is nothing to dispatch to
+        if plot or not torch.cuda.is_available():
+            return orig["ap_per_class"](tp, conf, pred_cls, target_cls, plot=plot, save_dir=save_dir, names=names)
+        return api.ap_per_class(tp, conf, pred_cls, target_cls)
+
+    out = dict(non_max_suppression=non_max_suppression, segoutput_to_target=segoutput_to_target,
+               batch_pix_accuracy=batch_pix_accuracy, batch_intersection_union=batch_intersection_union,
+               seg_validation=seg_validation, scale_coords=scale_coords, box_iou=box_iou, process_batch=process_batch,
+               ap_per_class=ap_per_class)
+    for name, fn in out.items():
+        fn._dsn_dispatch = True
+        fn._dsn_original = orig.get(name)
+        fn.__doc__ = f"desenet_b200 dispatcher for the reference's `{name}`: CUDA inputs -> sm_100a kernels, anything else -> the original."
+    return out
 
 
 class _LazyPermuted(list):
@@ -49,7 +119,10 @@ class _LazyPermuted(list):
 
     def _fill(self):
         if not self._done:
-            super().extend(self._ho.x)
+            xs = self._ho.x
+            if self._ho.dtype != torch.float32:
+                xs = [x.to(self._ho.dtype) for x in xs]
+            super().extend(xs)
             self._done = True
 
     def __iter__(self):
@@ -81,8 +154,8 @@ class DeferredUpsample(nn.Module):
         if self.training or not x.is_cuda:
             return self.original(x)
         if self.fused:
-            return api.SegLogits(x.float() if x.dtype != torch.float32 else x, scale_factor=self.scale)
-        return api.SegLogits(x.float(), scale_factor=self.scale).full().to(x.dtype)
+            return api.SegLogits(x, scale_factor=self.scale)
+        return api.SegLogits(x, scale_factor=self.scale).full().to(x.dtype)
 
 
 def _detect_forward_factory(original_forward, fused: bool):
@@ -90,11 +163,19 @@ def _detect_forward_factory(original_forward, fused: bool):
         if self.training or not x[0].is_cuda:
             return original_forward(self, x)
         raw = [self.m[i](x[i]) for i in range(self.nl)]                      # yolo.py:258
-        raw = [r.float() if r.dtype != torch.float32 else r for r in raw]
-        ho = api.HeadOutputs(raw, self.anchor_grid.reshape(self.nl, -1, 2), self.stride)
+        # host copy of anchor_grid / stride: once per head (re-read only when a buffer is updated in place)
+        ver = (self.anchor_grid.data_ptr(), self.anchor_grid._version, self.stride.data_ptr(), self.stride._version)
+        cached = getattr(self, "_dsn_spec", None)
+        if cached is None or cached[0] != ver:
+            cached = (ver, ops.HeadSpec(self.anchor_grid.reshape(self.nl, -1, 2), self.stride))
+            object.__setattr__(self, "_dsn_spec", cached)
+        ho = api.HeadOutputs(raw, cached[1], out_dtype=raw[0].dtype)
         if fused:
             return ho, _LazyPermuted(ho)
-        return ho.z, ho.x                                                    # yolo.py:277
+        z, xs = ho.z, ho.x                                                   # yolo.py:277
+        if raw[0].dtype != torch.float32:
+            z, xs = z.to(raw[0].dtype), [v.to(raw[0].dtype) for v in xs]
+        return z, xs
     return forward
 
 
@@ -119,58 +200,54 @@ class Installed:
         self.uninstall()
 
 
-def install(model: Optional[nn.Module] = None, fused: bool = True, modules: Optional[Iterable[str]] = None) -> Installed:
-    """Patch every already-imported reference module that holds one of the hot-path callables; with
-    ``model`` also defer the Detect decode and the seg head's final Upsample of that model instance."""
-    h = Installed()
-    for name in (modules or _MODULES):
-        mod = sys.modules.get(name)
-        if mod is None:
-            continue
-        for fn, repl in _FUNCS.items():
-            if hasattr(mod, fn):
-                h._set(mod, fn, repl)
-    # scale_coords: CUDA float32 tensors go to the kernel, everything else (CPU tensors, numpy) to the original
-    for name in (modules or _MODULES):
-        mod = sys.modules.get(name)
-        orig = getattr(mod, "scale_coords", None) if mod is not None else None
-        if orig is None or getattr(orig, "_dsn_dispatch", False):
-            continue
-
-        def scale_coords(img1_shape, coords, img0_shape, ratio_pad=None, _orig=orig):
-            if isinstance(coords, torch.Tensor) and coords.is_cuda and coords.dtype == torch.float32:
-                return api.scale_coords(img1_shape, coords, img0_shape, ratio_pad)
-            return _orig(img1_shape, coords, img0_shape, ratio_pad)
-
-        scale_coords._dsn_dispatch = True
-        h._set(mod, "scale_coords", scale_coords)
-    # detection metrics (SURVEY 8f ranks 2-3): CUDA tensors go to the kernels; ap_per_class takes the device path whenever
-    # a GPU is present and no plot is requested (plotting stays with the reference)
-    def _cuda_f32(*ts):
-        return all(isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 for t in ts)
-
-    for name in (modules or _MODULES):
-        mod = sys.modules.get(name)
-        if mod is None:
-            continue
-        for fn in ("box_iou", "process_batch", "ap_per_class"):
-            orig = getattr(mod, fn, None)
-            if orig is None or getattr(orig, "_dsn_dispatch", False):
+def _find_originals(modules):
+    """The reference's own function objects: from the defining modules, or (explicit ``modules``) from wherever
+    the name is found first."""
+    orig = {}
+    if modules is None:
+        for name, mods in _DEFINED_IN.items():
+            for m in mods:
+                mod = sys.modules.get(m)
+                fn = getattr(mod, name, None) if mod is not None else None
+                if fn is not None:
+                    if getattr(fn, "_dsn_dispatch", False):        # installed before: the original is remembered on it
+                        fn = fn._dsn_original
+                    if fn is not None:
+                        orig[name] = fn
+                        break
+    else:
+        for m in modules:
+            mod = sys.modules.get(m)
+            if mod is None:
                 continue
-            if fn == "box_iou":
-                def repl(box1, box2, _orig=orig):
-                    return api.box_iou(box1, box2) if _cuda_f32(box1, box2) else _orig(box1, box2)
-            elif fn == "process_batch":
-                def repl(detections, labels, iouv, _orig=orig):
-                    return api.process_batch(detections, labels, iouv) if _cuda_f32(detections, labels, iouv) else _orig(detections, labels, iouv)
-            else:
-                def repl(tp, conf, pred_cls, target_cls, plot=False, save_dir='.', names=(), _orig=orig):
-                    if plot or not torch.cuda.is_available():
-                        return _orig(tp, conf, pred_cls, target_cls, plot=plot, save_dir=save_dir, names=names)
-                    return api.ap_per_class(tp, conf, pred_cls, target_cls)
-            repl._dsn_dispatch = True
-            repl.__name__ = fn
-            h._set(mod, fn, repl)
+            for name in _DEFINED_IN:
+                fn = getattr(mod, name, None)
+                if fn is not None and name not in orig and not getattr(fn, "_dsn_dispatch", False):
+                    orig[name] = fn
+    return orig
+
+
+def install(model: Optional[nn.Module] = None, fused: bool = True, modules: Optional[Iterable[str]] = None) -> Installed:
+    """Patch every already-imported module that holds one of the reference's hot-path callables (wherever it was
+    imported by name — including ``__main__`` when scripts/detect.py or scripts/val.py is the entry script); with
+    ``model`` also defer the Detect decode and the seg head's final Upsample of that model instance.
+    ``modules``: restrict the patch to these module names (their current attributes are taken as the originals)."""
+    h = Installed()
+    modules = list(modules) if modules is not None else None
+    orig = _find_originals(modules)
+    disp = _make_dispatchers(orig)
+    if modules is None:
+        targets = [m for m in list(sys.modules.values()) if m is not None and getattr(m, "__name__", "").split(".")[0] != "desenet_b200"]
+    else:
+        targets = [sys.modules[m] for m in modules if m in sys.modules]
+    for mod in targets:
+        d = getattr(mod, "__dict__", None)
+        if not isinstance(d, dict):
+            continue
+        for name, fn in orig.items():
+            cur = d.get(name)
+            if cur is not None and cur is fn:                     # the very function object of the reference
+                h._set(mod, name, disp[name])
     if model is not None:
         patched_classes = set()
         for m in model.modules():
@@ -178,13 +255,27 @@ def install(model: Optional[nn.Module] = None, fused: bool = True, modules: Opti
             if cls.__name__ == "Detect" and hasattr(m, "anchor_grid") and hasattr(m, "m") and cls not in patched_classes:
                 h._set(cls, "forward", _detect_forward_factory(cls.forward, fused))
                 patched_classes.add(cls)
-            out = getattr(m, "out", None)
-            if (cls.__name__.startswith("SegMask") and isinstance(out, nn.Sequential) and len(out)
-                    and isinstance(out[-1], nn.Upsample)):
-                idx = len(out) - 1
-                h._undo.append((_SeqSlot(out, idx), "module", out[idx]))
-                out[idx] = DeferredUpsample(out[idx], fused)
+            if cls.__name__.startswith("SegMask"):
+                # every seg head of the reference ends in nn.Sequential(..., nn.Conv2d(c, n_segcls, k), nn.Upsample(x8,
+                # bilinear, align_corners=True)) — `out` (PSP yolo.py:178-184, PSP2 :227-230, BiSe :67-73), `decoder`
+                # (Lab :118-124), `m` (Base :141-150); the aux heads (training only) have the same tail
+                for seq in m.children():
+                    if _is_seg_tail(seq):
+                        idx = len(seq) - 1
+                        h._undo.append((_SeqSlot(seq, idx), "module", seq[idx]))
+                        seq[idx] = DeferredUpsample(seq[idx], fused)
     return h
+
+
+def _is_seg_tail(seq) -> bool:
+    if not isinstance(seq, nn.Sequential) or len(seq) < 2:
+        return False
+    up, conv = seq[-1], seq[-2]
+    if not isinstance(up, nn.Upsample) or up.mode != "bilinear" or not up.align_corners or up.scale_factor is None:
+        return False
+    sf = up.scale_factor
+    sf = sf if not isinstance(sf, (tuple, list)) else (sf[0] if len(set(sf)) == 1 else None)
+    return sf is not None and float(sf) == int(sf) and isinstance(conv, (nn.Conv2d, nn.Identity))
 
 
 class _SeqSlot:

@@ -56,7 +56,8 @@ class PostProcessor:
         with torch.cuda.device(d):
             self.cut = ops.ConfCut(bs, d) if self.conf_cut else None
         self._last_head = None
-        self.kernels_per_step = (1 if fused_det else (3 if self.conf_cut else 2)) + (0 if mode == "det_only" else 1)
+        # cut + filter + NMS + redo (all CTAs of the redo exit at once unless an image was starved) | filter + NMS | fused
+        self.kernels_per_step = (1 if fused_det else (4 if self.conf_cut else 2)) + (0 if mode == "det_only" else 1)
         self._graphs = {}
 
     # ---- enqueue-only device path --------------------------------------------------------------
@@ -105,6 +106,11 @@ class PostProcessor:
                           keys=self.keys, counts=self.counts, cut=cut)
         ops.nms_levels(head, self.keys, self.counts, kw["conf_thres"], kw["iou_thres"], kw["agnostic"], kw["max_det"],
                        det=self.det, det_count=self.det_count, cut=cut)
+        if cut is not None:
+            # images the sampled cut starved (det_count == -2) are redone uncut on the device, inside the same enqueue /
+            # graph: a negative count never reaches a consumer (HostPipeline, DetEvaluator, graph replay)
+            ops.detect_nms_redo_levels(head, kw["conf_thres"], kw["iou_thres"], kw["classes"], kw["agnostic"], kw["multi_label"],
+                                       kw["max_det"], keys=self.keys, counts=self.counts, det=self.det, det_count=self.det_count)
         self._scale()
 
     def _scale(self):
@@ -143,13 +149,8 @@ class PostProcessor:
     def detections(self) -> List[torch.Tensor]:
         """Host-synchronising: list of (n_i, 6) tensors like the reference's non_max_suppression."""
         n = self.det_count.cpu().tolist()
-        if any(v == -2 for v in n) and self._last_head is not None:
-            # the sampled confidence cut left an image with fewer than max_nms candidates: results would not be
-            # guaranteed identical to the reference, so the detection chain is redone without the cut (rare)
-            self._det(self._last_head, allow_cut=False)
-            n = self.det_count.cpu().tolist()
-        if any(v < 0 for v in n):
-            raise RuntimeError("desenet_b200: candidate buffer overflow (internal capacity error)")
+        if any(v < 0 for v in n):           # -1: key buffer too small; -2 cannot occur (redone on the device in _det)
+            raise RuntimeError(f"desenet_b200: detection chain reported {min(n)} (internal capacity error)")
         return [self.det[i, :n[i]].clone() for i in range(self.bs)]
 
 

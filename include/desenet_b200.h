@@ -88,7 +88,8 @@ int dsn_filter_levels(const float *const *raw, const int *ny, const int *nx, int
  * dsn_filter_levels_cut then emits only candidates at or above that bound - exactly the best ones.  dsn_nms_levels
  * takes cut_dropped: an image whose NMS runs out of emitted candidates before it stops by itself (max_det
  * survivors or max_nms candidates consumed) although a cut was in force gets det_count = -2 (dropped candidates
- * could have mattered) and the caller re-runs without the cut; every other result is exactly the uncut one.
+ * could have mattered) and the caller re-runs without the cut (on the device: dsn_detect_nms_redo_levels); every other result is exactly
+ * the uncut one.
  * Needs 16-byte aligned planes with ny*nx % 4 == 0 (DSN_E_UNSUPPORTED otherwise: run without a cut).
  *   target      candidates the NMS is expected to consume at most (e.g. 16*max_det), >= 1
  *   hist_ws     reserved, may be NULL (the histograms live in shared memory)
@@ -140,6 +141,17 @@ int dsn_detect_nms_levels(const float *const *raw, const int *ny, const int *nx,
                           float conf_thres, int multi_label, const uint64_t *class_mask,
                           double iou_thres, int agnostic, int max_nms, int max_det, float max_wh,
                           uint64_t *keys, int64_t cap, int *counts, float *det, int *det_count, void *stream);
+
+/* On-device redo for the confidence cut: the same kernel, but only images whose det_count[b] == -2 (the NMS of
+ * dsn_nms_levels ran out of emitted candidates while a cut was in force) are processed - uncut filter + NMS by one
+ * CTA per flagged image; every other CTA exits at once.  Enqueued right after dsn_nms_levels it makes the
+ * cut -> filter -> NMS chain exact without a host round trip (no det_count == -2 ever reaches the caller), so the
+ * chain can be captured in a CUDA graph.  keys / counts / det / det_count are the buffers of the preceding calls. */
+int dsn_detect_nms_redo_levels(const float *const *raw, const int *ny, const int *nx, const float *stride,
+                               const float *anchor_grid, int nl, int bs, int na, int no,
+                               float conf_thres, int multi_label, const uint64_t *class_mask,
+                               double iou_thres, int agnostic, int max_nms, int max_det, float max_wh,
+                               uint64_t *keys, int64_t cap, int *counts, float *det, int *det_count, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Segmentation tail.
