@@ -147,6 +147,7 @@ class DeferredUpsample(nn.Module):
         super().__init__()
         self.original = original
         self.fused = fused
+        self.training = original.training      # a module built after model.eval() would otherwise start in training mode
         sf = original.scale_factor
         self.scale = int(sf if not isinstance(sf, (tuple, list)) else sf[0])
 

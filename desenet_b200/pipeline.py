@@ -16,7 +16,10 @@ class PostProcessor:
                  iou_thres=0.45, classes=None, agnostic=False, multi_label=False, max_det=300, mode="detect",
                  nclass: Optional[int] = None, mask_dtype=torch.float32, device=None, overlap_streams=True,
                  na: int = 3, fused_det: bool = False, scale_params: Optional[torch.Tensor] = None, round_boxes: bool = False,
-                 conf_cut: Optional[bool] = None):
+                 conf_cut: Optional[bool] = None, det_out=None, det_count_out=None, gather=None):
+        """``det_out`` / ``det_count_out``: write the detections there instead of into buffers of this object (tensors, or
+        ``peer.RawView`` slices of a gather root's buffer); ``gather = (PeerGather, slot)``: after the detection chain of a
+        batch, signal the root that this rank's rows of that slot are complete (see ``desenet_b200.peer``)."""
         assert mode in ("detect", "eval", "det_only")
         assert 0 <= conf_thres <= 1 and 0 <= iou_thres <= 1
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -40,8 +43,10 @@ class PostProcessor:
         with torch.cuda.device(d):
             self.keys = torch.empty((bs, cap), dtype=torch.int64, device=d)
             self.counts = torch.zeros((bs,), dtype=torch.int32, device=d)
-            self.det = torch.zeros((bs, max(int(max_det), 0), 6), dtype=torch.float32, device=d)
-            self.det_count = torch.zeros((bs,), dtype=torch.int32, device=d)
+            self.det = torch.zeros((bs, max(int(max_det), 0), 6), dtype=torch.float32, device=d) if det_out is None else det_out
+            self.det_count = torch.zeros((bs,), dtype=torch.int32, device=d) if det_count_out is None else det_count_out
+            assert tuple(self.det.shape) == (bs, max(int(max_det), 0), 6) and tuple(self.det_count.shape) == (bs,)
+            self.gather = gather
             self.mask = torch.empty((bs, self.H, self.W), dtype=mask_dtype, device=d) if mode == "detect" else None
             self.cm = torch.zeros((min(bs, 64), self.cm_rows, n_segcls), dtype=torch.int64, device=d) if mode == "eval" else None
             self.side = torch.cuda.Stream(device=d, priority=-1) if (overlap_streams and mode != "det_only") else None
@@ -57,7 +62,8 @@ class PostProcessor:
             self.cut = ops.ConfCut(bs, d) if self.conf_cut else None
         self._last_head = None
         # cut + filter + NMS + redo (all CTAs of the redo exit at once unless an image was starved) | filter + NMS | fused
-        self.kernels_per_step = (1 if fused_det else (4 if self.conf_cut else 2)) + (0 if mode == "det_only" else 1)
+        self.kernels_per_step = (1 if fused_det else (4 if self.conf_cut else 2)) + (0 if mode == "det_only" else 1) \
+            + (1 if gather is not None else 0)
         self._graphs = {}
 
     # ---- enqueue-only device path --------------------------------------------------------------
@@ -116,6 +122,8 @@ class PostProcessor:
     def _scale(self):
         if self.scale_params is not None and self.det.shape[1] > 0:
             ops.scale_coords_(self.det, self.scale_params, self.det_count, self.round_boxes)
+        if self.gather is not None:
+            self.gather[0].signal(self.gather[1])
 
     def _seg(self, seg_low, target):
         if self.mode == "detect":
@@ -202,14 +210,33 @@ class HostPipeline:
             if slot["target"] is not None:
                 slot["target"].copy_(h_target, non_blocking=True)
             pp.run_head(slot["head"], slot["seg"], slot["target"])
-            slot["h_det"].copy_(pp.det, non_blocking=True)
-            slot["h_cnt"].copy_(pp.det_count, non_blocking=True)
-            if slot["h_mask"] is not None:
-                slot["h_mask"].copy_(pp.mask, non_blocking=True)
-            if slot["h_cm"] is not None:
-                slot["h_cm"].copy_(pp.cm, non_blocking=True)
-            slot["done"].record(slot["stream"])
+            self._copy_back(slot, pp)
         return slot
+
+    def submit_device(self, levels, seg=None, target=None):
+        """Same step for inputs that are ALREADY in device memory (what the patched model hands over): no H2D, the
+        results still go back to pinned host memory."""
+        slot = self.slots[self.i % self.depth]
+        self.i += 1
+        pp = slot["pp"]
+        head = slot.get("dev_heads", {}).get(levels[0].data_ptr())
+        if head is None:
+            head = ops.Head(levels, pp.anchor_grid, pp.stride)
+            slot.setdefault("dev_heads", {})[levels[0].data_ptr()] = head
+        slot["stream"].wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(slot["stream"]):
+            pp.run_head(head, seg, target)
+            self._copy_back(slot, pp)
+        return slot
+
+    def _copy_back(self, slot, pp):
+        slot["h_det"].copy_(pp.det, non_blocking=True)
+        slot["h_cnt"].copy_(pp.det_count, non_blocking=True)
+        if slot["h_mask"] is not None:
+            slot["h_mask"].copy_(pp.mask, non_blocking=True)
+        if slot["h_cm"] is not None:
+            slot["h_cm"].copy_(pp.cm, non_blocking=True)
+        slot["done"].record(slot["stream"])
 
     def synchronize(self):
         for s in self.slots:

@@ -264,6 +264,28 @@ int dsn_det_confusion_matrix(const float *det, int64_t det_image_stride, int64_t
                              int max_labels_per_image, int nc, float conf, float iou_thres, int skip_empty,
                              uint64_t *matrix, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU detection gather over peer memory.  One process per GPU; the reference never shards
+ * evaluation (scripts/val.py:170-172), so this is new: the gather root owns the gathered (global_bs, max_det, 6) /
+ * (global_bs) buffers, every rank passes pointers into ITS slice of them as `det` / `det_count` of dsn_nms_levels, and
+ * the NMS kernel's result rows go over NVLink as they are produced.  These five calls are host-side set-up (they are
+ * NOT enqueue-only: they allocate / map memory on the current device):
+ *   dsn_peer_alloc   cudaMalloc'ed, zero-filled buffer (CUDA IPC needs a cudaMalloc allocation of its own)
+ *   dsn_peer_export  64-byte CUDA IPC handle of such a buffer, to be sent to the other processes
+ *   dsn_peer_open    map another process's buffer into this one (peer access enabled lazily); dsn_peer_close unmaps */
+int dsn_peer_alloc(int64_t bytes, void **ptr);
+int dsn_peer_free(void *ptr);
+int dsn_peer_export(const void *ptr, unsigned char *handle64);
+int dsn_peer_open(const unsigned char *handle64, void **ptr);
+int dsn_peer_close(void *ptr);
+/* Enqueue-only.  dsn_peer_signal: after everything enqueued before it on `stream`, increment *local_step (device
+ * word of this rank) and publish the new value to *remote_flag (a word of the root's buffer) with a system-scope
+ * release store.  dsn_peer_wait: on the root, spin (acquire loads) until flags[i] - targets[i] >= 0 (both device
+ * uint32 arrays) for every i < n, for at most timeout_ms; on a timeout *status (device int, caller-zeroed) becomes
+ * 1 + index of a missing flag. */
+int dsn_peer_signal(unsigned int *local_step, unsigned int *remote_flag, void *stream);
+int dsn_peer_wait(const unsigned int *flags, const unsigned int *targets, int n, int64_t timeout_ms, int *status, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -149,7 +149,8 @@ def test_conf_cut_fallback_when_sample_misleads(env):
     """Adversarial input: only the SAMPLED cells (every 64th unit of 4 cells) are confident, so the histogram
     over-estimates 64x and the cut lands above almost everything; with agnostic NMS the few emitted candidates
     (same box for all classes of a cell) cannot give max_det survivors, the NMS runs out of emitted candidates
-    -> det_count -2 -> detections() redoes the batch without the cut."""
+    -> det_count -2 after dsn_nms_levels -> the on-device redo (dsn_detect_nms_redo_levels, part of the same enqueue and
+    of a captured graph) reruns those images without the cut: no negative count ever reaches a consumer."""
     api, ops, pipeline = env
     bs, S, nc = 2, 256, 80
     kw = dict(conf_thres=0.001, iou_thres=0.6, multi_label=True, max_det=300, agnostic=True)
@@ -177,12 +178,28 @@ def test_conf_cut_fallback_when_sample_misleads(env):
                                             conf_cut=cut, **kw)
     a, b = mk(False), mk(True)
     a.run(dl)
-    b.run(dl)
-    torch.cuda.synchronize()
+    # the chain by hand up to the NMS: the misled cut starves every image
+    head = ops.Head(dl, port.DEFAULT_ANCHORS, port.DEFAULT_STRIDES)
+    cut = ops.conf_cut_levels(head, kw["conf_thres"], True, None, target=b.cut_target, cut=b.cut)
+    ops.filter_levels(head, kw["conf_thres"], True, None, cap=int(b.keys.shape[1]), keys=b.keys, counts=b.counts, cut=cut)
+    ops.nms_levels(head, b.keys, b.counts, kw["conf_thres"], kw["iou_thres"], True, kw["max_det"], det=b.det, det_count=b.det_count, cut=cut)
     assert (b.det_count.cpu() == -2).all()
+    ops.detect_nms_redo_levels(head, kw["conf_thres"], kw["iou_thres"], None, True, True, kw["max_det"], keys=b.keys, counts=b.counts,
+                               det=b.det, det_count=b.det_count)
     for x, y in zip(a.detections(), b.detections()):
         assert torch.equal(x, y)
-    assert (b.det_count.cpu() >= 0).all()
+    # the whole chain in one enqueue, and replayed from a CUDA graph
+    c = mk(True)
+    c.run(dl)
+    torch.cuda.synchronize()
+    assert (c.det_count.cpu() >= 0).all()
+    for x, y in zip(a.detections(), c.detections()):
+        assert torch.equal(x, y)
+    c.capture(dl)
+    c.det_count.fill_(-7)
+    c.replay()
+    for x, y in zip(a.detections(), c.detections()):
+        assert torch.equal(x, y)
     ho = api.HeadOutputs(dl, port.DEFAULT_ANCHORS, port.DEFAULT_STRIDES)
     for x, y in zip(api.non_max_suppression(ho, **kw), a.detections()):      # same fallback inside the API call
         assert torch.equal(x, y)
