@@ -404,11 +404,18 @@ def run_config(args, cfg_id, rank, world, local_rank, dev, *, primary, host_info
     # ---- untimed: clock ramp + W warm-up steps ----------------------------------------------------
     t_end = time.perf_counter() + (args.prewarm_ms if primary else 200.0) / 1e3
     i = 0
-    while time.perf_counter() < t_end:
-        for _ in range(20):
+    if nccl_det is not None:
+        # NCCL route: every rank must issue the same number of collectives - a fixed count instead of a time-based ramp
+        for _ in range(200 if primary else 60):
             step(i)
             i += 1
         torch.cuda.synchronize(dev)
+    else:
+        while time.perf_counter() < t_end:
+            for _ in range(20):
+                step(i)
+                i += 1
+            torch.cuda.synchronize(dev)
     for w in range(warmup):
         step(w)
     join()

@@ -18,9 +18,16 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-cudart", "static",
 ]
+OBJ_TAG = "obj"
 if os.environ.get("DSN_TIMING"):          # tuning build: phase timeline markers, separate .so
     NVCC_FLAGS += ["-DDSN_TIMING", "-rdc=true"]
     LIB = os.path.join(LIBDIR, "libdesenet_b200_timing.so")
+    OBJ_TAG = "obj_timing"
+elif os.environ.get("DSN_VARIANT"):       # tuning build "name:-DFOO=1 -DBAR=2": separate .so with extra compile-time switches
+    _name, _, _flags = os.environ["DSN_VARIANT"].partition(":")
+    NVCC_FLAGS += _flags.split()
+    LIB = os.path.join(LIBDIR, f"libdesenet_b200_{_name}.so")
+    OBJ_TAG = f"obj_{_name}"
 
 
 def _nvcc() -> str:
@@ -42,7 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(HERE, "..", "build", "obj_timing" if os.environ.get("DSN_TIMING") else "obj")
+    objdir = os.path.join(HERE, "..", "build", OBJ_TAG)
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
     procs = []

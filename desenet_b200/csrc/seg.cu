@@ -26,6 +26,13 @@ struct SegParams {
 };
 
 constexpr int kMaxPackedC = 4;      // template instantiations of the fast path
+// build-time tuning switches (no run-time environment knobs in the launchers)
+#ifndef DSN_SEG_MASK_BULK
+#define DSN_SEG_MASK_BULK 1          // detect-mode fp32 mask: rows staged in shared memory, written with TMA bulk stores
+#endif
+#ifndef DSN_SEG_MASK_CTAS_PER_SM
+#define DSN_SEG_MASK_CTAS_PER_SM 2
+#endif
 constexpr int kPrefetchRows = 8;    // eval kernel: target rows pulled into L2 this far ahead of the register loads
 
 // ---- packed confusion-matrix counters ------------------------------------------------------
@@ -154,29 +161,12 @@ __device__ __forceinline__ SrcCols<C> load_src_row(const float *img, int plane, 
 // inner loop is branch-free: two LDS for the row's (l0, l1), C x 4 FMUL+FFMA, the compares, one
 // 16 B streaming store.  Between segments T/B swap roles and the stale one is rebuilt from raw
 // values prefetched one source row ahead.
-// RING (eval mode without a mask): the int64 target does not pass through registers on its way in.  Every thread
-// streams its own 32 B of each row into a private shared-memory ring with cp.async (LDGSTS, 16 B, L2 only), kRingAhead
-// rows ahead of the row it is working on, and reads it back with two LDS.128 when the row's predictions are done.
-// Registers bound the bytes a thread can keep in flight with plain loads, and those were consumed right after they
-// were issued (nothing in flight during the arithmetic); with the ring the next rows' bytes are in flight all the time.
-constexpr int kRingSlots = 8;      // rows per thread in the ring (power of two)
-constexpr int kRingAhead = 4;      // rows in flight beyond the group being consumed
-constexpr int kRingPrefetch = 12;  // rows ahead of the issue pointer that are prefetched into L2
-__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <int C, bool HAS_TGT, int MASK, typename W, bool RING = false>
+template <int C, bool HAS_TGT, int MASK, typename W>
 __global__ void __maxnreg__(HAS_TGT ? 96 : 128) seg_fused_rows_kernel(const SegParams p, const int rows_per_cta) {
     extern __shared__ __align__(16) unsigned char seg_smem[];
     float2 *lam = reinterpret_cast<float2 *>(seg_smem);                    // [H]   (l0, l1) of output row Y
     int *y0_of = reinterpret_cast<int *>(lam + p.H);                       // [H]   source row y0 of output row Y
     int *seg_start = y0_of + p.H;                                          // [h+1] first output row whose y0 is the index
-    // [RING] target ring: slot s, half q of thread t at ((s * 2 + q) * blockDim.x + t) * 16 bytes (conflict-free LDS.128)
-    unsigned char *ring = seg_smem + (((sizeof(float2) + sizeof(int)) * (size_t)p.H + sizeof(int) * (size_t)(p.h + 1) + 15) & ~(size_t)15);
     __shared__ unsigned int cm_smem[DSN_MAX_CM_ROWS * kMaxPackedC];
     const int G = p.W >> 2;
     const int plane = p.h * p.w;
@@ -238,36 +228,6 @@ __global__ void __maxnreg__(HAS_TGT ? 96 : 128) seg_fused_rows_kernel(const SegP
         int since_flush = 0;
         bool finite = true;
         unsigned int hi_sink = 0;
-        // [RING] stream state: next row to issue, rows of the run still to issue, issue / consume counters
-        const long long *tp_iss = tp;
-        long long iss_left = r_end - r_begin;
-        unsigned int iss = 0, con = 0;
-        auto ring_issue = [&]() {
-            // the row kRingPrefetch rows further down is pulled into L2 (one prefetch per 128 B line = every fourth lane),
-            // so that the cp.async of a row finds it there
-            if (iss_left > kRingPrefetch && active && (threadIdx.x & 3) == 0)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(tp_iss + (size_t)kRingPrefetch * p.W));
-            if (iss_left > 0 && active) {
-                unsigned char *d = ring + ((size_t)((iss & (kRingSlots - 1)) * 2) * blockDim.x + threadIdx.x) * 16;
-                cp_async16(d, tp_iss);
-                cp_async16(d + (size_t)blockDim.x * 16, tp_iss + 2);
-            }
-            cp_async_commit();
-            ++iss;
-            tp_iss += p.W;
-            --iss_left;
-        };
-        auto ring_read = [&](unsigned int slot, long long (&tv)[4]) {
-            const unsigned char *d = ring + ((size_t)((slot & (kRingSlots - 1)) * 2) * blockDim.x + threadIdx.x) * 16;
-            const longlong2 ta = *reinterpret_cast<const longlong2 *>(d);
-            const longlong2 tb = *reinterpret_cast<const longlong2 *>(d + (size_t)blockDim.x * 16);
-            tv[0] = ta.x; tv[1] = ta.y; tv[2] = tb.x; tv[3] = tb.y;
-        };
-        if constexpr (RING) {
-#pragma unroll
-            for (int q = 0; q < kRingAhead; ++q) ring_issue();
-        }
-
         // predictions of one output row only (no mask, no target): used by the pure-eval group path
         auto row_pred = [&](const float2 lm, const float (&top)[C][4], const float (&bot)[C][4], int (&pred)[4]) {
             if (C == 2 && finite) {
@@ -343,24 +303,6 @@ __global__ void __maxnreg__(HAS_TGT ? 96 : 128) seg_fused_rows_kernel(const SegP
         // output rows [Y, ye) of one segment; the target loads of 4 rows are issued together (8 x 16 B in flight)
         auto segment = [&](int Y, const int ye, const float (&top)[C][4], const float (&bot)[C][4]) {
             for (; Y + 4 <= ye; Y += 4) {
-                if constexpr (RING) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) ring_issue();
-                    cp_async_wait<kRingAhead>();
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        long long t4[4] = {0, 0, 0, 0};
-                        if (active) ring_read(con + q, t4);
-                        row_body(lam[Y + q], top, bot, t4);
-                    }
-                    con += 4;
-                    since_flush += 4;
-                    if (since_flush >= 60) {
-                        acc.flush(cm_smem, p.cm_rows);
-                        since_flush = 0;
-                    }
-                    continue;
-                }
                 long long tv[4][4];
                 if (HAS_TGT) {
                     // Registers bound the bytes a thread can have in flight (8 x 16 B here), and a dependent DRAM round
@@ -418,13 +360,7 @@ __global__ void __maxnreg__(HAS_TGT ? 96 : 128) seg_fused_rows_kernel(const SegP
             }
             for (; Y < ye; ++Y) {
                 long long tv[4] = {0, 0, 0, 0};
-                if constexpr (RING) {
-                    ring_issue();
-                    cp_async_wait<kRingAhead>();
-                    if (active) ring_read(con, tv);
-                    ++con;
-                    ++since_flush;
-                } else if (HAS_TGT) {
+                if (HAS_TGT) {
                     if (active) {
                         const longlong2 ta = ldg_stream_ll2(tp);
                         const longlong2 tb = ldg_stream_ll2(tp + 2);
@@ -474,7 +410,6 @@ __global__ void __maxnreg__(HAS_TGT ? 96 : 128) seg_fused_rows_kernel(const SegP
         }
         if (HAS_TGT) acc.flush(cm_smem, p.cm_rows);
         if (HAS_TGT && hi_sink == 0x9E3779B9u && p.bs < 0) p.cm[0] = hi_sink;      // never true: see hi_sink above
-        if constexpr (RING) cp_async_wait<0>();
     }
     if (HAS_TGT) {
         __syncthreads();
@@ -486,98 +421,39 @@ __global__ void __maxnreg__(HAS_TGT ? 96 : 128) seg_fused_rows_kernel(const SegP
     }
 }
 
-// ---- eval mode with a TMA-fed target ring -------------------------------------------------------------
-// The int64 target is 8 B per pixel — 98 % of the bytes of an eval step — and a CTA's run of output rows is
-// one contiguous range of it.  Instead of per-thread loads (registers bound the bytes in flight and the kernel
-// sat at ~3.8 TB/s on long-scoreboard stalls), a dedicated PRODUCER warp streams the run through a ring of
-// shared-memory stages with TMA bulk copies (cp.async.bulk + mbarrier complete_tx); the CONSUMER warps wait on
-// a stage's "full" barrier, read their pixels' targets with LDS.128 and release the stage through its "empty"
-// barrier.  The ring keeps ~56 KB per CTA in flight with zero register cost; everything else (segment walk,
-// packed confusion-matrix counters) is as in seg_fused_rows_kernel.
+// ---- detect mode (mask only): the store stream ---------------------------------------------------------------------
+// The fp32 mask is 98 % of the bytes of a detect-mode step (4 B per pixel out, 1/16 B per pixel in), so this kernel is a
+// pure write stream with ~20 instructions of arithmetic per 16 bytes.  Same decomposition as above (persistent grid,
+// one contiguous run of output rows per CTA, a thread owns a 4-pixel column group and keeps the horizontally
+// interpolated source rows T / B in registers), tuned for the time to the first store and for how the stores leave:
+//   * no per-CTA tables over all H rows: one 16-byte entry (l0, l1, y0) per output row of THIS CTA's run, built while
+//     the first source rows are already in flight;
+//   * BULK: the rows are staged in shared memory (one STS.128 per thread per row) and leave kStageRows at a time through
+//     ONE TMA bulk copy shared -> global per stage (cp.async.bulk, UBLKCP; the rows of a run are contiguous in the
+//     mask), double-buffered: no LSU store traffic, 20 KB bursts;
+//   * otherwise one 16-byte streaming store per thread per row (any width, uint8 masks).
+constexpr int kStageRows = 8;
+
 __device__ __forceinline__ uint32_t seg_smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
-__device__ __forceinline__ void seg_mbar_init(unsigned long long *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(seg_smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void seg_mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(seg_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void seg_mbar_arrive(unsigned long long *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(seg_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void seg_mbar_wait(unsigned long long *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "SEG_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra SEG_DONE;\n"
-        "bra SEG_WAIT;\n"
-        "SEG_DONE:\n"
-        "}\n" ::"r"(seg_smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void seg_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(seg_smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(seg_smem_u32(bar))
-                 : "memory");
-}
 
-constexpr int kMaxStages = 16;
-
-template <int C, int MASK, typename W>
-__global__ void __launch_bounds__(544) seg_eval_tma_kernel(const SegParams p, const int rows_per_cta, const int stage_rows,
-                                                           const int nstage) {
+template <int C, int MASK, bool BULK>
+__global__ void __launch_bounds__(512) seg_mask_rows_kernel(const SegParams p, const int rows_per_cta) {
     extern __shared__ __align__(128) unsigned char seg_smem[];
-    // layout: ring | lam[H] | y0_of[H]
-    const size_t stage_bytes = (size_t)stage_rows * p.W * sizeof(long long);
-    long long *ring = reinterpret_cast<long long *>(seg_smem);
-    float2 *lam = reinterpret_cast<float2 *>(seg_smem + stage_bytes * nstage);
-    int *y0_of = reinterpret_cast<int *>(lam + p.H);
-    __shared__ unsigned int cm_smem[DSN_MAX_CM_ROWS * kMaxPackedC];
-    __shared__ __align__(8) unsigned long long full_bar[kMaxStages], empty_bar[kMaxStages];
+    // [H], indexed by the output row Y: (l0, l1, y0 as int bits, -); filled for the min(run, H) rows this CTA visits
+    float4 *tab = reinterpret_cast<float4 *>(seg_smem);
+    float *stage = reinterpret_cast<float *>(seg_smem + (((size_t)p.H * sizeof(float4) + 127) & ~(size_t)127));   // BULK: [2][kStageRows][W]
     const int G = p.W >> 2;
     const int plane = p.h * p.w;
-    const int n_cons = blockDim.x - 32;                       // consumer threads (multiple of 32, >= G)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool producer = warp == (n_cons >> 5);
     const long long total_rows = (long long)p.bs * p.H;
     const long long r_begin = (long long)blockIdx.x * rows_per_cta;
     const long long r_end = min(total_rows, r_begin + rows_per_cta);
-    const int run_rows = (int)(r_end - r_begin);
-    if (threadIdx.x < DSN_MAX_CM_ROWS * kMaxPackedC) cm_smem[threadIdx.x] = 0u;
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < nstage; ++i) {
-            seg_mbar_init(&full_bar[i], 1);
-            seg_mbar_init(&empty_bar[i], n_cons >> 5);        // one arrival per consumer warp
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int Y = threadIdx.x; Y < p.H; Y += blockDim.x) {
-        const Lerp ly = lerp_coeff(p.sy, Y, p.h);
-        lam[Y] = make_float2(ly.l0, ly.l1);
-        y0_of[Y] = ly.i0;
-    }
-    __syncthreads();
-    const int n_stages_total = (run_rows + stage_rows - 1) / stage_rows;
+    if (r_begin >= r_end) return;
+    const int b0 = (int)(r_begin / p.H);
+    const int Y0 = (int)(r_begin - (long long)b0 * p.H);
 
-    if (producer) {
-        if (lane == 0) {
-            const long long *src = p.target + (size_t)r_begin * p.W;
-            int st = 0;
-            uint32_t ph = 1;                                  // parity of the PREVIOUS use of the slot
-            for (int k = 0; k < n_stages_total; ++k) {
-                if (k >= nstage) seg_mbar_wait(&empty_bar[st], ph);
-                const int rows_here = min(stage_rows, run_rows - k * stage_rows);
-                const uint32_t bytes = (uint32_t)((size_t)rows_here * p.W * sizeof(long long));
-                seg_mbar_expect_tx(&full_bar[st], bytes);
-                seg_bulk_g2s(reinterpret_cast<unsigned char *>(ring) + stage_bytes * st,
-                             src + (size_t)k * stage_rows * p.W, bytes, &full_bar[st]);
-                if (++st == nstage) { st = 0; ph ^= 1u; }
-            }
-        }
-    } else {
-        const int g = threadIdx.x;
+    for (int g0 = 0; g0 < G; g0 += blockDim.x) {
+        if (!BULK && g0 + (int)(threadIdx.x & ~31u) >= G) break;        // whole warp beyond the row: nothing to do
+        const int g = g0 + threadIdx.x;
         const bool active = g < G;
         const int X = (active ? g : 0) << 2;
         float l0[4], l1[4];
@@ -590,7 +466,7 @@ __global__ void __launch_bounds__(544) seg_eval_tma_kernel(const SegParams p, co
 #pragma unroll
             for (int k = 1; k < 4; ++k) {
                 const Lerp lx = lerp_coeff(p.sx, X + k, p.w);
-                l0[k] = lx.l0; l1[k] = lx.l1; shx[k] = lx.i0 != xa;
+                l0[k] = lx.l0; l1[k] = lx.l1; shx[k] = lx.i0 != xa;     // source column advanced by one
             }
         }
         const int c0 = xa, c1 = min(xa + 1, p.w - 1), c2 = min(xa + 2, p.w - 1);
@@ -608,109 +484,115 @@ __global__ void __launch_bounds__(544) seg_eval_tma_kernel(const SegParams p, co
             }
             return fin;
         };
-        CmAcc<C, W> acc;
-        acc.clear();
-        float *m32 = (MASK & 1) ? p.mask_f32 + (size_t)r_begin * p.W + X : nullptr;
+        // first source rows of the run: in flight while the row table is built
+        int y0 = lerp_coeff(p.sy, Y0, p.h).i0;
+        const float *img = p.logits + (size_t)b0 * C * plane;
+        SrcCols<C> s0 = load_src_row<C>(img, plane, y0 * p.w, c0, c1, c2);
+        SrcCols<C> s1 = load_src_row<C>(img, plane, min(y0 + 1, p.h - 1) * p.w, c0, c1, c2);
+        SrcCols<C> nxt = load_src_row<C>(img, plane, min(y0 + 2, p.h - 1) * p.w, c0, c1, c2);
+        if (g0 == 0) {
+            const int n = (int)min((long long)p.H, r_end - r_begin);
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                int Y = Y0 + i;
+                Y = Y >= p.H ? Y - p.H : Y;
+                const Lerp ly = lerp_coeff(p.sy, Y, p.h);
+                tab[Y] = make_float4(ly.l0, ly.l1, __int_as_float(ly.i0), 0.f);
+            }
+            __syncthreads();
+        }
+        float T[C][4], B[C][4];
+        bool finite = hrow(s0, T);
+        finite = hrow(s1, B) && finite;
+
+        float *m32 = (MASK & 1) ? p.mask_f32 + (size_t)r_begin * p.W + X : nullptr;     // (b*H + Y)*W + X == r*W + X
         uint8_t *m8 = (MASK & 2) ? p.mask_u8 + (size_t)r_begin * p.W + X : nullptr;
-        bool finite = true;
-        auto row_body = [&](const float2 lm, const float (&top)[C][4], const float (&bot)[C][4], const long long *trow) {
-            int pred[4];
-            if (C == 2 && finite) {
-                float v0[4], v1[4];
-                vlerp4(lm, top[0], bot[0], v0);
-                vlerp4(lm, top[C - 1], bot[C - 1], v1);
+        int st = 0, slot = 0;                         // BULK: current stage, rows staged in it
+        long long r_stage = r_begin;                  // BULK: global row of the stage's first row
+        auto flush_stage = [&]() {
+            // generic-proxy writes of the stage -> visible to the async proxy, then one thread hands the stage to the TMA
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const float *src = stage + (size_t)st * kStageRows * p.W;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.mask_f32 + (size_t)r_stage * p.W),
+                             "r"(seg_smem_u32(src)), "r"((unsigned)((size_t)slot * p.W * sizeof(float)))
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");       // the other stage has been read out
+            }
+            __syncthreads();
+            r_stage += slot;
+            slot = 0;
+            st ^= 1;
+        };
+
+        int b = b0, Y = Y0;
+        for (long long r = r_begin; r < r_end; ++r) {
+            const float4 t = tab[Y];
+            if (__float_as_int(t.z) != y0) {                        // CTA-uniform: the source row pair moves down by one
+                ++y0;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) pred[k] = v1[k] > v0[k] ? 1 : 0;
+                for (int c = 0; c < C; ++c)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) T[c][k] = B[c][k];
+                finite = hrow(nxt, B) && finite;
+                nxt = load_src_row<C>(img, plane, min(y0 + 2, p.h - 1) * p.w, c0, c1, c2);     // prefetch one source row ahead
+            }
+            const float2 lm = make_float2(t.x, t.y);
+            int pred[4];
+            float predf[4];
+            if (C == 2 && finite) {
+                float v0[4], v1[4];                                  // no NaN can appear: plain compare, first maximum wins
+                vlerp4(lm, T[0], B[0], v0);
+                vlerp4(lm, T[C - 1], B[C - 1], v1);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    pred[k] = v1[k] > v0[k] ? 1 : 0;
+                    predf[k] = v1[k] > v0[k] ? 1.0f : 0.0f;
+                }
             } else {
                 float vals[C][4];
 #pragma unroll
-                for (int c = 0; c < C; ++c) vlerp4(lm, top[c], bot[c], vals[c]);
+                for (int c = 0; c < C; ++c) vlerp4(lm, T[c], B[c], vals[c]);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    float best = 0.f;
+                    float best = vals[0][k];
                     int bi = 0;
 #pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        const float val = vals[c][k];
-                        if (c == 0) {
-                            best = val;
-                        } else if (argmax_better(val, best)) {
-                            best = val;
-                            bi = c;
-                        }
-                    }
+                    for (int c = 1; c < C; ++c)
+                        if (argmax_better(vals[c][k], best)) { best = vals[c][k]; bi = c; }
                     pred[k] = bi;
+                    predf[k] = (float)bi;
                 }
             }
-            if (active) {
-                const longlong2 ta = *reinterpret_cast<const longlong2 *>(trow + X);
-                const longlong2 tb = *reinterpret_cast<const longlong2 *>(trow + X + 2);
-                const long long tv[4] = {ta.x, ta.y, tb.x, tb.y};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) acc.add(pred[k], clamp_target_row(tv[k], p.cm_rows));
-                if (MASK & 1) stg_stream_f4(m32, make_float4((float)pred[0], (float)pred[1], (float)pred[2], (float)pred[3]));
+            if (BULK) {
+                if (active)
+                    *reinterpret_cast<float4 *>(stage + ((size_t)st * kStageRows + slot) * p.W + X) = make_float4(predf[0], predf[1], predf[2], predf[3]);
+                if (++slot == kStageRows) flush_stage();
+            } else if (active) {
+                if (MASK & 1) stg_stream_f4(m32, make_float4(predf[0], predf[1], predf[2], predf[3]));
                 if (MASK & 2)
                     *reinterpret_cast<uint32_t *>(m8) =
                         (uint32_t)pred[0] | ((uint32_t)pred[1] << 8) | ((uint32_t)pred[2] << 16) | ((uint32_t)pred[3] << 24);
             }
             if (MASK & 1) m32 += p.W;
             if (MASK & 2) m8 += p.W;
-        };
-
-        int b = (int)(r_begin / p.H);
-        int Y = (int)(r_begin - (long long)b * p.H);
-        const float *img = p.logits + (size_t)b * C * plane;
-        float T[C][4], B[C][4];
-        SrcCols<C> nxt;
-        int ycur = 0, since_flush = 0;
-        bool fresh = true, flip = false;
-        int st = 0;                                           // ring slot of the current stage
-        uint32_t phase = 0;                                   // parity of that slot's current fill
-        for (int rel0 = 0; rel0 < run_rows; rel0 += stage_rows) {
-            const int rows_here = min(stage_rows, run_rows - rel0);
-            seg_mbar_wait(&full_bar[st], phase);
-            const long long *trow = reinterpret_cast<const long long *>(reinterpret_cast<const unsigned char *>(ring) + stage_bytes * st);
-            for (int rs = 0; rs < rows_here; ++rs, trow += p.W) {
-                if (fresh) {                                  // first row of the run or of an image
-                    fresh = false;
-                    flip = false;
-                    ycur = y0_of[Y];
-                    const SrcCols<C> s0 = load_src_row<C>(img, plane, ycur * p.w, c0, c1, c2);
-                    const SrcCols<C> s1 = load_src_row<C>(img, plane, min(ycur + 1, p.h - 1) * p.w, c0, c1, c2);
-                    nxt = load_src_row<C>(img, plane, min(ycur + 2, p.h - 1) * p.w, c0, c1, c2);
-                    const bool f0 = hrow(s0, T);
-                    const bool f1 = hrow(s1, B);
-                    finite = finite && f0 && f1;
-                } else if (y0_of[Y] != ycur) {                // CTA-uniform: source row pair moved down by one
-                    ycur = y0_of[Y];
-                    const bool f2 = flip ? hrow(nxt, B) : hrow(nxt, T);
-                    finite = finite && f2;
-                    flip = !flip;
-                    nxt = load_src_row<C>(img, plane, min(ycur + 2, p.h - 1) * p.w, c0, c1, c2);
-                }
-                if (!flip) row_body(lam[Y], T, B, trow); else row_body(lam[Y], B, T, trow);
-                if (++Y == p.H) {
-                    Y = 0;
-                    img += (size_t)C * plane;
-                    fresh = true;
-                }
-            }
-            __syncwarp();                                     // done with this stage: hand it back to the producer
-            if (lane == 0) seg_mbar_arrive(&empty_bar[st]);
-            if (++st == nstage) { st = 0; phase ^= 1u; }
-            since_flush += rows_here;
-            if (since_flush >= 60) {                          // 4 px per row: an 8-bit field holds at most 255
-                acc.flush(cm_smem, p.cm_rows);
-                since_flush = 0;
+            if (++Y == p.H && r + 1 < r_end) {                      // next image: restart the source-row walk
+                Y = 0;
+                ++b;
+                img = p.logits + (size_t)b * C * plane;
+                y0 = 0;
+                s0 = load_src_row<C>(img, plane, 0, c0, c1, c2);
+                s1 = load_src_row<C>(img, plane, min(1, p.h - 1) * p.w, c0, c1, c2);
+                nxt = load_src_row<C>(img, plane, min(2, p.h - 1) * p.w, c0, c1, c2);
+                finite = hrow(s0, T) && finite;
+                finite = hrow(s1, B) && finite;
             }
         }
-        acc.flush(cm_smem, p.cm_rows);
-    }
-    __syncthreads();
-    const int nb = p.cm_rows * C;
-    if (threadIdx.x < nb) {
-        const unsigned int cnt = cm_smem[threadIdx.x];
-        if (cnt) atomicAdd(p.cm + (size_t)(blockIdx.x % p.cm_slots) * nb + threadIdx.x, (unsigned long long)cnt);
+        if (BULK) {
+            if (slot > 0) flush_stage();
+            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // smem must outlive the reads
+        }
     }
 }
 
@@ -910,115 +792,74 @@ static int launch_general(const SegParams &p, cudaStream_t st) {
     return DSN_OK;
 }
 
-static inline int G_of(const SegParams &p) { return p.W / 4; }
-
 static int sm_count() { return sm_count_current_device(); }
 
-template <int C, bool T, int M, typename W, bool RING = false>
-static int launch_rows_w(const SegParams &p, cudaStream_t st) {
+// Persistent grid for the row kernels: SMs x resident CTAs, at least 8 output rows per CTA.
+static inline void rows_grid(const SegParams &p, int ctas_per_sm, long long &grid, int &rows_per_cta) {
+    const long long total_rows = (long long)p.bs * p.H;
+    grid = std::min<long long>((long long)sm_count() * ctas_per_sm, (total_rows + 7) / 8);
+    rows_per_cta = (int)((total_rows + grid - 1) / grid);
+    grid = (total_rows + rows_per_cta - 1) / rows_per_cta;
+}
+
+// eval mode (target -> confusion matrix, optionally the mask as well)
+template <int C, int M, typename W>
+static int launch_eval_rows_w(const SegParams &p, cudaStream_t st) {
     const int G = p.W / 4;
     const int threads = std::min(512, (G + 31) / 32 * 32);
-    size_t smem = (sizeof(float2) + sizeof(int)) * (size_t)p.H + sizeof(int) * (size_t)(p.h + 1);
-    if (RING) smem = ((smem + 15) & ~(size_t)15) + (size_t)kRingSlots * 32 * threads;
+    const size_t smem = (sizeof(float2) + sizeof(int)) * (size_t)p.H + sizeof(int) * (size_t)(p.h + 1);
     static DeviceOnce once;                   // per template instantiation
-    if (int rc = raise_dynamic_smem(once, seg_fused_rows_kernel<C, T, M, W, RING>, 200 * 1024)) return rc;
+    if (int rc = raise_dynamic_smem(once, seg_fused_rows_kernel<C, true, M, W>, 200 * 1024)) return rc;
     int occ = 0;
-    DSN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seg_fused_rows_kernel<C, T, M, W, RING>, threads, smem));
+    DSN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seg_fused_rows_kernel<C, true, M, W>, threads, smem));
     if (occ < 1) occ = 1;
-    static int occ_cap = -1;                 // experiment knob: DSN_SEG_OCC=<resident CTAs per SM the persistent grid is sized for>
-    if (occ_cap < 0) {
-        const char *e = getenv("DSN_SEG_OCC");
-        occ_cap = e ? atoi(e) : 0;
-    }
-    // detect mode is a pure store stream: two 160-thread CTAs per SM already saturate it (21.8 vs 22.1 us), and the
-    // register file they leave free lets an NMS CTA of a batch in flight share the SM (step 29.85 -> 29.3 us at cfg 2)
-    if (!T && occ_cap == 0 && occ > 2) occ = 2;
-    if (occ_cap > 0 && occ > occ_cap) occ = occ_cap;
-    const long long total_rows = (long long)p.bs * p.H;
-    long long grid = std::min<long long>((long long)sm_count() * occ, (total_rows + 7) / 8);
-    int rows_per_cta = (int)((total_rows + grid - 1) / grid);
-    static int forced = -1;                  // experiment knob: DSN_SEG_ROWS=<rows per CTA>
-    if (forced < 0) {
-        const char *e = getenv("DSN_SEG_ROWS");
-        forced = e ? atoi(e) : 0;
-    }
-    if (forced > 0) rows_per_cta = forced;
-    grid = (total_rows + rows_per_cta - 1) / rows_per_cta;
-    seg_fused_rows_kernel<C, T, M, W, RING><<<(unsigned)grid, threads, smem, st>>>(p, rows_per_cta);
+    long long grid;
+    int rows_per_cta;
+    rows_grid(p, occ, grid, rows_per_cta);
+    seg_fused_rows_kernel<C, true, M, W><<<(unsigned)grid, threads, smem, st>>>(p, rows_per_cta);
     DSN_CHECK_LAUNCH();
     return DSN_OK;
 }
 
-template <int C, int M, typename W>
-static int launch_eval_tma_w(const SegParams &p, cudaStream_t st) {
+// detect mode (mask only).  Two CTAs per SM saturate the store stream and leave the rest of the SM (registers, shared
+// memory) to the NMS CTA of another batch in flight.
+constexpr int kMaskCtasPerSm = DSN_SEG_MASK_CTAS_PER_SM;
+template <int C, int M, bool BULK>
+static int launch_mask_rows(const SegParams &p, cudaStream_t st) {
     const int G = p.W / 4;
-    const int cons = (G + 31) / 32 * 32;
-    const int threads = cons + 32;
-    const int stage_rows = 2;
-    const size_t stage_bytes = (size_t)stage_rows * p.W * sizeof(long long);
-    int nstage = (int)std::min<size_t>(kMaxStages, std::max<size_t>(3, (56 * 1024) / stage_bytes));
-    const size_t smem = stage_bytes * nstage + (sizeof(float2) + sizeof(int)) * (size_t)p.H;
+    const int threads = std::min(512, (G + 31) / 32 * 32);
+    size_t smem = (((size_t)p.H * sizeof(float4) + 127) & ~(size_t)127);
+    if (BULK) smem += (size_t)2 * kStageRows * p.W * sizeof(float);
     static DeviceOnce once;                   // per template instantiation
-    if (int rc = raise_dynamic_smem(once, seg_eval_tma_kernel<C, M, W>, 200 * 1024)) return rc;
-    int occ = 0;
-    DSN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seg_eval_tma_kernel<C, M, W>, threads, smem));
-    if (occ < 1) return DSN_E_UNSUPPORTED;
-    const long long total_rows = (long long)p.bs * p.H;
-    long long grid = std::min<long long>((long long)sm_count() * occ, (total_rows + 7) / 8);
-    const int rows_per_cta = (int)((total_rows + grid - 1) / grid);
-    grid = (total_rows + rows_per_cta - 1) / rows_per_cta;
-    seg_eval_tma_kernel<C, M, W><<<(unsigned)grid, threads, smem, st>>>(p, rows_per_cta, stage_rows, nstage);
+    if (int rc = raise_dynamic_smem(once, seg_mask_rows_kernel<C, M, BULK>, 200 * 1024)) return rc;
+    long long grid;
+    int rows_per_cta;
+    rows_grid(p, kMaskCtasPerSm, grid, rows_per_cta);
+    seg_mask_rows_kernel<C, M, BULK><<<(unsigned)grid, threads, smem, st>>>(p, rows_per_cta);
     DSN_CHECK_LAUNCH();
     return DSN_OK;
-}
-
-template <int C, bool T, int M>
-static int launch_rows_one(const SegParams &p, cudaStream_t st) {
-    if constexpr (T && M == 0) {
-        // pure eval, opt-in (DSN_SEG_RING=1): target streamed through a per-thread cp.async ring.  Measured on B200
-        // (cfg 3, bs 512): the kernel ALONE is slower than the plain-load variant (463 vs 363 us: 4 rows ahead do not
-        // cover a DRAM round trip and 8 slots x 32 B x threads of shared memory cap the ring depth), while the whole
-        // step with 3 batches in flight is ~6 % faster (the ring CTAs share the SMs better with the detection chain);
-        // at 1280 px it loses both ways.  The default stays the variant with the higher stand-alone bandwidth.
-        static int ring = -1;
-        if (ring < 0) { const char *e = getenv("DSN_SEG_RING"); ring = (e && atoi(e)) ? 1 : 0; }
-        if (ring && (size_t)kRingSlots * 32 * std::min(512, (p.W / 4 + 31) / 32 * 32) <= 160 * 1024) {
-            if (p.cm_rows <= 4) return launch_rows_w<C, T, M, unsigned int, true>(p, st);
-            return launch_rows_w<C, T, M, unsigned long long, true>(p, st);
-        }
-    }
-    if (!T || p.cm_rows <= 4) return launch_rows_w<C, T, M, unsigned int>(p, st);
-    return launch_rows_w<C, T, M, unsigned long long>(p, st);
-}
-template <int C, int M>
-static int launch_eval_tma(const SegParams &p, cudaStream_t st) {
-    if (p.cm_rows <= 4) return launch_eval_tma_w<C, M, unsigned int>(p, st);
-    return launch_eval_tma_w<C, M, unsigned long long>(p, st);
 }
 
 template <int C>
 static int launch_tile(const SegParams &p, cudaStream_t st) {
     const bool tgt = p.target != nullptr;
     const int mk = (p.mask_f32 ? 1 : 0) | (p.mask_u8 ? 2 : 0);
-    // eval mode: the TMA-fed target ring (seg_eval_tma_kernel) is parity-green but measured no faster than the
-    // streaming-load variant on B200 (55.6 vs 55.3 us at bs 64, 640x640), so it is opt-in: DSN_SEG_TMA=1
-    static int use_tma = -1;
-    if (use_tma < 0) { const char *e = getenv("DSN_SEG_TMA"); use_tma = (e && atoi(e)) ? 1 : 0; }
-    if (tgt && use_tma && G_of(p) <= 512 && (size_t)2 * p.W * 8 * 3 <= 160 * 1024) {
-        if (mk == 0) return launch_eval_tma<C, 0>(p, st);
-        if (mk == 1) return launch_eval_tma<C, 1>(p, st);
-        if (mk == 2) return launch_eval_tma<C, 2>(p, st);
-        return launch_eval_tma<C, 3>(p, st);
-    }
     if (tgt) {
-        if (mk == 0) return launch_rows_one<C, true, 0>(p, st);
-        if (mk == 1) return launch_rows_one<C, true, 1>(p, st);
-        if (mk == 2) return launch_rows_one<C, true, 2>(p, st);
-        return launch_rows_one<C, true, 3>(p, st);
+        const bool small = p.cm_rows <= 4;      // 8-bit counters of 4 rows fit one 32-bit word
+        switch (mk) {
+            case 0: return small ? launch_eval_rows_w<C, 0, unsigned int>(p, st) : launch_eval_rows_w<C, 0, unsigned long long>(p, st);
+            case 1: return small ? launch_eval_rows_w<C, 1, unsigned int>(p, st) : launch_eval_rows_w<C, 1, unsigned long long>(p, st);
+            case 2: return small ? launch_eval_rows_w<C, 2, unsigned int>(p, st) : launch_eval_rows_w<C, 2, unsigned long long>(p, st);
+            default: return small ? launch_eval_rows_w<C, 3, unsigned int>(p, st) : launch_eval_rows_w<C, 3, unsigned long long>(p, st);
+        }
     }
-    if (mk == 1) return launch_rows_one<C, false, 1>(p, st);
-    if (mk == 2) return launch_rows_one<C, false, 2>(p, st);
-    return launch_rows_one<C, false, 3>(p, st);
+    if (mk == 1) {
+        // fp32 mask, one pass of the CTA covers a row, stages fit: rows leave through TMA bulk stores
+        const bool bulk = DSN_SEG_MASK_BULK && p.W / 4 <= 512 && (size_t)2 * kStageRows * p.W * sizeof(float) + (size_t)p.H * 16 <= 96 * 1024;
+        return bulk ? launch_mask_rows<C, 1, true>(p, st) : launch_mask_rows<C, 1, false>(p, st);
+    }
+    if (mk == 2) return launch_mask_rows<C, 2, false>(p, st);
+    return launch_mask_rows<C, 3, false>(p, st);
 }
 
 }  // namespace dsn

@@ -72,30 +72,41 @@ class PeerGather:
         self.slot_bytes = self.det_bytes + self.cnt_bytes + self.flag_bytes
         total = self.slot_bytes * self.slots
         self._owned = self._mapped = None
+        err = None
         with torch.cuda.device(self.device):
+            payload = [None]
             if self.rank == root:
-                p = c_void_p()
-                _lib.check(self.lib.dsn_peer_alloc(total, ctypes.byref(p)), "dsn_peer_alloc")
-                self._owned = p.value
-                h = ctypes.create_string_buffer(64)
-                _lib.check(self.lib.dsn_peer_export(c_void_p(self._owned), h), "dsn_peer_export")
-                payload = [h.raw]
-            else:
-                payload = [None]
+                try:
+                    p = c_void_p()
+                    _lib.check(self.lib.dsn_peer_alloc(total, ctypes.byref(p)), "dsn_peer_alloc")
+                    self._owned = p.value
+                    h = ctypes.create_string_buffer(64)
+                    _lib.check(self.lib.dsn_peer_export(c_void_p(self._owned), h), "dsn_peer_export")
+                    payload = [h.raw]
+                except Exception as e:          # keep taking part in the collectives below, fail together afterwards
+                    err = e
             if self.world > 1:
                 dist.broadcast_object_list(payload, src=dist.get_global_rank(group, root) if group is not None else root, group=group)
             if self.rank == root:
                 self.base = self._owned
-            else:
-                p = c_void_p()
-                _lib.check(self.lib.dsn_peer_open(payload[0], ctypes.byref(p)), "dsn_peer_open")
-                self._mapped = p.value
-                self.base = self._mapped
+            elif payload[0] is not None:
+                try:
+                    p = c_void_p()
+                    _lib.check(self.lib.dsn_peer_open(payload[0], ctypes.byref(p)), "dsn_peer_open")
+                    self._mapped = p.value
+                    self.base = self._mapped
+                except Exception as e:
+                    err = e
             # per-slot step counters of THIS rank (device words the signal kernel increments)
             self.local_step = torch.zeros((self.slots,), dtype=torch.int32, device=self.device)
             self.status = torch.zeros((1,), dtype=torch.int32, device=self.device)
+            ok = torch.tensor([0 if (err is not None or getattr(self, "base", None) is None) else 1], dtype=torch.int32, device=self.device)
         if self.world > 1:
-            dist.barrier(group=group)          # nobody signals before everybody has mapped the buffer
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)      # also: nobody signals before everybody has mapped the buffer
+        if int(ok.item()) == 0:
+            self._release()
+            raise RuntimeError(f"desenet_b200.peer: the gathered buffer could not be shared over CUDA IPC on every rank "
+                               f"(rank {self.rank}: {err!r})")
 
     # ---- addresses ------------------------------------------------------------------------------
     def _slot(self, q: int) -> int:
@@ -154,16 +165,24 @@ class PeerGather:
         n = cnt.cpu().tolist()
         return [det[i, :max(n[i], 0)] for i in range(self.global_bs)]
 
-    def close(self):
-        if self.world > 1:
-            torch.cuda.synchronize(self.device)
-            dist.barrier(group=self.group)     # nobody unmaps / frees while a peer may still be writing
+    def _release(self):
         with torch.cuda.device(self.device):
             if self._mapped:
                 self.lib.dsn_peer_close(c_void_p(self._mapped))
                 self._mapped = None
-            if self.world > 1:
-                dist.barrier(group=self.group)
             if self._owned:
                 self.lib.dsn_peer_free(c_void_p(self._owned))
                 self._owned = None
+
+    def close(self):
+        """Collective: every rank unmaps, then the root frees (nobody unmaps / frees while a peer may still be writing)."""
+        if self.world > 1:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+        with torch.cuda.device(self.device):
+            if self._mapped:
+                self.lib.dsn_peer_close(c_void_p(self._mapped))
+                self._mapped = None
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        self._release()
