@@ -271,22 +271,31 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
     assert 0 <= conf_thres <= 1, f'Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0'
     assert 0 <= iou_thres <= 1, f'Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0'
     has_labels = bool(labels) and any(len(l) for l in labels)
-    if isinstance(prediction, HeadOutputs) and not has_labels:
+    if isinstance(prediction, HeadOutputs):
         head = prediction.head
         ml = bool(multi_label) and head.nc > 1
-        target = min(ops.MAX_NMS, max(8192, 16 * int(max_det)))
-        cut = None
-        if ml and head.A * head.nc >= 8 * target:          # eval setting: sampled confidence cut (exact, see ops.conf_cut_levels)
-            cut = ops.conf_cut_levels(head, conf_thres, ml, classes, target=target)
-        if cut is not None:
-            keys, counts = ops.filter_levels(head, conf_thres, ml, classes, cut=cut)
-            det, det_count = ops.nms_levels(head, keys, counts, conf_thres, iou_thres, agnostic, int(max_det), cut=cut)
-            # images whose NMS ran out of emitted candidates (det_count == -2) are redone uncut on the device
-            ops.detect_nms_redo_levels(head, conf_thres, iou_thres, classes, agnostic, ml, int(max_det), keys, counts, det, det_count)
+        if has_labels:
+            # a-priori labels (general.py:690-696) join the candidates as rows A + j of confidence 1.0; filter + NMS as
+            # two launches, without the confidence cut (autolabelling runs are not the throughput case)
+            padded = ops.pad_labels(labels, head.bs, head.device)
+            cap = head.A * (head.nc if ml else 1) + int(padded[0].shape[1])
+            keys, counts = ops.filter_levels(head, conf_thres, ml, classes, cap=cap)
+            ops.append_label_keys(head, padded, conf_thres, classes, keys, counts)
+            det, det_count = ops.nms_levels(head, keys, counts, conf_thres, iou_thres, agnostic, int(max_det), labels=padded)
         else:
-            det, det_count, _ = ops.detect_nms_levels(head, conf_thres, iou_thres, classes, agnostic, multi_label, int(max_det))
+            target = min(ops.MAX_NMS, max(8192, 16 * int(max_det)))
+            cut = None
+            if ml and head.A * head.nc >= 8 * target:      # eval setting: sampled confidence cut (exact, see ops.conf_cut_levels)
+                cut = ops.conf_cut_levels(head, conf_thres, ml, classes, target=target)
+            if cut is not None:
+                keys, counts = ops.filter_levels(head, conf_thres, ml, classes, cut=cut)
+                det, det_count = ops.nms_levels(head, keys, counts, conf_thres, iou_thres, agnostic, int(max_det), cut=cut)
+                # images whose NMS ran out of emitted candidates (det_count == -2) are redone uncut on the device
+                ops.detect_nms_redo_levels(head, conf_thres, iou_thres, classes, agnostic, ml, int(max_det), keys, counts, det, det_count)
+            else:
+                det, det_count, _ = ops.detect_nms_levels(head, conf_thres, iou_thres, classes, agnostic, multi_label, int(max_det))
     else:
-        z = prediction.z if isinstance(prediction, HeadOutputs) else _f32(prediction)
+        z = _f32(prediction)
         if has_labels:
             z = _append_label_rows(z, labels)
         if z.shape[0] == 0:

@@ -23,9 +23,14 @@ if os.environ.get("DSN_TIMING"):          # tuning build: phase timeline markers
     NVCC_FLAGS += ["-DDSN_TIMING", "-rdc=true"]
     LIB = os.path.join(LIBDIR, "libdesenet_b200_timing.so")
     OBJ_TAG = "obj_timing"
-elif os.environ.get("DSN_VARIANT"):       # tuning build "name:-DFOO=1 -DBAR=2": separate .so with extra compile-time switches
-    _name, _, _flags = os.environ["DSN_VARIANT"].partition(":")
-    NVCC_FLAGS += _flags.split()
+VARIANT_FLAGS = []
+VARIANT_SOURCES = None                    # sources recompiled with VARIANT_FLAGS (None: all); the others are linked from build/obj
+if not os.environ.get("DSN_TIMING") and os.environ.get("DSN_VARIANT"):
+    # tuning build "name:-DFOO=1 -DBAR=2[:a.cu,b.cu]": separate .so with extra compile-time switches
+    _name, _, _rest = os.environ["DSN_VARIANT"].partition(":")
+    _flags, _, _srcs = _rest.partition(":")
+    VARIANT_FLAGS = _flags.split()
+    VARIANT_SOURCES = _srcs.split(",") if _srcs else None
     LIB = os.path.join(LIBDIR, f"libdesenet_b200_{_name}.so")
     OBJ_TAG = f"obj_{_name}"
 
@@ -55,9 +60,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     objs = []
     for s in SOURCES:
+        if VARIANT_SOURCES is not None and s not in VARIANT_SOURCES:     # reuse the default build's object
+            objs.append(os.path.join(HERE, "..", "build", "obj", s.replace(".cu", ".o")))
+            continue
         o = os.path.join(objdir, s.replace(".cu", ".o"))
         objs.append(o)
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [nvcc, *NVCC_FLAGS, *VARIANT_FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -28,7 +28,13 @@ extern "C" __attribute__((visibility("default"))) int dsn_graph_launch_many(void
 }
 
 #ifdef DSN_TIMING
-namespace dsn { __device__ unsigned long long dsn_timing[64]; }
+namespace dsn { __device__ unsigned long long dsn_timing[64]; __device__ unsigned long long dsn_log[2048]; }
+extern "C" __attribute__((visibility("default"))) int dsn_debug_log(unsigned long long *host_out) {
+    cudaError_t e = cudaMemcpyFromSymbol(host_out, dsn::dsn_log, sizeof(unsigned long long) * 2048);
+    if (e != cudaSuccess) return (int)e;
+    static unsigned long long zeros[2048];
+    return (int)cudaMemcpyToSymbol(dsn::dsn_log, zeros, sizeof(zeros));
+}
 extern "C" __attribute__((visibility("default"))) int dsn_debug_timing(unsigned long long *host_out) {
     return (int)cudaMemcpyFromSymbol(host_out, dsn::dsn_timing, sizeof(unsigned long long) * 64);
 }

@@ -62,9 +62,16 @@ __device__ __forceinline__ void dsn_mark(int slot) {
 }
 #define DSN_MARK(slot) dsn::dsn_mark(slot)
 // accumulate the time since the previous DSN_LAP / DSN_LAP_START of this thread into dsn_timing[slot]
-#define DSN_LAP_START() unsigned long long dsn_lap_t = 0; if (threadIdx.x == 0 && blockIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dsn_lap_t))
-#define DSN_LAP(slot) do { if (threadIdx.x == 0 && blockIdx.x == 0) { unsigned long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); dsn::dsn_timing[slot] += t__ - dsn_lap_t; dsn_lap_t = t__; } } while (0)
+// (a log of (slot, time) pairs written with plain stores - a read-modify-write of global memory per lap would cost the
+// timed thread a memory round trip each time; the host sums the differences per slot)
+extern __device__ unsigned long long dsn_log[2048];
+#define DSN_LAP_START() unsigned int dsn_lap_n = 0; DSN_LAP(0)
+#define DSN_LAP(slot) do { if (threadIdx.x == 0 && blockIdx.x == 0 && dsn_lap_n < 2048u) { unsigned long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); dsn::dsn_log[dsn_lap_n++] = ((unsigned long long)(slot) << 56) | (t__ & 0x00FFFFFFFFFFFFFFull); } } while (0)
+#define DSN_COUNT(slot, v) do { if (threadIdx.x == 0 && blockIdx.x == 0) dsn::dsn_timing[slot] += (unsigned long long)(v); } while (0)
+#define DSN_COUNT_ALL(slot_sum, slot_max, v) do { if (threadIdx.x == 0) { atomicAdd(&dsn::dsn_timing[slot_sum], (unsigned long long)(v)); atomicMax(&dsn::dsn_timing[slot_max], (unsigned long long)(v)); } } while (0)
 #else
+#define DSN_COUNT_ALL(slot_sum, slot_max, v) ((void)0)
+#define DSN_COUNT(slot, v) ((void)0)
 #define DSN_MARK(slot) ((void)0)
 #define DSN_LAP_START() ((void)0)
 #define DSN_LAP(slot) ((void)0)

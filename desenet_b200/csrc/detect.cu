@@ -309,6 +309,236 @@ __global__ void __launch_bounds__(kDenseThreads, 3) filter_dense_kernel(const He
     if (nk > 0) flush();
 }
 
+// ---- dense multi-label filter, nc <= 8: TMA-fed persistent warps -------------------------------------------------------
+// With few classes (the reference's own head: nc = 6) the kernel above is neither HBM- nor issue-bound but LATENCY-bound:
+// a warp loads its tile (one DRAM round trip), works on it with nothing in flight, and leaves; the parked copy of the tile
+// costs 68 KB of shared memory per CTA and caps the occupancy at 24 warps per SM (cfg 3: 0.46 of the HBM peak).  Here every
+// warp is a small persistent pipeline of its own: it walks a contiguous range of tiles (128 cells x (1 + nc) planes) and
+// keeps kTmaStages tiles in flight with TMA bulk copies (cp.async.bulk global -> shared, one 512-byte row per plane,
+// issued by lanes 0..nc, completion on one mbarrier per stage) - no registers hold data in flight, the tile arrives where
+// the exact pass wants to index it, and nothing is parked.  The arithmetic is the kernel above's: logit-space bound per
+// cell, one compare per (cell, class), warp compaction of the pairs above the bound, exact sigmoid * sigmoid for those,
+// keys staged per warp and written with one atomic per batch.  Warps never synchronise with each other.
+constexpr int kTmaWarps = 4;             // per CTA
+constexpr int kTmaStages = 3;            // tiles in flight per warp
+constexpr int kTmaKbuf = 128;            // keys staged per warp
+constexpr int kTmaTileCells = 128;
+
+struct TmaLevel {
+    const float *raw;
+    int plane, row_off, tiles;           // tiles per (image, anchor) plane
+};
+
+__device__ __forceinline__ uint32_t flt_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+struct TileCursor {
+    int b, l, a, t;
+};
+
+__global__ void __launch_bounds__(kTmaWarps * 32) filter_dense_tma_kernel(const HeadGeom g, const FilterOut f, const float obj_logit_lo,
+                                                                         const float obj_logit_hi, const int tiles_per_image,
+                                                                         const long long total_tiles, const int tiles_per_warp) {
+    extern __shared__ __align__(128) unsigned char tma_smem[];
+    __shared__ TmaLevel lv[DSN_MAX_LEVELS];
+    const int nc = g.no - 5;
+    const int planes = nc + 1;                                   // objectness + classes: channels 4 .. 4 + nc of an anchor
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // per-warp shared memory: stages [kTmaStages][planes][128] floats | kbuf | idx | mbarriers
+    const size_t stage_bytes = (size_t)planes * kTmaTileCells * sizeof(float);
+    const size_t warp_bytes = ((kTmaStages * stage_bytes + kTmaKbuf * 8 + (size_t)nc * kTmaTileCells * 2 + kTmaStages * 8) + 127) & ~(size_t)127;
+    unsigned char *wbase = tma_smem + warp_bytes * warp;
+    float *stages = reinterpret_cast<float *>(wbase);
+    unsigned long long *kbuf = reinterpret_cast<unsigned long long *>(wbase + kTmaStages * stage_bytes);
+    unsigned short *idx = reinterpret_cast<unsigned short *>(kbuf + kTmaKbuf);
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(wbase + kTmaStages * stage_bytes + kTmaKbuf * 8 + (size_t)nc * kTmaTileCells * 2);
+#pragma unroll
+    for (int i = 0; i < DSN_MAX_LEVELS; ++i)
+        if ((int)threadIdx.x == i && i < g.nl)
+            lv[i] = TmaLevel{g.raw[i], g.plane[i], g.row_off[i], (g.plane[i] + kTmaTileCells - 1) / kTmaTileCells};
+    if (lane == 0) {
+        for (int i = 0; i < kTmaStages; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(flt_smem_u32(&full[i])), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const long long w_global = (long long)blockIdx.x * kTmaWarps + warp;
+    const long long first = w_global * tiles_per_warp;
+    if (first >= total_tiles) return;
+    const int my_tiles = (int)min((long long)tiles_per_warp, total_tiles - first);
+
+    auto advance = [&](TileCursor &c) {
+        if (++c.t == lv[c.l].tiles) {
+            c.t = 0;
+            if (++c.a == g.na) {
+                c.a = 0;
+                if (++c.l == g.nl) { c.l = 0; ++c.b; }
+            }
+        }
+    };
+    TileCursor cons;
+    {
+        cons.b = (int)(first / tiles_per_image);
+        int r = (int)(first - (long long)cons.b * tiles_per_image);
+        cons.l = 0;
+        while (r >= g.na * lv[cons.l].tiles) { r -= g.na * lv[cons.l].tiles; ++cons.l; }
+        cons.a = r / lv[cons.l].tiles;
+        cons.t = r - cons.a * lv[cons.l].tiles;
+    }
+    TileCursor prod = cons;
+    // lanes 0 .. nc each copy one 512-byte row of the tile (lane 0: objectness); lane 0 posts the byte count with its arrival
+    auto issue = [&](const TileCursor &c, int st) {
+        const TmaLevel L = lv[c.l];
+        const int cell0 = c.t * kTmaTileCells;
+        const unsigned bytes = (unsigned)min(kTmaTileCells, L.plane - cell0) * 4u;
+        const uint32_t bar = flt_smem_u32(&full[st]);
+        if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * (unsigned)planes) : "memory");
+        if (lane < planes) {
+            const float *src = L.raw + ((size_t)(c.b * g.na + c.a) * g.no + 4 + lane) * L.plane + cell0;
+            const uint32_t dst = flt_smem_u32(stages + ((size_t)st * planes + lane) * kTmaTileCells);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                         "r"(bytes), "r"(bar)
+                         : "memory");
+        }
+    };
+    const int prefill = min(kTmaStages, my_tiles);
+    for (int i = 0; i < prefill; ++i) {
+        issue(prod, i);
+        advance(prod);
+    }
+    int issued = prefill;
+
+    const unsigned int cap = f.cap > 0x7fffffffLL ? 0x7fffffffu : (unsigned)f.cap;
+    int nk = 0;                                         // keys waiting in the warp's kbuf (warp-uniform)
+    int kb = cons.b;                                    // image the staged keys belong to
+    unsigned long long *kout = f.keys + (size_t)kb * f.cap;
+    auto flush = [&]() {                                // ONE atomic on the image's counter, coalesced 8-byte stores
+        unsigned int base = 0;
+        if (lane == 0) base = (unsigned)atomicAdd(f.counts + kb, nk);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        __syncwarp();
+        unsigned long long *dst = kout + base;
+        if (base + (unsigned)nk <= cap) {
+            for (int i = lane; i < nk; i += 32) dst[i] = kbuf[i];
+        } else {
+            for (int i = lane; i < nk; i += 32)
+                if (base + i < cap) dst[i] = kbuf[i];
+        }
+        __syncwarp();
+        nk = 0;
+    };
+    unsigned int cut = f.cut_hi ? f.cut_hi[kb] : 0xFFFFFFFFu;
+    float t_lo = fmaxf(f.conf_thres, __uint_as_float(~cut)) * 0.999f;      // see filter_dense_kernel
+
+    for (int it = 0; it < my_tiles; ++it) {
+        const int st = it % kTmaStages;
+        const unsigned parity = (unsigned)(it / kTmaStages) & 1u;
+        if (cons.b != kb) {                              // next image: its keys go to another buffer, its cut differs
+            if (nk > 0) flush();
+            kb = cons.b;
+            kout = f.keys + (size_t)kb * f.cap;
+            cut = f.cut_hi ? f.cut_hi[kb] : 0xFFFFFFFFu;
+            t_lo = fmaxf(f.conf_thres, __uint_as_float(~cut)) * 0.999f;
+        }
+        {
+            const uint32_t bar = flt_smem_u32(&full[st]);
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "FLT_WAIT:\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                "@p bra FLT_DONE;\n"
+                "bra FLT_WAIT;\n"
+                "FLT_DONE:\n"
+                "}\n" ::"r"(bar),
+                "r"(parity)
+                : "memory");
+        }
+        const TmaLevel L = lv[cons.l];
+        const int cell0 = cons.t * kTmaTileCells;
+        const int nvalid = min(kTmaTileCells, L.plane - cell0);
+        const float *tile = stages + (size_t)st * planes * kTmaTileCells;          // [planes][128]: row 0 objectness, 1 + c class c
+        const bool in = lane * 4 < nvalid;                      // plane % 4 == 0: the 4 cells are all in or all out
+        // ---- per-cell logit bound (identical to filter_dense_kernel) -------------------------------------------------
+        float Lb[4];
+        bool any = false;
+        {
+            float4 o4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            if (in) o4 = *reinterpret_cast<const float4 *>(tile + lane * 4);
+            const float ol[4] = {o4.x, o4.y, o4.z, o4.w};
+            const float inv_t = __fdividef(1.0f, t_lo);                                      // +inf when T' == 0
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                Lb[k] = INFINITY;
+                bool pass = ol[k] >= obj_logit_hi;
+                if (!pass && ol[k] >= obj_logit_lo) pass = sigmoidf_ref(ol[k]) > f.conf_thres;   // yolo.py:266, general.py:668
+                if (pass) {
+                    const float q = __fdividef(inv_t, 1.0f + __expf(-ol[k])) - 1.0f;
+                    if (q > 0.f) Lb[k] = -__logf(q) - 4e-3f;                                 // q == +inf -> -inf: everything passes
+                }
+                any = any || Lb[k] < INFINITY;
+            }
+        }
+        if (__any_sync(0xffffffffu, any)) {
+            // ---- logit-space test, one compare per (cell, class) ------------------------------------------------------
+            unsigned int mask = 0;
+#pragma unroll
+            for (int ci = 0; ci < kDenseChunk; ++ci) {
+                if (ci < nc) {
+                    float4 v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                    if (in) v = *reinterpret_cast<const float4 *>(tile + (size_t)(1 + ci) * kTmaTileCells + lane * 4);
+                    mask |= (v.x > Lb[0] ? 1u : 0u) << (ci * 4 + 0);
+                    mask |= (v.y > Lb[1] ? 1u : 0u) << (ci * 4 + 1);
+                    mask |= (v.z > Lb[2] ? 1u : 0u) << (ci * 4 + 2);
+                    mask |= (v.w > Lb[3] ? 1u : 0u) << (ci * 4 + 3);
+                }
+            }
+            if (__any_sync(0xffffffffu, mask != 0)) {
+                const int mine = __popc(mask);
+                int incl = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += up;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                int slot = incl - mine;
+                const unsigned int tag = (unsigned)lane;
+                for (unsigned int m = mask; m; m &= m - 1) idx[slot++] = (unsigned short)(((__ffs(m) - 1) << 5) | tag);   // (bit, lane)
+                __syncwarp();
+                // ---- exact arithmetic for the surviving pairs, one per lane ---------------------------------------------
+                const unsigned int row0 = (unsigned)(L.row_off + cons.a * L.plane + cell0);
+                for (int e0 = 0; e0 < total; e0 += 32) {
+                    if (nk > kTmaKbuf - 32) flush();
+                    const int e = e0 + lane;
+                    bool emit = false;
+                    unsigned long long key = 0ull;
+                    if (e < total) {
+                        const unsigned int id = idx[e], bit = id >> 5;
+                        const int ci = bit >> 2, cell = (id & 31) * 4 + (bit & 3);      // bit = class * 4 + cell of the lane
+                        const float conf = __fmul_rn(sigmoidf_ref(tile[(1 + ci) * kTmaTileCells + cell]), sigmoidf_ref(tile[cell]));   // general.py:703
+                        const unsigned int ck = conf_key(conf);
+                        emit = conf > f.conf_thres && ck <= cut && class_allowed(f, ci);                      // general.py:710,717
+                        key = ((unsigned long long)ck << 32) | (unsigned long long)((row0 + cell) * (unsigned)nc + (unsigned)ci);
+                    }
+                    const unsigned int bal = __ballot_sync(0xffffffffu, emit);
+                    if (emit) kbuf[nk + __popc(bal & ((1u << lane) - 1u))] = key;
+                    nk += __popc(bal);
+                }
+            }
+        }
+        __syncwarp();                                    // every lane is done with the stage
+        if (issued < my_tiles) {                         // refill it with the tile kTmaStages ahead
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(prod, st);
+            advance(prod);
+            ++issued;
+        }
+        advance(cons);
+    }
+    if (nk > 0) flush();
+}
+
 // ---- confidence cut for huge candidate sets (eval setting, multi-label) -------------------------------------------
 // With conf 0.001 and multi_label the filter would emit up to A*nc candidates per image (1.28 M at nc = 80), while
 // the greedy NMS stops after max_det survivors and never looks past the max_nms = 30000 best (general.py:728-736).
@@ -584,6 +814,29 @@ extern "C" __attribute__((visibility("default"))) int dsn_filter_levels_cut(cons
     }
     g.cta_off[nl] = ctas;
     const float lo = obj_logit_lower_bound(conf_thres);
+    if (vec && f.multi_label && no - 5 <= kDenseChunk) {      // few classes: TMA-fed persistent warps
+        const int nc = no - 5;
+        int tiles_per_image = 0;
+        for (int l = 0; l < nl; ++l) tiles_per_image += na * ((g.plane[l] + kTmaTileCells - 1) / kTmaTileCells);
+        const long long total_tiles = (long long)bs * tiles_per_image;
+        const size_t stage_bytes = (size_t)(nc + 1) * kTmaTileCells * sizeof(float);
+        const size_t warp_bytes = ((kTmaStages * stage_bytes + kTmaKbuf * 8 + (size_t)nc * kTmaTileCells * 2 + kTmaStages * 8) + 127) & ~(size_t)127;
+        const size_t smem = warp_bytes * kTmaWarps;
+        static DeviceOnce once;
+        if (int rc2 = raise_dynamic_smem(once, filter_dense_tma_kernel, 200 * 1024)) return rc2;
+        int occ = 0;
+        DSN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, filter_dense_tma_kernel, kTmaWarps * 32, smem));
+        if (occ < 1) occ = 1;
+        // a warp takes a contiguous range of at least kTmaStages + 1 tiles; the grid is what the SMs hold at once
+        const long long max_warps = (long long)sm_count_current_device() * occ * kTmaWarps;
+        long long tpw = std::max<long long>(kTmaStages + 1, (total_tiles + max_warps - 1) / max_warps);
+        const long long warps = (total_tiles + tpw - 1) / tpw;
+        const long long grid = (warps + kTmaWarps - 1) / kTmaWarps;
+        filter_dense_tma_kernel<<<(unsigned)grid, kTmaWarps * 32, smem, st>>>(g, f, lo, obj_logit_upper_bound(conf_thres), tiles_per_image,
+                                                                           total_tiles, (int)tpw);
+        DSN_CHECK_LAUNCH();
+        return DSN_OK;
+    }
     if (vec && f.multi_label) {                // dense multi-label path: every class plane is streamed
         ctas = 0;
         for (int l = 0; l < nl; ++l) {

@@ -26,7 +26,7 @@
 
 namespace dsn {
 
-constexpr int kStageFloats = 16384;      // objectness logits staged per round (64 KB)
+constexpr int kStageFloats = 14336;      // objectness logits staged per round (56 KB)
 constexpr int kListCap = kStageFloats;   // rows in the shared list: a whole stage can pass, so the list never overflows
 constexpr int kMaxPieces = 24;           // bulk copies per round
 
@@ -286,7 +286,7 @@ static int detect_nms_levels_impl(
         rc = dsn_filter_levels(raw, ny, nx, nl, bs, na, no, conf_thres, multi_label, class_mask, keys, cap, counts, stream);
         if (rc) return rc;
         return dsn_nms_levels(raw, ny, nx, stride, anchor_grid, nl, bs, na, no, keys, cap, counts, conf_thres, iou_thres,
-                              agnostic, max_nms, max_det, max_wh, nullptr, det, det_count, stream);
+                              agnostic, max_nms, max_det, max_wh, nullptr, nullptr, det, det_count, stream);
     }
     const float lo = obj_logit_lower_bound(conf_thres);
     const size_t smem = sizeof(FusedSmem);

@@ -19,6 +19,11 @@
 
 namespace dsn {
 
+struct FilterClassMask {
+    unsigned long long m[4];
+    int use;
+};
+
 template <class BoxSrc>
 __global__ void __launch_bounds__(kNmsThreads, 1024 / kNmsThreads) nms_kernel(const NmsParams p, const BoxSrc src) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -37,6 +42,24 @@ __global__ void __launch_bounds__(kNmsThreads, 1024 / kNmsThreads) nms_kernel(co
     nms_image(s, p, src, b, p.keys + (size_t)b * p.cap, total);
 }
 
+// A-priori labels as candidates (general.py:690-696, val.py:228 save_hybrid): label j of image b is prediction row A + j
+// with obj = 1 and a one-hot class, i.e. ONE candidate of confidence 1.0 for its class in both selection modes.
+__global__ void append_label_keys_kernel(const float *__restrict__ labels, const int *__restrict__ label_count, int max_labels, int A,
+                                         int nc, float conf_thres, FilterClassMask cm, unsigned long long *__restrict__ keys,
+                                         long long cap, int *__restrict__ counts) {
+    const int b = blockIdx.x;
+    const int n = min(label_count[b], max_labels);
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const float c = labels[((size_t)b * max_labels + j) * 5];
+        const int cls = (int)c;                                              // .long() of the class column (general.py:695)
+        if (!(1.0f > conf_thres) || cls < 0 || cls >= nc) continue;          // conf = 1 * 1 must exceed the threshold (general.py:710-714)
+        if (cm.use && !((cm.m[(cls >> 6) & 3] >> (cls & 63)) & 1ull)) continue;   // general.py:717-718
+        const int slot = atomicAdd(counts + b, 1);
+        if (slot < cap)
+            keys[(size_t)b * cap + slot] = ((unsigned long long)conf_key(1.0f) << 32) | (unsigned long long)((unsigned)(A + j) * (unsigned)nc + (unsigned)cls);
+    }
+}
+
 template <class BoxSrc>
 static int launch_nms(const NmsParams &p, const BoxSrc &src, int bs, cudaStream_t st) {
     if (bs == 0) return DSN_OK;
@@ -53,20 +76,59 @@ static int launch_nms(const NmsParams &p, const BoxSrc &src, int bs, cudaStream_
 
 using namespace dsn;
 
-extern "C" __attribute__((visibility("default"))) int dsn_nms_levels(const float *const *raw, const int *ny, const int *nx, const float *stride,
-                              const float *anchor_grid, int nl, int bs, int na, int no, const uint64_t *keys,
-                              int64_t cap, const int *counts, float conf_thres, double iou_thres, int agnostic,
-                              int max_nms, int max_det, float max_wh, const int *cut_dropped, float *det, int *det_count,
-                              void *stream) {
+static int nms_levels_impl(const float *const *raw, const int *ny, const int *nx, const float *stride, const float *anchor_grid, int nl,
+                           int bs, int na, int no, const uint64_t *keys, int64_t cap, const int *counts, float conf_thres,
+                           double iou_thres, int agnostic, int max_nms, int max_det, float max_wh, const unsigned int *cut_hi,
+                           const int *cut_dropped, const float *labels, int max_labels, float *det, int *det_count, void *stream) {
     if (!stride || !anchor_grid) return DSN_E_INVALID;
+    if (max_labels < 0 || (max_labels > 0 && !labels)) return DSN_E_INVALID;
     BoxFromLevels src;
     int rc = make_geom(src.g, raw, ny, nx, stride, anchor_grid, nl, bs, na, no);
     if (rc) return rc;
+    if ((unsigned long long)(src.g.A + max_labels) * (unsigned long long)(no - 5) >= (1ull << 32)) return DSN_E_UNSUPPORTED;
+    src.extra = labels;
+    src.extra_rows = max_labels;
     NmsParams p;
     rc = make_nms_params(p, keys, cap, counts, bs, no - 5, conf_thres, iou_thres, agnostic, max_nms, max_det, max_wh, det, det_count);
     if (rc) return rc;
     p.cut_dropped = cut_dropped;
+    p.cut_hi = cut_dropped ? cut_hi : nullptr;
     return launch_nms(p, src, bs, (cudaStream_t)stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int dsn_nms_levels(const float *const *raw, const int *ny, const int *nx, const float *stride,
+                              const float *anchor_grid, int nl, int bs, int na, int no, const uint64_t *keys,
+                              int64_t cap, const int *counts, float conf_thres, double iou_thres, int agnostic,
+                              int max_nms, int max_det, float max_wh, const unsigned int *cut_hi, const int *cut_dropped,
+                              float *det, int *det_count, void *stream) {
+    return nms_levels_impl(raw, ny, nx, stride, anchor_grid, nl, bs, na, no, keys, cap, counts, conf_thres, iou_thres, agnostic, max_nms,
+                           max_det, max_wh, cut_hi, cut_dropped, nullptr, 0, det, det_count, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int dsn_nms_levels_labels(const float *const *raw, const int *ny, const int *nx, const float *stride,
+                              const float *anchor_grid, int nl, int bs, int na, int no, const uint64_t *keys,
+                              int64_t cap, const int *counts, float conf_thres, double iou_thres, int agnostic,
+                              int max_nms, int max_det, float max_wh, const float *labels, int max_labels, float *det,
+                              int *det_count, void *stream) {
+    return nms_levels_impl(raw, ny, nx, stride, anchor_grid, nl, bs, na, no, keys, cap, counts, conf_thres, iou_thres, agnostic, max_nms,
+                           max_det, max_wh, nullptr, nullptr, labels, max_labels, det, det_count, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int dsn_append_label_keys(const float *labels, const int *label_count, int bs, int max_labels,
+                                                                            int64_t A, int nc, float conf_thres, const uint64_t *class_mask,
+                                                                            uint64_t *keys, int64_t cap, int *counts, void *stream) {
+    if (bs < 0 || max_labels < 0 || A < 0 || nc < 1 || cap < 1 || !keys || !counts) return DSN_E_INVALID;
+    if (!(conf_thres >= 0.f && conf_thres <= 1.f)) return DSN_E_INVALID;
+    if (bs == 0 || max_labels == 0) return DSN_OK;
+    if (!labels || !label_count) return DSN_E_INVALID;
+    if ((unsigned long long)(A + max_labels) * (unsigned long long)nc >= (1ull << 32) || bs > 65535) return DSN_E_UNSUPPORTED;
+    FilterClassMask cm;
+    cm.use = class_mask != nullptr;
+    for (int i = 0; i < 4; ++i) cm.m[i] = class_mask ? class_mask[i] : ~0ull;
+    append_label_keys_kernel<<<bs, 128, 0, (cudaStream_t)stream>>>(labels, label_count, max_labels, (int)A, nc, conf_thres, cm,
+                                                                   (unsigned long long *)keys, cap, counts);
+    DSN_CHECK_LAUNCH();
+    return DSN_OK;
 }
 
 extern "C" __attribute__((visibility("default"))) int dsn_nms_z(const float *z, int bs, int64_t A, int no, const uint64_t *keys, int64_t cap,

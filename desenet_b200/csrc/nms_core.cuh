@@ -30,32 +30,55 @@ struct NmsParams {
     unsigned long long key_lo_hint;   // keys of conf <= 1.0 are >= this (hint, not required)
     unsigned long long key_hi;        // every key is <= this (conf > conf_thres)
     const int *cut_dropped;           // optional (bs): the filter dropped candidates below a confidence cut
+    const unsigned int *cut_hi;       // optional (bs): that cut (confidence half of the largest emitted key) - bounds the selection range
     float *det;
     int *det_count;
+};
+
+// Box sources: fetch() issues the loads of one row (raw values + what finish() needs), finish() turns them into the
+// xyxy box.  The NMS fetches several rows per thread before finishing any, so their DRAM round trips overlap.
+struct RawBox {
+    float x, y, w, h;
+    int l, a, cell;        // l < 0: x, y, w, h are already pixels (decoded prediction or an a-priori label row)
 };
 
 struct BoxFromZ {
     const float *z;
     long long A;
     int no;
-    __device__ __forceinline__ float4 operator()(int b, unsigned int row) const {
+    __device__ __forceinline__ RawBox fetch(int b, unsigned int row) const {
         const float *r = z + ((size_t)b * A + row) * no;
-        return xywh2xyxy(__ldg(r), __ldg(r + 1), __ldg(r + 2), __ldg(r + 3));       // general.py:706
+        return RawBox{__ldg(r), __ldg(r + 1), __ldg(r + 2), __ldg(r + 3), -1, 0, 0};
     }
+    __device__ __forceinline__ float4 finish(const RawBox &q) const { return xywh2xyxy(q.x, q.y, q.w, q.h); }   // general.py:706
+    __device__ __forceinline__ float4 operator()(int b, unsigned int row) const { return finish(fetch(b, row)); }
 };
 
 struct BoxFromLevels {
     HeadGeom g;
-    __device__ __forceinline__ float4 operator()(int b, unsigned int row) const {
+    // optional a-priori label rows appended after the A anchor rows (general.py:690-696): (bs, extra_rows, 5) [cls, x, y, w, h]
+    const float *extra = nullptr;
+    int extra_rows = 0;
+    __device__ __forceinline__ RawBox fetch(int b, unsigned int row) const {
+        if (row >= (unsigned)g.A) {
+            const float *r = extra + ((size_t)b * extra_rows + (row - (unsigned)g.A)) * 5;
+            return RawBox{__ldg(r + 1), __ldg(r + 2), __ldg(r + 3), __ldg(r + 4), -1, 0, 0};       // general.py:692
+        }
         const RowGeom rg = row_geom(g, (int)row);
-        const int l = rg.l, plane = rg.plane, a = rg.a, cell = rg.cell;
-        const float *base = g.raw[l] + ((size_t)(b * g.na + a) * g.no) * plane + cell;
-        const float x = decode_xy(__ldg(base), cell % g.nx[l], g.stride[l]);
-        const float y = decode_xy(__ldg(base + plane), cell / g.nx[l], g.stride[l]);
-        const float w = decode_wh(__ldg(base + 2 * (size_t)plane), g.anchor_w[l][a]);
-        const float h = decode_wh(__ldg(base + 3 * (size_t)plane), g.anchor_h[l][a]);
+        const float *base = g.raw[rg.l] + ((size_t)(b * g.na + rg.a) * g.no) * rg.plane + rg.cell;
+        return RawBox{__ldg(base), __ldg(base + rg.plane), __ldg(base + 2 * (size_t)rg.plane), __ldg(base + 3 * (size_t)rg.plane),
+                      rg.l, rg.a, rg.cell};
+    }
+    __device__ __forceinline__ float4 finish(const RawBox &q) const {
+        if (q.l < 0) return xywh2xyxy(q.x, q.y, q.w, q.h);                                           // general.py:706
+        const int l = q.l;
+        const float x = decode_xy(q.x, q.cell % g.nx[l], g.stride[l]);
+        const float y = decode_xy(q.y, q.cell / g.nx[l], g.stride[l]);
+        const float w = decode_wh(q.w, g.anchor_w[l][q.a]);
+        const float h = decode_wh(q.h, g.anchor_h[l][q.a]);
         return xywh2xyxy(x, y, w, h);
     }
+    __device__ __forceinline__ float4 operator()(int b, unsigned int row) const { return finish(fetch(b, row)); }
 };
 
 // torchvision CPU kernel arithmetic: std::max/min, fp32 products and sums rounded one by one.
@@ -87,6 +110,7 @@ constexpr int kRound = 256;          // candidates resolved per bitmask round
 constexpr int kRankSortMax = 256;    // O(m^2) rank sort below, bitonic sort above
 constexpr int kWords = kRound / 64;
 constexpr int kChainClasses = 256;
+constexpr int kChainSplit = 2;       // = kNmsThreads / kRound: threads per candidate in the survivor test
 
 struct NmsSmem {
     unsigned long long key[kChunk];
@@ -111,15 +135,25 @@ struct NmsSmem {
     unsigned long long keptbits[kWords];
     // class chains (used while the class-aware culling holds and nc <= kChainClasses): survivors / round candidates of
     // one class are linked newest-to-oldest, so a candidate only meets the boxes that can overlap it
-    int khead[kChainClasses];         // newest survivor slot of the class (-1: none); slots < kKeptSmem only
-    short knext[kKeptSmem];           // next older survivor of the same class
+    // Survivors of one class are split over kChainSplit interleaved chains (by slot parity), so that the threads testing
+    // one candidate against the survivors each walk a fraction of them.
+    int khead[kChainClasses][kChainSplit];   // newest survivor slot of (class, slot % kChainSplit) (-1: none); slots < kKeptSmem only
+    short knext[kKeptSmem];           // next older survivor of the same class and parity
+    short lastw[kRound / 32][kChainClasses];   // last candidate of each class inside each warp of the round (-1: none)
     short rprev[kRound];              // previous (better-scored) candidate of the same class inside the round
+    short ralive[kRound];             // ... the previous one that survived the test against the survivors so far
+    short rslot[kRound];              // survivor slot of the round's candidate (-1: not kept)
     unsigned short rcls[kRound];      // class of the round's candidates
     unsigned int m;                   // gathered count
     unsigned int below;
     unsigned int red_sum, red_max, red_min;
     int nkept;
 };
+
+// mask[row] |= bit col, as a native 32-bit shared-memory atomic (64-bit ones are compare-and-swap loops)
+__device__ __forceinline__ void mask_set(NmsSmem &s, int row, int col) {
+    atomicOr(reinterpret_cast<unsigned int *>(&s.mask[row][0]) + (col >> 5), 1u << (col & 31));
+}
 
 // Visit every key of the image once: 16 B loads, 4 independent loads in flight per thread (the
 // selection passes are latency-bound on L2, not bandwidth-bound).
@@ -150,9 +184,13 @@ __device__ __forceinline__ void for_each_key(const unsigned long long *keys, int
 // Select the next chunk: the smallest keys in [lo, hi] (hi inclusive), about `target` of them and
 // never more than kChunk.  Returns the chunk's inclusive upper key in *chunk_hi and its size; size
 // 0 = nothing left in [lo, hi].  `below` (first call only) counts keys < lo.
+// On success the histogram is left as the FIRST FREE POSITION of every bin (exclusive prefix) and *bin_lo / *bin_sh /
+// *crowded describe the bins, so that the gather can drop each key straight into its bin (counting sort): bin of key k =
+// (k - *bin_lo) >> *bin_sh; *crowded != 0: some bin of the chunk holds more than kBinSortMax keys (ties in the confidence).
+constexpr unsigned int kBinSortMax = 16;
 static __device__ int select_chunk(NmsSmem &s, const unsigned long long *keys, int n, unsigned long long lo,
                             unsigned long long hi, unsigned int target, unsigned long long *chunk_hi,
-                            unsigned int *below) {
+                            unsigned int *below, unsigned long long *bin_lo, int *bin_sh, int *crowded) {
     for (;;) {
         const unsigned long long width = hi - lo;
         const int bits = 64 - __clzll((long long)(width | 1ull));
@@ -219,6 +257,17 @@ static __device__ int select_chunk(NmsSmem &s, const unsigned long long *keys, i
         if (cnt > 0) {
             const unsigned long long span = jmax >= (unsigned)kBins ? ~0ull : (((unsigned long long)jmax << sh) - 1ull);
             *chunk_hi = span > width ? hi : lo + span;     // saturating: empty bins may lie beyond hi
+            unsigned int first = wbase + incl - mine, big = 0;
+#pragma unroll
+            for (int j = 0; j < per; ++j) {
+                const unsigned int bin = threadIdx.x * per + j;
+                s.hist[bin] = first;
+                big |= (bin < jmax && h[j] > kBinSortMax) ? 1u : 0u;
+                first += h[j];
+            }
+            *crowded = __syncthreads_or((int)big);         // (also: every bin start is written before the gather reads it)
+            *bin_lo = lo;
+            *bin_sh = sh;
             return (int)cnt;
         }
         // bins [0, jmax) are empty and bin jmax alone exceeds kChunk: refine inside it
@@ -229,19 +278,71 @@ static __device__ int select_chunk(NmsSmem &s, const unsigned long long *keys, i
     }
 }
 
-static __device__ void bitonic_sort(unsigned long long *a, int n_pow2) {
-    for (int k = 2; k <= n_pow2; k <<= 1) {
+// Bitonic sort of P = E * kNmsThreads keys in shared memory `a` (ascending).  Thread t keeps the E consecutive keys
+// a[t*E .. t*E+E) in registers: partners at distance j < E are exchanged in registers, at E <= j < 32*E by warp shuffles,
+// and only at j >= 32*E (a partner in another warp: 10 of the 55 / 66 steps at P = 1024 / 2048) through shared memory,
+// alternating between `a` and `scratch` so that one barrier per such step suffices.
+template <int E>
+static __device__ void bitonic_sort_regs(unsigned long long *a, unsigned long long *scratch) {
+    constexpr int P = E * kNmsThreads;
+    const int t = threadIdx.x;
+    unsigned long long v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = a[t * E + e];
+    bool to_scratch = true;
+    for (int k = 2; k <= P; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < (n_pow2 >> 1); t += kNmsThreads) {
-                const int ix = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int pj = ix | j;
-                const unsigned long long x = a[ix], y = a[pj];
-                const bool up = (ix & k) == 0;
-                if ((x > y) == up) { a[ix] = y; a[pj] = x; }
+            if (j >= 32 * E) {
+                unsigned long long *buf = to_scratch ? scratch : a;
+                to_scratch = !to_scratch;
+#pragma unroll
+                for (int e = 0; e < E; ++e) buf[t * E + e] = v[e];
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int i = t * E + e;
+                    const unsigned long long pv = buf[i ^ j];
+                    const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+                    v[e] = keep_min ? (pv < v[e] ? pv : v[e]) : (pv > v[e] ? pv : v[e]);
+                }
+            } else if (j >= E) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int i = t * E + e;
+                    const unsigned long long pv = __shfl_xor_sync(0xffffffffu, v[e], j / E);
+                    const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+                    v[e] = keep_min ? (pv < v[e] ? pv : v[e]) : (pv > v[e] ? pv : v[e]);
+                }
+            } else {
+                // static register indices (a run-time e ^ j would put v[] in local memory); all E keys of a thread lie in
+                // the same k-block for k >= 2 * j, so they share the direction
+                const bool up = ((t * E) & k) == 0 || k < E;
+                auto cx = [&](unsigned long long &x, unsigned long long &y, bool ascending) {
+                    if ((x > y) == ascending) { const unsigned long long tmp = x; x = y; y = tmp; }
+                };
+                if constexpr (E == 2) {
+                    cx(v[0], v[1], up);
+                } else if constexpr (E == 4) {
+                    if (j == 1) {
+                        cx(v[0], v[1], k == 2 ? true : up);
+                        cx(v[2], v[3], k == 2 ? false : up);
+                    } else {
+                        cx(v[0], v[2], up);
+                        cx(v[1], v[3], up);
+                    }
+                }
             }
-            __syncthreads();
         }
     }
+    __syncthreads();                     // the last exchange step may still be reading `a`
+#pragma unroll
+    for (int e = 0; e < E; ++e) a[t * E + e] = v[e];
+    __syncthreads();
+}
+static __device__ void bitonic_sort(unsigned long long *a, unsigned long long *scratch, int n_pow2) {
+    if (n_pow2 <= kNmsThreads) bitonic_sort_regs<1>(a, scratch);          // callers pad to kNmsThreads keys at least
+    else if (n_pow2 == 2 * kNmsThreads) bitonic_sort_regs<2>(a, scratch);
+    else bitonic_sort_regs<4>(a, scratch);
 }
 
 // m <= kNmsThreads unique keys.  T = kNmsThreads / pow2ceil(m) (<= 32) adjacent lanes share one key:
@@ -275,8 +376,9 @@ __device__ void nms_image(NmsSmem &s, const NmsParams &p, const BoxSrc &src, int
                           bool stashed = false) {
     float *det = p.det + (size_t)b * p.max_det * 6;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // candidates wanted per selection: survivors rarely need more than ~2x max_det candidates
-    const unsigned int target = (unsigned)min(kChunk, max(kRound, 2 * p.max_det));
+    // candidates wanted per selection.  First chunk: survivors rarely need more than ~2x max_det candidates (the
+    // real-time setting never gets past it); later chunks are as large as the sort allows
+    unsigned int target = (unsigned)min(kChunk, max(kRound, 2 * p.max_det));
     if (threadIdx.x == 0) {
         s.nkept = 0;
         s.ext[0] = s.ext[1] = INFINITY;
@@ -284,7 +386,11 @@ __device__ void nms_image(NmsSmem &s, const NmsParams &p, const BoxSrc &src, int
         s.ext_bad = 0;
     }
     const bool chainable = p.nc <= kChainClasses;
-    for (int i = threadIdx.x; i < kChainClasses; i += kNmsThreads) s.khead[i] = -1;
+    for (int i = threadIdx.x; i < kChainClasses * kChainSplit; i += kNmsThreads) (&s.khead[0][0])[i] = -1;
+    // every key is <= key_hi (conf > conf_thres); with a confidence cut in force, <= the cut: a tighter range spreads the
+    // keys over more histogram bins (fewer shared-memory atomic conflicts, no refinement pass)
+    unsigned long long key_hi = p.key_hi;
+    if (p.cut_hi != nullptr) key_hi = min(key_hi, ((unsigned long long)p.cut_hi[b] << 32) | 0xFFFFFFFFull);
     int consumed = 0;               // candidates taken in sorted order so far (max_nms cut)
     int seen = 0;                   // keys gathered so far
     unsigned long long cur = 0ull;
@@ -295,17 +401,19 @@ __device__ void nms_image(NmsSmem &s, const NmsParams &p, const BoxSrc &src, int
 
     for (;;) {
         // ---- 1. next chunk of keys -------------------------------------------------------------
-        unsigned long long chunk_hi = ~0ull;
-        int m;
+        unsigned long long chunk_hi = ~0ull, bin_lo = 0ull;
+        int m, bin_sh = 0, crowded = 0;
+        bool binned = true;               // the chunk came out of select_chunk: its histogram positions the keys
         if (first && n <= kChunk) {
             m = n;
+            binned = false;
         } else if (first) {
             unsigned int below = 0;
-            m = select_chunk(s, keys, n, p.key_lo_hint, p.key_hi, target, &chunk_hi, &below);
-            if (below) m = select_chunk(s, keys, n, 0ull, p.key_hi, target, &chunk_hi, nullptr);   // conf > 1.0 exists
+            m = select_chunk(s, keys, n, p.key_lo_hint, key_hi, target, &chunk_hi, &below, &bin_lo, &bin_sh, &crowded);
+            if (below) m = select_chunk(s, keys, n, 0ull, key_hi, target, &chunk_hi, nullptr, &bin_lo, &bin_sh, &crowded);   // conf > 1.0 exists
             else cur = p.key_lo_hint;
         } else {
-            m = select_chunk(s, keys, n, cur, p.key_hi, target, &chunk_hi, nullptr);
+            m = select_chunk(s, keys, n, cur, key_hi, target, &chunk_hi, nullptr, &bin_lo, &bin_sh, &crowded);
         }
         first = false;
         if (m == 0) break;
@@ -314,31 +422,93 @@ __device__ void nms_image(NmsSmem &s, const NmsParams &p, const BoxSrc &src, int
         // ---- 2. gather + sort ------------------------------------------------------------------
         int mp = 32;
         while (mp < m) mp <<= 1;
-        if (!stashed) {                     // stashed implies first chunk, m == n <= kRankSortMax, keys in s.key
-            if (threadIdx.x == 0) s.m = 0u;
-            if (m > kRankSortMax)
-                for (int i = threadIdx.x; i < mp; i += kNmsThreads) s.key[i] = ~0ull;
-            __syncthreads();
+        unsigned long long *scratch = reinterpret_cast<unsigned long long *>(s.box);      // s.box is free until step 3
+        if (binned) {
+            // counting sort: every key of the chunk goes to the next free position of its histogram bin (the bins are in
+            // key order), then the few keys sharing a bin are ordered among themselves - O(m) instead of a bitonic network
             for_each_key(keys, n, [&](unsigned long long k) {
-                if (k >= cur && k <= chunk_hi) s.key[atomicAdd(&s.m, 1u)] = k;
+                if (k >= cur && k <= chunk_hi) s.key[atomicAdd(&s.hist[(unsigned int)((k - bin_lo) >> bin_sh)], 1u)] = k;
             });
             __syncthreads();
+            DSN_MARK(11);
+            DSN_LAP(33);   // gather
+            if (!crowded) {
+                for (int q = threadIdx.x; q < m; q += kNmsThreads) {
+                    const unsigned long long k = s.key[q];
+                    const unsigned int bin = (unsigned int)((k - bin_lo) >> bin_sh);
+                    const unsigned int st = bin ? s.hist[bin - 1] : 0u, en = s.hist[bin];      // after the gather: hist = bin ends
+                    unsigned int r = st;
+                    for (unsigned int i = st; i < en; ++i) r += s.key[i] < k ? 1u : 0u;
+                    scratch[en - st > 1u ? r : (unsigned)q] = k;
+                }
+                __syncthreads();
+                for (int q = threadIdx.x; q < m; q += kNmsThreads) s.key[q] = scratch[q];
+                __syncthreads();
+            } else {
+                mp = max(mp, kNmsThreads);
+                for (int i = m + threadIdx.x; i < mp; i += kNmsThreads) s.key[i] = ~0ull;
+                __syncthreads();
+                bitonic_sort(s.key, scratch, mp);
+            }
+        } else {
+            if (!stashed) {                     // stashed implies first chunk, m == n <= kRankSortMax, keys in s.key
+                if (threadIdx.x == 0) s.m = 0u;
+                if (m > kRankSortMax) {
+                    mp = max(mp, kNmsThreads);          // the register sort works on kNmsThreads keys or more
+                    for (int i = threadIdx.x; i < mp; i += kNmsThreads) s.key[i] = ~0ull;
+                }
+                __syncthreads();
+                for_each_key(keys, n, [&](unsigned long long k) {
+                    // one shared-memory atomic per warp and call instead of one per key
+                    const unsigned int act = __activemask();
+                    const bool take = k >= cur && k <= chunk_hi;
+                    const unsigned int bal = __ballot_sync(act, take);
+                    if (bal) {
+                        const int leader = __ffs(bal) - 1;
+                        unsigned int base = 0;
+                        if (lane == leader) base = atomicAdd(&s.m, (unsigned)__popc(bal));
+                        base = __shfl_sync(act, base, leader);
+                        if (take) s.key[base + __popc(bal & ((1u << lane) - 1u))] = k;
+                    }
+                });
+                __syncthreads();
+            }
+            DSN_MARK(11);
+            DSN_LAP(33);   // gather
+            if (m <= kRankSortMax) rank_sort(s.key, m);
+            else bitonic_sort(s.key, scratch, mp);
         }
-        DSN_MARK(11);
-        DSN_LAP(33);   // gather
-        if (m <= kRankSortMax) rank_sort(s.key, m);
-        else bitonic_sort(s.key, mp);
         DSN_MARK(12);
         DSN_LAP(34);   // sort
+        DSN_COUNT(52, 1);              // chunks
+        DSN_COUNT(53, m);              // keys gathered
         seen += m;
         if (m > p.max_nms - consumed) m = p.max_nms - consumed;          // general.py:728-729
         consumed += m;
         // ---- 3. boxes --------------------------------------------------------------------------
-        for (int i = threadIdx.x; i < m; i += kNmsThreads) {
-            const unsigned int ref = (unsigned int)s.key[i];
-            const unsigned int row = ref / (unsigned)p.nc;
-            s.box[i] = src(b, row);
-            s.off[i] = __fmul_rn((float)(ref - row * (unsigned)p.nc), p.off_mul);      // general.py:732
+        for (int i0 = 0; i0 < m; i0 += 2 * kNmsThreads) {
+            // two candidates per thread and pass: both rows' loads are in flight before either is decoded
+            const int ia = i0 + threadIdx.x, ib = ia + kNmsThreads;
+            unsigned int refa = 0, refb = 0, rowa = 0, rowb = 0;
+            RawBox qa{}, qb{};
+            if (ia < m) {
+                refa = (unsigned int)s.key[ia];
+                rowa = refa / (unsigned)p.nc;
+                qa = src.fetch(b, rowa);
+            }
+            if (ib < m) {
+                refb = (unsigned int)s.key[ib];
+                rowb = refb / (unsigned)p.nc;
+                qb = src.fetch(b, rowb);
+            }
+            if (ia < m) {
+                s.box[ia] = src.finish(qa);
+                s.off[ia] = __fmul_rn((float)(refa - rowa * (unsigned)p.nc), p.off_mul);      // general.py:732
+            }
+            if (ib < m) {
+                s.box[ib] = src.finish(qb);
+                s.off[ib] = __fmul_rn((float)(refb - rowb * (unsigned)p.nc), p.off_mul);
+            }
         }
         __syncthreads();
         DSN_MARK(13);
@@ -399,29 +569,60 @@ __device__ void nms_image(NmsSmem &s, const NmsParams &p, const BoxSrc &src, int
             // survivor chains stay complete; used for the pair tests only while the class-aware culling holds)
             const bool use_chain = chainable && cull;
             if (chainable) {
-                if (threadIdx.x < cnt) {
-                    const unsigned short c = s.rcls[threadIdx.x];
-                    int j = (int)threadIdx.x - 1;
-                    while (j >= 0 && s.rcls[j] != c) --j;
+                // previous candidate of the same class: inside the warp with one MATCH; across warps through a table of the
+                // last candidate of every class in every warp (at most kRound / 32 - 1 look-ups, whatever the class count)
+                for (int i = threadIdx.x; i < (kRound / 32) * p.nc; i += kNmsThreads) s.lastw[i / p.nc][i % p.nc] = -1;
+                __syncthreads();
+                const bool in_round = threadIdx.x < kRound;
+                const bool valid = in_round && threadIdx.x < cnt;
+                const unsigned int c = valid ? (unsigned)s.rcls[threadIdx.x] : 0xFFFFFFFFu;
+                unsigned int peers = 0;
+                if (in_round) {                                   // warps 0 .. kRound/32 - 1, all lanes
+                    peers = __match_any_sync(0xffffffffu, c);
+                    if (valid && (peers >> lane) == 1u) s.lastw[warp][c] = (short)threadIdx.x;      // no same-class lane above me
+                }
+                __syncthreads();
+                if (valid) {
+                    const unsigned int below = peers & ((1u << lane) - 1u);
+                    int j = -1;
+                    if (below) {
+                        j = (int)(threadIdx.x & ~31u) + (31 - __clz(below));
+                    } else {
+                        for (int w = warp - 1; w >= 0 && j < 0; --w) j = s.lastw[w][c];
+                    }
                     s.rprev[threadIdx.x] = (short)j;
                 }
                 __syncthreads();
             }
-            static_assert(kNmsThreads >= 2 * kRound, "the chain path runs (a) and (b) on disjoint halves of the CTA");
+            static_assert(kNmsThreads == kChainSplit * kRound, "the chain path tests a candidate with kChainSplit threads");
+            DSN_LAP(45);   // rprev chains
+            DSN_COUNT(50, 1);          // rounds
+            DSN_COUNT(51, cnt);        // candidates consumed
             if (use_chain) {
-                if (threadIdx.x < kRound) {
-                    // (a) against the survivors of the candidate's own class (newest first), then any survivors beyond
-                    //     the shared-memory cache
-                    const int j = threadIdx.x;
+                // (a) against the survivors of the candidate's own class: thread (j, half) walks the chain of that parity,
+                //     four hops at a time (the hops are the serial part, the tests of a group are independent), and leaves
+                //     at the first hit - at the eval setting nine candidates in ten die here
+                {
+                    const int j = threadIdx.x & (kRound - 1), half = threadIdx.x / kRound;
                     bool dead = false;
                     if (j < cnt && nkept0 > 0) {
                         const float4 bj = s.rbox[j];
                         const float aj = s.rarea[j], oj = s.roff[j];
-                        // no early exit: the tests of successive hops are independent, only the hop itself (one LDS) is serial
-#pragma unroll 4
-                        for (int k = s.khead[s.rcls[j]]; k >= 0; k = s.knext[k]) dead = suppresses(s.kbox[k], s.karea[k], bj, aj, p.thr_f) || dead;
-                        for (int k = kKeptSmem; k < nkept0 && !dead; ++k) {
-                            const float *r = det + (size_t)k * 6;
+                        int k = s.khead[s.rcls[j]][half];
+                        while (k >= 0) {
+                            const int k1 = s.knext[k];
+                            const int k2 = k1 >= 0 ? s.knext[k1] : -1;
+                            const int k3 = k2 >= 0 ? s.knext[k2] : -1;
+                            bool hit = suppresses(s.kbox[k], s.karea[k], bj, aj, p.thr_f);
+                            if (k1 >= 0) hit = suppresses(s.kbox[k1], s.karea[k1], bj, aj, p.thr_f) || hit;
+                            if (k2 >= 0) hit = suppresses(s.kbox[k2], s.karea[k2], bj, aj, p.thr_f) || hit;
+                            if (k3 >= 0) hit = suppresses(s.kbox[k3], s.karea[k3], bj, aj, p.thr_f) || hit;
+                            if (hit) { dead = true; break; }
+                            k = k3 >= 0 ? s.knext[k3] : -1;
+                        }
+                        // survivors beyond the shared-memory cache (max_det > kKeptSmem): split by parity as well
+                        for (int kk = kKeptSmem + half; kk < nkept0 && !dead; kk += kChainSplit) {
+                            const float *r = det + (size_t)kk * 6;
                             const float ok = __fmul_rn(r[5], p.off_mul);
                             if (ok != oj) continue;
                             const float4 bk = offset_box(make_float4(r[0], r[1], r[2], r[3]), ok);
@@ -429,17 +630,32 @@ __device__ void nms_image(NmsSmem &s, const NmsParams &p, const BoxSrc &src, int
                         }
                     }
                     const unsigned int bal = __ballot_sync(0xffffffffu, dead);
-                    if (lane == 0 && bal) atomicOr(&s.dead[warp], bal);
-                } else if (threadIdx.x < 2 * kRound) {
-                    // (b) inside the round: candidate i against the better-scored candidates of its class
-                    const int i = threadIdx.x - kRound;
-                    if (i < cnt) {
+                    if (lane == 0 && bal) atomicOr(&s.dead[warp & (kRound / 32 - 1)], bal);
+                }
+                __syncthreads();
+                DSN_LAP(46);   // (a) chains vs kept + sync
+                // (b) inside the round, among the candidates still alive: link each to the nearest better-scored alive
+                //     candidate of its class, then test it against that chain
+                if (threadIdx.x < cnt) {
+                    int j = s.rprev[threadIdx.x];
+                    while (j >= 0 && ((s.dead[j >> 5] >> (j & 31)) & 1u)) j = s.rprev[j];
+                    s.ralive[threadIdx.x] = (short)j;
+                }
+                __syncthreads();
+                DSN_LAP(47);   // alive links + sync
+                {
+                    // thread (i, half): the hop is a dependent shared-memory load, the test ~10x that - both threads of a
+                    // candidate walk its whole chain and each tests every other hop
+                    const int i = threadIdx.x & (kRound - 1), half = threadIdx.x / kRound;
+                    if (i < cnt && !((s.dead[i >> 5] >> (i & 31)) & 1u)) {
                         const float4 bi = s.rbox[i];
                         const float ai = s.rarea[i];
-#pragma unroll 4
-                        for (int j = s.rprev[i]; j >= 0; j = s.rprev[j]) {
+                        int hop = 0;
+#pragma unroll 2
+                        for (int j = s.ralive[i]; j >= 0; j = s.ralive[j], ++hop) {
+                            if ((hop & (kChainSplit - 1)) != half) continue;
                             if (suppresses(s.rbox[j], s.rarea[j], bi, ai, p.thr_f)) {
-                                atomicOr(&s.mask[j][i >> 6], 1ull << (i & 63));
+                                mask_set(s, j, i);
                                 atomicOr(&s.nz[j >> 5], 1u << (j & 31));
                             }
                         }
@@ -493,7 +709,7 @@ __device__ void nms_image(NmsSmem &s, const NmsParams &p, const BoxSrc &src, int
                         const int j = fst ? i1 + 1 + k : i2 + 1 + (k - len1);
                         if (cull && s.roff[j] != (fst ? o1 : o2)) continue;   // other class: cannot overlap
                         if (suppresses(fst ? b1 : b2, fst ? a1 : a2, s.rbox[j], s.rarea[j], p.thr_f)) {
-                            atomicOr(&s.mask[i][j >> 6], 1ull << (j & 63));
+                            mask_set(s, i, j);
                             atomicOr(&s.nz[i >> 5], 1u << (i & 31));
                         }
                     }
@@ -547,12 +763,18 @@ __device__ void nms_image(NmsSmem &s, const NmsParams &p, const BoxSrc &src, int
             DSN_LAP(40);   // (c) scan
             // (d) append survivors                                               general.py:745
             int my_slot = -1;
-            if (threadIdx.x < cnt) {
-                const int w = threadIdx.x >> 6, bit = threadIdx.x & 63;
-                const unsigned long long kb = s.keptbits[w];
-                if ((kb >> bit) & 1ull) {
-                    int slot = nkept0 + __popcll(kb & ((1ull << bit) - 1ull));
-                    for (int v = 0; v < w; ++v) slot += __popcll(s.keptbits[v]);
+            if (threadIdx.x < kRound) {
+                int slot = -1;
+                if (threadIdx.x < cnt) {
+                    const int w = threadIdx.x >> 6, bit = threadIdx.x & 63;
+                    const unsigned long long kb = s.keptbits[w];
+                    if ((kb >> bit) & 1ull) {
+                        slot = nkept0 + __popcll(kb & ((1ull << bit) - 1ull));
+                        for (int v = 0; v < w; ++v) slot += __popcll(s.keptbits[v]);
+                    }
+                }
+                s.rslot[threadIdx.x] = (short)slot;
+                if (slot >= 0) {
                     const int ci = s0 + threadIdx.x;
                     const float4 bx = s.box[ci];
                     const unsigned long long key = s.key[ci];
@@ -564,38 +786,37 @@ __device__ void nms_image(NmsSmem &s, const NmsParams &p, const BoxSrc &src, int
                         s.kbox[slot] = s.rbox[threadIdx.x];
                         s.karea[slot] = s.rarea[threadIdx.x];
                         s.koff[slot] = s.roff[threadIdx.x];
-                        if (chainable) {
-                            // link behind the previous survivor of the class: the nearest kept one up the round's chain,
-                            // else the class's newest survivor of earlier rounds
-                            int j = s.rprev[threadIdx.x];
-                            while (j >= 0 && !((s.keptbits[j >> 6] >> (j & 63)) & 1ull)) j = s.rprev[j];
-                            int prev;
-                            if (j >= 0) {
-                                prev = nkept0 + __popcll(s.keptbits[j >> 6] & ((1ull << (j & 63)) - 1ull));
-                                for (int v = 0; v < (j >> 6); ++v) prev += __popcll(s.keptbits[v]);
-                            } else {
-                                prev = s.khead[s.rcls[threadIdx.x]];
-                            }
-                            s.knext[slot] = (short)prev;
-                            my_slot = slot;
-                        }
+                        if (chainable) my_slot = slot;
                     }
                 }
             }
             if (chainable) {
+                __syncthreads();                                   // every rslot is written
+                if (my_slot >= 0) {
+                    // link behind the previous survivor of the class with the same slot parity: the nearest such kept
+                    // candidate up the round's chain, else that chain's newest survivor of earlier rounds
+                    int j = s.rprev[threadIdx.x];
+                    while (j >= 0 && (s.rslot[j] < 0 || ((s.rslot[j] ^ my_slot) & (kChainSplit - 1)))) j = s.rprev[j];
+                    s.knext[my_slot] = j >= 0 ? s.rslot[j] : (short)s.khead[s.rcls[threadIdx.x]][my_slot & (kChainSplit - 1)];
+                }
                 __syncthreads();                                   // every knext is written before a head moves
-                if (my_slot >= 0) atomicMax(&s.khead[s.rcls[threadIdx.x]], my_slot);
+                if (my_slot >= 0) atomicMax(&s.khead[s.rcls[threadIdx.x]][my_slot & (kChainSplit - 1)], my_slot);
             }
             __syncthreads();
             DSN_LAP(41);   // (d) append
             done = s.nkept >= p.max_det;
         }
         if (done || consumed >= p.max_nms || seen >= n) break;
-        if (chunk_hi >= p.key_hi) break;
+        if (chunk_hi >= key_hi) break;
         cur = chunk_hi + 1ull;
+        // an image that needs a second chunk is in the many-candidates regime (a few percent survive, and the survival
+        // rate keeps falling as survivors accumulate): pay for select + gather + sort as rarely as possible
+        target = (unsigned)kChunk;
     }
     __syncthreads();
     DSN_MARK(16);
+    DSN_COUNT_ALL(54, 55, consumed);      // candidates consumed: sum / max over the images
+    DSN_COUNT_ALL(56, 57, seen);          // keys gathered (all chunks)
     // Confidence cut (dsn_conf_cut_levels): the emitted keys are exactly the best candidates of the image, so the
     // result is the reference's whenever the greedy pass stopped by itself (max_det survivors, or max_nms candidates
     // consumed).  Running out of emitted keys first means dropped candidates could still have mattered: -2.
@@ -625,6 +846,7 @@ static inline int make_nms_params(NmsParams &p, const uint64_t *keys, int64_t ca
     memcpy(&tb, &ct, 4);
     p.key_hi = ((unsigned long long)(~tb) << 32) | 0xFFFFFFFFull;   // conf > conf_thres  =>  key <= this
     p.cut_dropped = nullptr;
+    p.cut_hi = nullptr;
     p.det = det;
     p.det_count = det_count;
     return DSN_OK;

@@ -27,11 +27,14 @@ struct SegParams {
 
 constexpr int kMaxPackedC = 4;      // template instantiations of the fast path
 // build-time tuning switches (no run-time environment knobs in the launchers)
-#ifndef DSN_SEG_MASK_BULK
-#define DSN_SEG_MASK_BULK 1          // detect-mode fp32 mask: rows staged in shared memory, written with TMA bulk stores
-#endif
 #ifndef DSN_SEG_MASK_CTAS_PER_SM
-#define DSN_SEG_MASK_CTAS_PER_SM 2
+#define DSN_SEG_MASK_CTAS_PER_SM 0   // detect-mode mask kernel: resident CTAs per SM the grid is sized for (0: one CTA per block)
+#endif
+#ifndef DSN_SEG_MASK_RPB
+#define DSN_SEG_MASK_RPB 32          // ... output rows per block (work item)
+#endif
+#ifndef DSN_SEG_MASK_PX
+#define DSN_SEG_MASK_PX 4            // ... pixels per thread (4 or 8)
 #endif
 constexpr int kPrefetchRows = 8;    // eval kernel: target rows pulled into L2 this far ahead of the register loads
 
@@ -423,175 +426,144 @@ __global__ void __maxnreg__(HAS_TGT ? 96 : 128) seg_fused_rows_kernel(const SegP
 
 // ---- detect mode (mask only): the store stream ---------------------------------------------------------------------
 // The fp32 mask is 98 % of the bytes of a detect-mode step (4 B per pixel out, 1/16 B per pixel in), so this kernel is a
-// pure write stream with ~20 instructions of arithmetic per 16 bytes.  Same decomposition as above (persistent grid,
-// one contiguous run of output rows per CTA, a thread owns a 4-pixel column group and keeps the horizontally
-// interpolated source rows T / B in registers), tuned for the time to the first store and for how the stores leave:
-//   * no per-CTA tables over all H rows: one 16-byte entry (l0, l1, y0) per output row of THIS CTA's run, built while
-//     the first source rows are already in flight;
-//   * BULK: the rows are staged in shared memory (one STS.128 per thread per row) and leave kStageRows at a time through
-//     ONE TMA bulk copy shared -> global per stage (cp.async.bulk, UBLKCP; the rows of a run are contiguous in the
-//     mask), double-buffered: no LSU store traffic, 20 KB bursts;
-//   * otherwise one 16-byte streaming store per thread per row (any width, uint8 masks).
-constexpr int kStageRows = 8;
+// pure write stream with ~25 instructions of arithmetic per 16 bytes.  A thread owns a PX-pixel column group and keeps the
+// horizontally interpolated source rows T / B in registers, as above; what differs is how the work is cut:
+//   * a work item is a BLOCK of `rows_per_block` consecutive output rows of one image (full width), and CTA c takes the
+//     blocks c, c + gridDim.x, ... — at any moment the resident CTAs write ONE compact, advancing window of the mask
+//     instead of one far-apart run per CTA.  A pure store stream with the same cut reaches 6.2 TB/s on B200, against
+//     5.2 TB/s for 296 separate runs and for TMA bulk stores out of shared memory (profiles/experiments/stbw.cu);
+//   * no shared-memory tables and no barrier: row coefficients are computed on the fly (6 instructions per row), so a
+//     CTA's first store is one L2 round trip (its two source rows) after launch.
+template <int PX>
+struct XCoef {
+    float l0[PX], l1[PX];
+    unsigned shx;          // bit k: pixel k interpolates between source columns (c1, c2) instead of (c0, c1)
+    int c0, c1, c2;
+};
+template <int PX>
+__device__ __forceinline__ XCoef<PX> make_xcoef(const SegParams &p, int X) {
+    XCoef<PX> xc;
+    const Lerp lx0 = lerp_coeff(p.sx, X, p.w);
+    xc.l0[0] = lx0.l0; xc.l1[0] = lx0.l1; xc.shx = 0u;
+#pragma unroll
+    for (int k = 1; k < PX; ++k) {
+        const Lerp lx = lerp_coeff(p.sx, X + k, p.w);
+        xc.l0[k] = lx.l0; xc.l1[k] = lx.l1;
+        xc.shx |= (lx.i0 != lx0.i0 ? 1u : 0u) << k;                  // source column advanced by one (never by two: see the dispatch)
+    }
+    xc.c0 = lx0.i0; xc.c1 = min(lx0.i0 + 1, p.w - 1); xc.c2 = min(lx0.i0 + 2, p.w - 1);
+    return xc;
+}
+// horizontal lerp of one source row (yolo.py:183, horizontal first); returns false if a raw value is inf / NaN
+template <int C, int PX>
+__device__ __forceinline__ bool hrow_px(const XCoef<PX> &xc, const SrcCols<C> &sc, float (&out)[C][PX]) {
+    bool fin = true;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        fin = fin && (fabsf(sc.v[c][0]) < INFINITY) && (fabsf(sc.v[c][1]) < INFINITY) && (fabsf(sc.v[c][2]) < INFINITY);
+#pragma unroll
+        for (int k = 0; k < PX; ++k) {
+            const bool sh = (xc.shx >> k) & 1u;
+            const float a = sh ? sc.v[c][1] : sc.v[c][0];
+            const float bb = sh ? sc.v[c][2] : sc.v[c][1];
+            out[c][k] = __fmaf_rn(xc.l0[k], a, __fmul_rn(xc.l1[k], bb));
+        }
+    }
+    return fin;
+}
 
-__device__ __forceinline__ uint32_t seg_smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
-
-template <int C, int MASK, bool BULK>
-__global__ void __launch_bounds__(512) seg_mask_rows_kernel(const SegParams p, const int rows_per_cta) {
-    extern __shared__ __align__(128) unsigned char seg_smem[];
-    // [H], indexed by the output row Y: (l0, l1, y0 as int bits, -); filled for the min(run, H) rows this CTA visits
-    float4 *tab = reinterpret_cast<float4 *>(seg_smem);
-    float *stage = reinterpret_cast<float *>(seg_smem + (((size_t)p.H * sizeof(float4) + 127) & ~(size_t)127));   // BULK: [2][kStageRows][W]
-    const int G = p.W >> 2;
+template <int C, int MASK, int PX>
+__global__ void __launch_bounds__(512) seg_mask_rows_kernel(const SegParams p, const int rows_per_block, const int blocks_per_image,
+                                                            const long long nblocks) {
+    static_assert(PX == 4 || PX == 8, "a thread owns 4 or 8 pixels of a row");
+    const int G = p.W / PX;
     const int plane = p.h * p.w;
-    const long long total_rows = (long long)p.bs * p.H;
-    const long long r_begin = (long long)blockIdx.x * rows_per_cta;
-    const long long r_end = min(total_rows, r_begin + rows_per_cta);
-    if (r_begin >= r_end) return;
-    const int b0 = (int)(r_begin / p.H);
-    const int Y0 = (int)(r_begin - (long long)b0 * p.H);
-
     for (int g0 = 0; g0 < G; g0 += blockDim.x) {
-        if (!BULK && g0 + (int)(threadIdx.x & ~31u) >= G) break;        // whole warp beyond the row: nothing to do
+        if (g0 + (int)(threadIdx.x & ~31u) >= G) break;        // whole warp beyond the row: nothing to do
         const int g = g0 + threadIdx.x;
         const bool active = g < G;
-        const int X = (active ? g : 0) << 2;
-        float l0[4], l1[4];
-        bool shx[4];
-        int xa;
-        {
-            const Lerp lx0 = lerp_coeff(p.sx, X, p.w);
-            xa = lx0.i0;
-            l0[0] = lx0.l0; l1[0] = lx0.l1; shx[0] = false;
-#pragma unroll
-            for (int k = 1; k < 4; ++k) {
-                const Lerp lx = lerp_coeff(p.sx, X + k, p.w);
-                l0[k] = lx.l0; l1[k] = lx.l1; shx[k] = lx.i0 != xa;     // source column advanced by one
+        const int X = (active ? g : 0) * PX;
+        const XCoef<PX> xc = make_xcoef<PX>(p, X);
+        bool finite = true;
+        for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+            const int b = (int)(blk / blocks_per_image);
+            int Y = (int)(blk - (long long)b * blocks_per_image) * rows_per_block;
+            const int Yend = min(p.H, Y + rows_per_block);
+            const float *img = p.logits + (size_t)b * C * plane;
+            int y0 = lerp_coeff(p.sy, Y, p.h).i0;
+            float T[C][PX], B[C][PX];
+            SrcCols<C> nxt;
+            {
+                const SrcCols<C> s0 = load_src_row<C>(img, plane, y0 * p.w, xc.c0, xc.c1, xc.c2);
+                const SrcCols<C> s1 = load_src_row<C>(img, plane, min(y0 + 1, p.h - 1) * p.w, xc.c0, xc.c1, xc.c2);
+                nxt = load_src_row<C>(img, plane, min(y0 + 2, p.h - 1) * p.w, xc.c0, xc.c1, xc.c2);     // one source row ahead
+                const bool f0 = hrow_px<C, PX>(xc, s0, T);
+                const bool f1 = hrow_px<C, PX>(xc, s1, B);
+                finite = finite && f0 && f1;
             }
-        }
-        const int c0 = xa, c1 = min(xa + 1, p.w - 1), c2 = min(xa + 2, p.w - 1);
-        auto hrow = [&](const SrcCols<C> &sc, float (&out)[C][4]) -> bool {
-            bool fin = true;
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                fin = fin && (fabsf(sc.v[c][0]) < INFINITY) && (fabsf(sc.v[c][1]) < INFINITY) && (fabsf(sc.v[c][2]) < INFINITY);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float a = shx[k] ? sc.v[c][1] : sc.v[c][0];
-                    const float bb = shx[k] ? sc.v[c][2] : sc.v[c][1];
-                    out[c][k] = __fmaf_rn(l0[k], a, __fmul_rn(l1[k], bb));
-                }
-            }
-            return fin;
-        };
-        // first source rows of the run: in flight while the row table is built
-        int y0 = lerp_coeff(p.sy, Y0, p.h).i0;
-        const float *img = p.logits + (size_t)b0 * C * plane;
-        SrcCols<C> s0 = load_src_row<C>(img, plane, y0 * p.w, c0, c1, c2);
-        SrcCols<C> s1 = load_src_row<C>(img, plane, min(y0 + 1, p.h - 1) * p.w, c0, c1, c2);
-        SrcCols<C> nxt = load_src_row<C>(img, plane, min(y0 + 2, p.h - 1) * p.w, c0, c1, c2);
-        if (g0 == 0) {
-            const int n = (int)min((long long)p.H, r_end - r_begin);
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                int Y = Y0 + i;
-                Y = Y >= p.H ? Y - p.H : Y;
+            const size_t off = ((size_t)b * p.H + Y) * p.W + X;
+            float *m32 = (MASK & 1) ? p.mask_f32 + off : nullptr;
+            uint8_t *m8 = (MASK & 2) ? p.mask_u8 + off : nullptr;
+#pragma unroll 2
+            for (; Y < Yend; ++Y) {
                 const Lerp ly = lerp_coeff(p.sy, Y, p.h);
-                tab[Y] = make_float4(ly.l0, ly.l1, __int_as_float(ly.i0), 0.f);
-            }
-            __syncthreads();
-        }
-        float T[C][4], B[C][4];
-        bool finite = hrow(s0, T);
-        finite = hrow(s1, B) && finite;
-
-        float *m32 = (MASK & 1) ? p.mask_f32 + (size_t)r_begin * p.W + X : nullptr;     // (b*H + Y)*W + X == r*W + X
-        uint8_t *m8 = (MASK & 2) ? p.mask_u8 + (size_t)r_begin * p.W + X : nullptr;
-        int st = 0, slot = 0;                         // BULK: current stage, rows staged in it
-        long long r_stage = r_begin;                  // BULK: global row of the stage's first row
-        auto flush_stage = [&]() {
-            // generic-proxy writes of the stage -> visible to the async proxy, then one thread hands the stage to the TMA
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                const float *src = stage + (size_t)st * kStageRows * p.W;
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.mask_f32 + (size_t)r_stage * p.W),
-                             "r"(seg_smem_u32(src)), "r"((unsigned)((size_t)slot * p.W * sizeof(float)))
-                             : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");       // the other stage has been read out
-            }
-            __syncthreads();
-            r_stage += slot;
-            slot = 0;
-            st ^= 1;
-        };
-
-        int b = b0, Y = Y0;
-        for (long long r = r_begin; r < r_end; ++r) {
-            const float4 t = tab[Y];
-            if (__float_as_int(t.z) != y0) {                        // CTA-uniform: the source row pair moves down by one
-                ++y0;
+                if (ly.i0 != y0) {                                   // CTA-uniform: the source row pair moves down by one
+                    ++y0;
 #pragma unroll
-                for (int c = 0; c < C; ++c)
+                    for (int c = 0; c < C; ++c)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) T[c][k] = B[c][k];
-                finite = hrow(nxt, B) && finite;
-                nxt = load_src_row<C>(img, plane, min(y0 + 2, p.h - 1) * p.w, c0, c1, c2);     // prefetch one source row ahead
-            }
-            const float2 lm = make_float2(t.x, t.y);
-            int pred[4];
-            float predf[4];
-            if (C == 2 && finite) {
-                float v0[4], v1[4];                                  // no NaN can appear: plain compare, first maximum wins
-                vlerp4(lm, T[0], B[0], v0);
-                vlerp4(lm, T[C - 1], B[C - 1], v1);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    pred[k] = v1[k] > v0[k] ? 1 : 0;
-                    predf[k] = v1[k] > v0[k] ? 1.0f : 0.0f;
+                        for (int k = 0; k < PX; ++k) T[c][k] = B[c][k];
+                    const bool f2 = hrow_px<C, PX>(xc, nxt, B);
+                    finite = finite && f2;
+                    nxt = load_src_row<C>(img, plane, min(y0 + 2, p.h - 1) * p.w, xc.c0, xc.c1, xc.c2);
                 }
-            } else {
-                float vals[C][4];
+                const float2 lm = make_float2(ly.l0, ly.l1);
+                int pred[PX];
+                float predf[PX];
+                if (C == 2 && finite) {
+                    // no NaN can appear: plain compare, first maximum wins
 #pragma unroll
-                for (int c = 0; c < C; ++c) vlerp4(lm, T[c], B[c], vals[c]);
+                    for (int q = 0; q < PX; q += 4) {
+                        float v0[4], v1[4];
+                        vlerp4(lm, *reinterpret_cast<const float(*)[4]>(&T[0][q]), *reinterpret_cast<const float(*)[4]>(&B[0][q]), v0);
+                        vlerp4(lm, *reinterpret_cast<const float(*)[4]>(&T[C - 1][q]), *reinterpret_cast<const float(*)[4]>(&B[C - 1][q]), v1);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    float best = vals[0][k];
-                    int bi = 0;
+                        for (int k = 0; k < 4; ++k) {
+                            pred[q + k] = v1[k] > v0[k] ? 1 : 0;
+                            predf[q + k] = v1[k] > v0[k] ? 1.0f : 0.0f;
+                        }
+                    }
+                } else {
 #pragma unroll
-                    for (int c = 1; c < C; ++c)
-                        if (argmax_better(vals[c][k], best)) { best = vals[c][k]; bi = c; }
-                    pred[k] = bi;
-                    predf[k] = (float)bi;
+                    for (int q = 0; q < PX; q += 4) {
+                        float vals[C][4];
+#pragma unroll
+                        for (int c = 0; c < C; ++c)
+                            vlerp4(lm, *reinterpret_cast<const float(*)[4]>(&T[c][q]), *reinterpret_cast<const float(*)[4]>(&B[c][q]), vals[c]);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            float best = vals[0][k];
+                            int bi = 0;
+#pragma unroll
+                            for (int c = 1; c < C; ++c)
+                                if (argmax_better(vals[c][k], best)) { best = vals[c][k]; bi = c; }
+                            pred[q + k] = bi;
+                            predf[q + k] = (float)bi;
+                        }
+                    }
                 }
+                if (active) {
+#pragma unroll
+                    for (int q = 0; q < PX; q += 4) {
+                        if (MASK & 1) stg_stream_f4(m32 + q, make_float4(predf[q], predf[q + 1], predf[q + 2], predf[q + 3]));
+                        if (MASK & 2)
+                            *reinterpret_cast<uint32_t *>(m8 + q) = (uint32_t)pred[q] | ((uint32_t)pred[q + 1] << 8) |
+                                                                    ((uint32_t)pred[q + 2] << 16) | ((uint32_t)pred[q + 3] << 24);
+                    }
+                }
+                if (MASK & 1) m32 += p.W;
+                if (MASK & 2) m8 += p.W;
             }
-            if (BULK) {
-                if (active)
-                    *reinterpret_cast<float4 *>(stage + ((size_t)st * kStageRows + slot) * p.W + X) = make_float4(predf[0], predf[1], predf[2], predf[3]);
-                if (++slot == kStageRows) flush_stage();
-            } else if (active) {
-                if (MASK & 1) stg_stream_f4(m32, make_float4(predf[0], predf[1], predf[2], predf[3]));
-                if (MASK & 2)
-                    *reinterpret_cast<uint32_t *>(m8) =
-                        (uint32_t)pred[0] | ((uint32_t)pred[1] << 8) | ((uint32_t)pred[2] << 16) | ((uint32_t)pred[3] << 24);
-            }
-            if (MASK & 1) m32 += p.W;
-            if (MASK & 2) m8 += p.W;
-            if (++Y == p.H && r + 1 < r_end) {                      // next image: restart the source-row walk
-                Y = 0;
-                ++b;
-                img = p.logits + (size_t)b * C * plane;
-                y0 = 0;
-                s0 = load_src_row<C>(img, plane, 0, c0, c1, c2);
-                s1 = load_src_row<C>(img, plane, min(1, p.h - 1) * p.w, c0, c1, c2);
-                nxt = load_src_row<C>(img, plane, min(2, p.h - 1) * p.w, c0, c1, c2);
-                finite = hrow(s0, T) && finite;
-                finite = hrow(s1, B) && finite;
-            }
-        }
-        if (BULK) {
-            if (slot > 0) flush_stage();
-            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // smem must outlive the reads
         }
     }
 }
@@ -821,23 +793,29 @@ static int launch_eval_rows_w(const SegParams &p, cudaStream_t st) {
     return DSN_OK;
 }
 
-// detect mode (mask only).  Two CTAs per SM saturate the store stream and leave the rest of the SM (registers, shared
-// memory) to the NMS CTA of another batch in flight.
+// detect mode (mask only): blocks of kMaskRowsPerBlock rows dealt round-robin to a grid of kMaskCtasPerSm CTAs per SM
+// (0: one CTA per block)
 constexpr int kMaskCtasPerSm = DSN_SEG_MASK_CTAS_PER_SM;
-template <int C, int M, bool BULK>
+constexpr int kMaskRowsPerBlock = DSN_SEG_MASK_RPB;
+template <int C, int M, int PX>
 static int launch_mask_rows(const SegParams &p, cudaStream_t st) {
-    const int G = p.W / 4;
+    const int G = p.W / PX;
     const int threads = std::min(512, (G + 31) / 32 * 32);
-    size_t smem = (((size_t)p.H * sizeof(float4) + 127) & ~(size_t)127);
-    if (BULK) smem += (size_t)2 * kStageRows * p.W * sizeof(float);
-    static DeviceOnce once;                   // per template instantiation
-    if (int rc = raise_dynamic_smem(once, seg_mask_rows_kernel<C, M, BULK>, 200 * 1024)) return rc;
-    long long grid;
-    int rows_per_cta;
-    rows_grid(p, kMaskCtasPerSm, grid, rows_per_cta);
-    seg_mask_rows_kernel<C, M, BULK><<<(unsigned)grid, threads, smem, st>>>(p, rows_per_cta);
+    const int rpb = std::min(p.H, kMaskRowsPerBlock);
+    const int bpi = (p.H + rpb - 1) / rpb;
+    const long long nblocks = (long long)p.bs * bpi;
+    long long grid = kMaskCtasPerSm > 0 ? std::min<long long>(nblocks, (long long)sm_count() * kMaskCtasPerSm) : nblocks;
+    grid = std::min<long long>(grid, 0x7fffffffLL);
+    seg_mask_rows_kernel<C, M, PX><<<(unsigned)grid, threads, 0, st>>>(p, rpb, bpi, nblocks);
     DSN_CHECK_LAUNCH();
     return DSN_OK;
+}
+template <int C, int M>
+static int launch_mask(const SegParams &p, cudaStream_t st) {
+    // 8 pixels per thread when they cannot span more than two source intervals (7 * sx < 1) and the rows allow 32-byte groups
+    const bool px8 = DSN_SEG_MASK_PX == 8 && p.W % 8 == 0 && (double)(p.W - 1) > 7.0 * (double)(p.w - 1) + 1e-3 &&
+                     ((M & 1) == 0 || (((uintptr_t)p.mask_f32 & 15) == 0)) && ((M & 2) == 0 || (((uintptr_t)p.mask_u8 & 3) == 0));
+    return px8 ? launch_mask_rows<C, M, 8>(p, st) : launch_mask_rows<C, M, 4>(p, st);
 }
 
 template <int C>
@@ -853,13 +831,9 @@ static int launch_tile(const SegParams &p, cudaStream_t st) {
             default: return small ? launch_eval_rows_w<C, 3, unsigned int>(p, st) : launch_eval_rows_w<C, 3, unsigned long long>(p, st);
         }
     }
-    if (mk == 1) {
-        // fp32 mask, one pass of the CTA covers a row, stages fit: rows leave through TMA bulk stores
-        const bool bulk = DSN_SEG_MASK_BULK && p.W / 4 <= 512 && (size_t)2 * kStageRows * p.W * sizeof(float) + (size_t)p.H * 16 <= 96 * 1024;
-        return bulk ? launch_mask_rows<C, 1, true>(p, st) : launch_mask_rows<C, 1, false>(p, st);
-    }
-    if (mk == 2) return launch_mask_rows<C, 2, false>(p, st);
-    return launch_mask_rows<C, 3, false>(p, st);
+    if (mk == 1) return launch_mask<C, 1>(p, st);
+    if (mk == 2) return launch_mask<C, 2>(p, st);
+    return launch_mask<C, 3>(p, st);
 }
 
 }  // namespace dsn

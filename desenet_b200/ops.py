@@ -208,19 +208,57 @@ def filter_z(z: torch.Tensor, conf_thres: float, multi_label: bool, classes=None
     return keys, counts
 
 
+def pad_labels(labels, bs: int, device):
+    """general.py:690-696 a-priori labels (one (n_i, 5) [cls, x, y, w, h] array per image) as the padded device arrays of
+    the C ABI: ``(labels (bs, L, 5) fp32, label_count (bs) int32)``, or None when there is no label at all."""
+    L = max((len(l) for l in labels), default=0)
+    if L == 0:
+        return None
+    out = torch.zeros((bs, L, 5), dtype=torch.float32)
+    cnt = torch.zeros((bs,), dtype=torch.int32)
+    for i, l in enumerate(labels[:bs]):
+        if len(l):
+            t = torch.as_tensor(l, dtype=torch.float32).detach().cpu().reshape(-1, 5)
+            out[i, :t.shape[0]] = t
+            cnt[i] = t.shape[0]
+    return out.to(device), cnt.to(device)
+
+
+def append_label_keys(head: Head, padded, conf_thres: float, classes, keys: torch.Tensor, counts: torch.Tensor):
+    """Add the label candidates (see ``pad_labels``) to the keys ``filter_levels`` produced (same stream, after it)."""
+    lib = _lib.load()
+    labels, label_count = padded
+    with torch.cuda.device(head.device):
+        rc = lib.dsn_append_label_keys(_ptr(labels), _ptr(label_count), head.bs, int(labels.shape[1]), head.A, head.nc,
+                                       float(conf_thres), class_mask(classes, head.nc), _ptr(keys), int(keys.shape[1]),
+                                       _ptr(counts), _stream(head.device))
+    _lib.check(rc, "dsn_append_label_keys")
+
+
 def nms_levels(head: Head, keys: torch.Tensor, counts: torch.Tensor, conf_thres: float, iou_thres: float,
                agnostic: bool, max_det: int, max_nms: int = MAX_NMS, max_wh: float = MAX_WH,
-               det: Optional[torch.Tensor] = None, det_count: Optional[torch.Tensor] = None, cut: Optional[ConfCut] = None):
+               det: Optional[torch.Tensor] = None, det_count: Optional[torch.Tensor] = None, cut: Optional[ConfCut] = None,
+               labels=None):
     lib = _lib.load()
     with torch.cuda.device(head.device):
         if det is None:
             det = torch.empty((head.bs, max(max_det, 0), 6), dtype=torch.float32, device=head.device)
         if det_count is None:
             det_count = torch.empty((head.bs,), dtype=torch.int32, device=head.device)
+        if labels is not None:          # rows >= A are the label rows of ``pad_labels`` (no confidence cut on this path)
+            assert cut is None
+            rc = lib.dsn_nms_levels_labels(head.c_raw, head.c_ny, head.c_nx, head.c_stride, head.c_anchor, head.nl, head.bs,
+                                           head.na, head.no, _ptr(keys), int(keys.shape[1]), _ptr(counts), float(conf_thres),
+                                           float(iou_thres), int(bool(agnostic)), int(max_nms), int(max_det), float(max_wh),
+                                           _ptr(labels[0]), int(labels[0].shape[1]), _ptr(det), _ptr(det_count),
+                                           _stream(head.device))
+            _lib.check(rc, "dsn_nms_levels_labels")
+            return det, det_count
         rc = lib.dsn_nms_levels(head.c_raw, head.c_ny, head.c_nx, head.c_stride, head.c_anchor, head.nl, head.bs,
                                 head.na, head.no, _ptr(keys), int(keys.shape[1]), _ptr(counts), float(conf_thres),
                                 float(iou_thres), int(bool(agnostic)), int(max_nms), int(max_det), float(max_wh),
-                                _ptr(cut.dropped if cut else None), _ptr(det), _ptr(det_count), _stream(head.device))
+                                _ptr(cut.cut_hi if cut else None), _ptr(cut.dropped if cut else None), _ptr(det), _ptr(det_count),
+                                _stream(head.device))
     _lib.check(rc, "dsn_nms_levels")
     return det, det_count
 

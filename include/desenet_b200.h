@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define DSN_VERSION 100          /* major*10000 + minor*100 + patch */
+#define DSN_VERSION 200          /* major*10000 + minor*100 + patch */
 #define DSN_MAX_LEVELS 8         /* detection levels (reference: nl = 3, core/models/yolo.py:244) */
 #define DSN_MAX_ANCHORS 16       /* anchors per level (reference: na = 3, yolo.py:245) */
 #define DSN_MAX_CM_ROWS 8        /* confusion-matrix rows handled by the packed-counter path */
@@ -118,14 +118,31 @@ int dsn_filter_z(const float *z, int bs, int64_t A, int no, float conf_thres, in
  *   det        (bs, max_det, 6) fp32, rows >= det_count[i] are left untouched
  *   det_count  (bs) int32; -1 when counts[i] > cap (keys were dropped: retry with a larger cap); -2 when a
  *              confidence cut was in force and the NMS ran out of emitted candidates (retry without the cut)
- *   cut_dropped (dsn_nms_levels only) device (bs) int32 written by dsn_conf_cut_levels, or NULL
+ *   cut_hi / cut_dropped (dsn_nms_levels only) device (bs) uint32 / int32 written by dsn_conf_cut_levels, or both NULL
+ *              (cut_hi bounds the key range the selection looks at; cut_dropped arms the -2 report)
  * Box source is either the raw levels (dsn_nms_levels: decode on the fly, yolo.py:266-269 +
  * general.py:523-530) or a decoded prediction (dsn_nms_z). */
 int dsn_nms_levels(const float *const *raw, const int *ny, const int *nx, const float *stride,
                    const float *anchor_grid, int nl, int bs, int na, int no,
                    const uint64_t *keys, int64_t cap, const int *counts, float conf_thres,
                    double iou_thres, int agnostic, int max_nms, int max_det, float max_wh,
-                   const int *cut_dropped, float *det, int *det_count, void *stream);
+                   const unsigned int *cut_hi, const int *cut_dropped, float *det, int *det_count, void *stream);
+
+/* A-priori labels on the raw-level path (general.py:690-696; scripts/val.py:228 passes them with save_hybrid): label j
+ * of image b acts as prediction row A + j with obj = 1 and a one-hot class, i.e. one candidate of confidence 1.0.
+ * dsn_append_label_keys adds those candidates to the keys of dsn_filter_levels (same stream, after it; cap must leave
+ * room for max_labels more keys per image); dsn_nms_levels_labels is dsn_nms_levels with the label boxes as the box
+ * source of rows >= A.
+ *   labels       device (bs, max_labels, 5) fp32 rows [cls, x, y, w, h] in network-input pixels
+ *   label_count  device (bs) int32 valid rows per image */
+int dsn_append_label_keys(const float *labels, const int *label_count, int bs, int max_labels, int64_t A, int nc,
+                          float conf_thres, const uint64_t *class_mask, uint64_t *keys, int64_t cap, int *counts,
+                          void *stream);
+int dsn_nms_levels_labels(const float *const *raw, const int *ny, const int *nx, const float *stride,
+                          const float *anchor_grid, int nl, int bs, int na, int no,
+                          const uint64_t *keys, int64_t cap, const int *counts, float conf_thres,
+                          double iou_thres, int agnostic, int max_nms, int max_det, float max_wh,
+                          const float *labels, int max_labels, float *det, int *det_count, void *stream);
 
 int dsn_nms_z(const float *z, int bs, int64_t A, int no,
               const uint64_t *keys, int64_t cap, const int *counts, float conf_thres,
