@@ -18,37 +18,37 @@ SIGNATURES = {
     "dsn_version": (c_int, []),
     "dsn_error_string": (c_char_p, [c_int]),
     "dsn_graph_launch_many": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int]),
-    "dsn_detect_decode": (c_int, [_FLOATPP, POINTER(c_int), POINTER(c_int), POINTER(c_float), POINTER(c_float),
+    "dsn_detect_decode": (c_int, [_FLOATPP, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_float), POINTER(c_float),
                                   c_int, c_int, c_int, c_int, c_void_p, _FLOATPP, c_void_p]),
-    "dsn_filter_levels": (c_int, [_FLOATPP, POINTER(c_int), POINTER(c_int), c_int, c_int, c_int, c_int, c_float, c_int,
+    "dsn_filter_levels": (c_int, [_FLOATPP, c_int, POINTER(c_int), POINTER(c_int), c_int, c_int, c_int, c_int, c_float, c_int,
                                   POINTER(c_uint64), c_void_p, c_int64, c_void_p, c_void_p]),
-    "dsn_filter_z": (c_int, [c_void_p, c_int, c_int64, c_int, c_float, c_int, POINTER(c_uint64), c_void_p, c_int64,
+    "dsn_filter_z": (c_int, [c_void_p, c_int, c_int, c_int64, c_int, c_float, c_int, POINTER(c_uint64), c_void_p, c_int64,
                              c_void_p, c_void_p]),
-    "dsn_nms_levels": (c_int, [_FLOATPP, POINTER(c_int), POINTER(c_int), POINTER(c_float), POINTER(c_float), c_int, c_int,
+    "dsn_nms_levels": (c_int, [_FLOATPP, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_float), POINTER(c_float), c_int, c_int,
                                c_int, c_int, c_void_p, c_int64, c_void_p, c_float, c_double, c_int, c_int, c_int, c_float,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dsn_append_label_keys": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_float, POINTER(c_uint64), c_void_p, c_int64,
                                       c_void_p, c_void_p]),
-    "dsn_nms_levels_labels": (c_int, [_FLOATPP, POINTER(c_int), POINTER(c_int), POINTER(c_float), POINTER(c_float), c_int, c_int,
+    "dsn_nms_levels_labels": (c_int, [_FLOATPP, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_float), POINTER(c_float), c_int, c_int,
                                       c_int, c_int, c_void_p, c_int64, c_void_p, c_float, c_double, c_int, c_int, c_int, c_float,
                                       c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
-    "dsn_conf_cut_levels": (c_int, [_FLOATPP, POINTER(c_int), POINTER(c_int), c_int, c_int, c_int, c_int, c_float, c_int,
+    "dsn_conf_cut_levels": (c_int, [_FLOATPP, c_int, POINTER(c_int), POINTER(c_int), c_int, c_int, c_int, c_int, c_float, c_int,
                                     POINTER(c_uint64), c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "dsn_filter_levels_cut": (c_int, [_FLOATPP, POINTER(c_int), POINTER(c_int), c_int, c_int, c_int, c_int, c_float, c_int,
+    "dsn_filter_levels_cut": (c_int, [_FLOATPP, c_int, POINTER(c_int), POINTER(c_int), c_int, c_int, c_int, c_int, c_float, c_int,
                                       POINTER(c_uint64), c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
-    "dsn_detect_nms_levels": (c_int, [_FLOATPP, POINTER(c_int), POINTER(c_int), POINTER(c_float), POINTER(c_float), c_int,
+    "dsn_detect_nms_levels": (c_int, [_FLOATPP, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_float), POINTER(c_float), c_int,
                                       c_int, c_int, c_int, c_float, c_int, POINTER(c_uint64), c_double, c_int, c_int,
                                       c_int, c_float, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "dsn_detect_nms_redo_levels": (c_int, [_FLOATPP, POINTER(c_int), POINTER(c_int), POINTER(c_float), POINTER(c_float), c_int,
+    "dsn_detect_nms_redo_levels": (c_int, [_FLOATPP, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_float), POINTER(c_float), c_int,
                                            c_int, c_int, c_int, c_float, c_int, POINTER(c_uint64), c_double, c_int, c_int,
                                            c_int, c_float, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "dsn_nms_z": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int64, c_void_p, c_float, c_double, c_int, c_int,
+    "dsn_nms_z": (c_int, [c_void_p, c_int, c_int, c_int64, c_int, c_void_p, c_int64, c_void_p, c_float, c_double, c_int, c_int,
                           c_int, c_float, c_void_p, c_void_p, c_void_p]),
-    "dsn_seg_fused": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
+    "dsn_seg_fused": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
                               c_int, c_void_p, c_int, c_int, c_void_p]),
-    "dsn_seg_fullres": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+    "dsn_seg_fullres": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                 c_void_p, c_int, c_int, c_void_p]),
-    "dsn_upsample_bilinear_ac": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dsn_upsample_bilinear_ac": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dsn_box_iou": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "dsn_process_batch": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                   c_int, c_void_p, c_void_p]),

@@ -27,10 +27,11 @@ __all__ = [
 ]
 
 
-def _f32(t: torch.Tensor) -> torch.Tensor:
-    """Kernels compute in fp32, like the reference's fp32 path; fp16 / bf16 head outputs (``--half``, val.py:144,178-179)
-    are upcast on load — the results are those of the fp32 path on ``t.float()``."""
-    return t if t.dtype == torch.float32 else t.float()
+def _kernel_input(t: torch.Tensor) -> torch.Tensor:
+    """The kernels compute in fp32, like the reference's fp32 path, and load fp32 / fp16 / bf16 natively: half-precision
+    head outputs (``--half``, val.py:144,178-179) are converted as they are read — the results are those of the fp32 path
+    on ``t.float()`` without a conversion pass.  Any other floating type is upcast here."""
+    return t if t.dtype in ops.DTYPE_CODE else t.float()
 
 
 class _TensorLike:
@@ -122,7 +123,7 @@ class HeadOutputs(_TensorLike):
 
     def __init__(self, levels: Sequence[torch.Tensor], anchor_grid, stride=None, out_dtype=None):
         self._out_dtype = out_dtype if out_dtype is not None else levels[0].dtype
-        self.head = ops.Head([_f32(l) for l in levels], anchor_grid, stride)
+        self.head = ops.Head([_kernel_input(l) for l in levels], anchor_grid, stride)
         self._z = None
         self._zc = None
         self._x = None
@@ -203,12 +204,12 @@ class SegLogits(_TensorLike):
         return self.out_dtype
 
     @property
-    def low_f32(self) -> torch.Tensor:
-        return _f32(self.low)
+    def low_in(self) -> torch.Tensor:
+        return _kernel_input(self.low)
 
     def full(self) -> torch.Tensor:
         """The full-resolution fp32 logits on the GPU (bit-identical to ATen's CPU upsample of the fp32 logits)."""
-        return ops.upsample_bilinear_ac(self.low_f32, self.full_hw)
+        return ops.upsample_bilinear_ac(self.low_in, self.full_hw)
 
     def _materialise(self):
         return self.full().to(device=self.out_device, dtype=self.out_dtype)
@@ -295,7 +296,7 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
             else:
                 det, det_count, _ = ops.detect_nms_levels(head, conf_thres, iou_thres, classes, agnostic, multi_label, int(max_det))
     else:
-        z = _f32(prediction)
+        z = _kernel_input(prediction)
         if has_labels:
             z = _append_label_rows(z, labels)
         if z.shape[0] == 0:
@@ -456,9 +457,9 @@ def segoutput_to_target(output, size=None) -> torch.Tensor:
     if isinstance(output, SegLogits):
         full = output.full_hw
         msize = full if size is None else tuple(int(v) for v in size)[-2:]
-        mask, _ = ops.seg_fused(output.low_f32, full, mask_dtype=torch.float32, mask_size=msize)
+        mask, _ = ops.seg_fused(output.low_in, full, mask_dtype=torch.float32, mask_size=msize)
         return mask if output.out_device == mask.device else mask.to(output.out_device)
-    output = _f32(output)
+    output = _kernel_input(output)
     H, W = int(output.shape[2]), int(output.shape[3])
     msize = (H, W) if size is None else tuple(int(v) for v in size)[-2:]
     mask, _ = ops.seg_fullres(output, mask_dtype=torch.float32, mask_size=msize)
@@ -481,9 +482,9 @@ def seg_confusion_matrix(output, target: torch.Tensor, nclass: int, cm: Optional
     if target.device != dev or target.dtype != torch.int64:
         target = target.to(device=dev, dtype=torch.int64)
     if isinstance(output, SegLogits):
-        _, cm = ops.seg_fused(output.low_f32, output.full_hw, target=target, cm=cm, cm_rows=rows)
+        _, cm = ops.seg_fused(output.low_in, output.full_hw, target=target, cm=cm, cm_rows=rows)
     else:
-        _, cm = ops.seg_fullres(_f32(output), target=target, cm=cm, cm_rows=rows)
+        _, cm = ops.seg_fullres(_kernel_input(output), target=target, cm=cm, cm_rows=rows)
     return cm
 
 

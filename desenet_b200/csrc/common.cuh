@@ -1,5 +1,7 @@
 // Shared device helpers for the DeSeNet post-process kernels (sm_100a).
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -100,6 +102,73 @@ __device__ __forceinline__ void stg_stream_f4(float *p, float4 v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
 }
+
+// ---- element types of the raw network outputs (the `dtype` argument of the C ABI) ----------------------------------------
+// The kernels compute in fp32 whatever the network's precision: fp16 / bf16 head outputs (`--half`, scripts/val.py:144,
+// 178-179) are converted as they are loaded (exact), so the results are those of the fp32 path on the upcast values, with
+// half the input bytes and no separate conversion pass.
+//   ld1 / ld4   streaming loads of 1 / 4 consecutive elements from global memory (ld4: 4 * sizeof(T) aligned)
+//   ld1c        cached load (values that are re-read)
+//   lds4 / cvt  4 consecutive elements / one element already in hand (shared memory, registers)
+template <typename T>
+struct Elem;
+template <>
+struct Elem<float> {
+    static __device__ __forceinline__ float ld1(const float *p) { return ldg_stream_f1(p); }
+    static __device__ __forceinline__ float4 ld4(const float *p) { return ldg_stream_f4(p); }
+    static __device__ __forceinline__ float ld1c(const float *p) { return __ldg(p); }
+    static __device__ __forceinline__ float4 lds4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+    static __device__ __forceinline__ float cvt(float v) { return v; }
+};
+template <>
+struct Elem<__half> {
+    static __device__ __forceinline__ float cvt(__half v) { return __half2float(v); }
+    static __device__ __forceinline__ float4 unpack(uint2 r) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&r.x)), b = __half22float2(*reinterpret_cast<const __half2 *>(&r.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+    static __device__ __forceinline__ float ld1(const __half *p) {
+        unsigned short r;
+        asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(r) : "l"(p));
+        return __half2float(__ushort_as_half(r));
+    }
+    static __device__ __forceinline__ float4 ld4(const __half *p) {
+        uint2 r;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+        return unpack(r);
+    }
+    static __device__ __forceinline__ float ld1c(const __half *p) { return __half2float(__ldg(p)); }
+    static __device__ __forceinline__ float4 lds4(const __half *p) { return unpack(*reinterpret_cast<const uint2 *>(p)); }
+};
+template <>
+struct Elem<__nv_bfloat16> {
+    static __device__ __forceinline__ float cvt(__nv_bfloat16 v) { return __bfloat162float(v); }
+    static __device__ __forceinline__ float4 unpack(uint2 r) {          // bf16 -> fp32 is a 16-bit shift
+        return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xFFFF0000u), __uint_as_float(r.y << 16),
+                           __uint_as_float(r.y & 0xFFFF0000u));
+    }
+    static __device__ __forceinline__ float ld1(const __nv_bfloat16 *p) {
+        unsigned short r;
+        asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(r) : "l"(p));
+        return __uint_as_float((unsigned int)r << 16);
+    }
+    static __device__ __forceinline__ float4 ld4(const __nv_bfloat16 *p) {
+        uint2 r;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+        return unpack(r);
+    }
+    static __device__ __forceinline__ float ld1c(const __nv_bfloat16 *p) { return __bfloat162float(__ldg(p)); }
+    static __device__ __forceinline__ float4 lds4(const __nv_bfloat16 *p) { return unpack(*reinterpret_cast<const uint2 *>(p)); }
+};
+static inline int dtype_size(int dtype) { return dtype == DSN_F32 ? 4 : ((dtype == DSN_F16 || dtype == DSN_BF16) ? 2 : 0); }
+// runs `...` with `T` bound to the element type of `dtype`
+#define DSN_DISPATCH_DTYPE(dtype, T, ...)                                  \
+    switch (dtype) {                                                       \
+        case DSN_F32: { using T = float; __VA_ARGS__; break; }             \
+        case DSN_F16: { using T = __half; __VA_ARGS__; break; }            \
+        case DSN_BF16: { using T = __nv_bfloat16; __VA_ARGS__; break; }    \
+        default: return DSN_E_INVALID;                                     \
+    }
 
 // sigmoid as the reference computes it (torch.sigmoid, core/models/yolo.py:266): 1/(1+exp(-x)).
 // expf / IEEE division (no fast-math): within a few ulp of ATen's CPU kernel; the north-star

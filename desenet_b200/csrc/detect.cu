@@ -25,6 +25,7 @@ namespace dsn {
 // ONE contiguous run of cells*no floats of z (rows of one anchor plane are adjacent in z) and of
 // xperm.
 // =============================================================================================
+template <typename T>
 __global__ void __launch_bounds__(256) detect_decode_kernel(const HeadGeom g, float *__restrict__ z, XpermPtrs xp, int cells) {
     extern __shared__ float sm[];
     const int no = g.no;
@@ -40,12 +41,12 @@ __global__ void __launch_bounds__(256) detect_decode_kernel(const HeadGeom g, fl
     const int c0 = (t % tiles_per_plane) * cells;
     const int n = min(cells, plane - c0);
     const int b = blockIdx.y;
-    const float *src = g.raw[l] + ((size_t)(b * g.na + a) * no) * plane + c0;
+    const T *src = static_cast<const T *>(g.raw[l]) + ((size_t)(b * g.na + a) * no) * plane + c0;
     const float stride = g.stride[l], aw = g.anchor_w[l][a], ah = g.anchor_h[l][a];
     const int nx = g.nx[l];
     for (int i = threadIdx.x; i < no * n; i += blockDim.x) {
         const int o = i / n, c = i - o * n;
-        const float v = ldg_stream_f1(src + (size_t)o * plane + c);
+        const float v = Elem<T>::ld1(src + (size_t)o * plane + c);
         float r;
         const int cell = c0 + c;
         if (o == 0) r = decode_xy(v, cell % nx, stride);                     // yolo.py:268
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(256) detect_decode_kernel(const HeadGeom g, fl
 constexpr int kFilterUnroll = 4;
 constexpr int kFilterThreads = 256;
 
-template <int V>
+template <typename T, int V>
 __global__ void __launch_bounds__(kFilterThreads) filter_levels_kernel(const HeadGeom g, const FilterOut f, const float obj_logit_lo) {
     __shared__ unsigned int list_cell[kFilterThreads * kFilterUnroll * V];
     __shared__ float list_obj[kFilterThreads * kFilterUnroll * V];
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(kFilterThreads) filter_levels_kernel(const Hea
     const int tile = tg.tile;
     const int plane = tg.plane;
     const int units = plane / V;
-    const float *pbase = tg.raw + ((size_t)(b * g.na + a) * g.no) * plane;
+    const T *pbase = static_cast<const T *>(tg.raw) + ((size_t)(b * g.na + a) * g.no) * plane;
     const unsigned int prow0 = (unsigned)(tg.row_off + a * plane);
     const int u0 = tile * (kFilterThreads * kFilterUnroll) + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -104,10 +105,10 @@ __global__ void __launch_bounds__(kFilterThreads) filter_levels_kernel(const Hea
         for (int k = 0; k < V; ++k) objraw[j][k] = -INFINITY;
         if (u < units) {
             if constexpr (V == 4) {
-                const float4 t = ldg_stream_f4(pbase + (size_t)4 * plane + u * 4);
+                const float4 t = Elem<T>::ld4(pbase + (size_t)4 * plane + u * 4);
                 objraw[j][0] = t.x; objraw[j][1] = t.y; objraw[j][2] = t.z; objraw[j][3] = t.w;
             } else {
-                objraw[j][0] = ldg_stream_f1(pbase + (size_t)4 * plane + u);
+                objraw[j][0] = Elem<T>::ld1(pbase + (size_t)4 * plane + u);
             }
         }
     }
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(kFilterThreads) filter_levels_kernel(const Hea
         const bool valid = i < n;
         const unsigned int cell = valid ? list_cell[i] : 0u;
         const float obj = valid ? list_obj[i] : 0.f;
-        ClsFromPlanes cls{pbase + (size_t)5 * plane + cell, (size_t)plane};
+        ClsFromPlanes<T> cls{pbase + (size_t)5 * plane + cell, (size_t)plane};
         filter_emit(f, prow0 + cell, g.no - 5, obj, valid, cls, f.counts + b, KeySinkGlobal(f.keys + (size_t)b * f.cap, f.cap),
                     f.cut_hi ? f.cut_hi + b : nullptr);
     }
@@ -182,6 +183,7 @@ struct DenseSmem {
     unsigned long long kbuf[kDenseWarps][kDenseRound];  // keys of one round, written out together
 };
 
+template <typename T>
 __global__ void __launch_bounds__(kDenseThreads, 3) filter_dense_kernel(const HeadGeom g, const FilterOut f, const float obj_logit_lo,
                                                                                    const float obj_logit_hi) {
     extern __shared__ __align__(16) unsigned char dense_smem_raw[];
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(kDenseThreads, 3) filter_dense_kernel(const He
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cell0 = tile * kDenseCells + threadIdx.x * 4;       // plane % 4 == 0: the 4 cells are all in or all out
     const bool in = cell0 < plane;
-    const float *pbase = tg.raw + ((size_t)(b * g.na + a) * g.no) * plane + (in ? cell0 : 0);
+    const T *pbase = static_cast<const T *>(tg.raw) + ((size_t)(b * g.na + a) * g.no) * plane + (in ? cell0 : 0);
     const unsigned int row0 = (unsigned)(tg.row_off + a * plane + tile * kDenseCells + warp * 128);   // warp's first row
     const unsigned int cut = f.cut_hi ? f.cut_hi[b] : 0xFFFFFFFFu;
     const float cut_conf = __uint_as_float(~cut);                 // keys <= cut  <=>  conf >= cut_conf  (0 when no cut)
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(kDenseThreads, 3) filter_dense_kernel(const He
 #pragma unroll
     for (int ci = 0; ci < kDenseChunk; ++ci) {
         v[ci] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        if (in && ci < nc) v[ci] = ldg_stream_f4(pbase + (size_t)(5 + ci) * plane);
+        if (in && ci < nc) v[ci] = Elem<T>::ld4(pbase + (size_t)(5 + ci) * plane);
     }
     // ---- objectness: the per-cell logit bound L = -ln(obj / T' - 1) - margin, obj = 1 / (1 + exp(-o)) ------------------
     // Approximate exp / division / log are enough here: the margins (0.1 % on T, 4e-3 on L) are >1000x their error
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(kDenseThreads, 3) filter_dense_kernel(const He
     bool any = false;
     {
         float4 o4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        if (in) o4 = ldg_stream_f4(pbase + (size_t)4 * plane);
+        if (in) o4 = Elem<T>::ld4(pbase + (size_t)4 * plane);
         const float ol[4] = {o4.x, o4.y, o4.z, o4.w};
         const float inv_t = __fdividef(1.0f, t_lo);                                      // +inf when T' == 0
 #pragma unroll
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(kDenseThreads, 3) filter_dense_kernel(const He
 #pragma unroll
             for (int ci = 0; ci < kDenseChunk; ++ci) {
                 v[ci] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-                if (any && c0 + kDenseChunk + ci < nc) v[ci] = ldg_stream_f4(pbase + (size_t)(5 + c0 + kDenseChunk + ci) * plane);
+                if (any && c0 + kDenseChunk + ci < nc) v[ci] = Elem<T>::ld4(pbase + (size_t)(5 + c0 + kDenseChunk + ci) * plane);
             }
         }
         if (!work) continue;
@@ -325,7 +327,7 @@ constexpr int kTmaKbuf = 128;            // keys staged per warp
 constexpr int kTmaTileCells = 128;
 
 struct TmaLevel {
-    const float *raw;
+    const void *raw;
     int plane, row_off, tiles;           // tiles per (image, anchor) plane
 };
 
@@ -335,6 +337,12 @@ struct TileCursor {
     int b, l, a, t;
 };
 
+static inline size_t tma_warp_bytes(int nc, int esize) {
+    const size_t stage_bytes = (size_t)(nc + 1) * kTmaTileCells * esize;
+    return ((kTmaStages * stage_bytes + kTmaKbuf * 8 + (size_t)nc * kTmaTileCells * 2 + kTmaStages * 8) + 127) & ~(size_t)127;
+}
+
+template <typename T>
 __global__ void __launch_bounds__(kTmaWarps * 32) filter_dense_tma_kernel(const HeadGeom g, const FilterOut f, const float obj_logit_lo,
                                                                          const float obj_logit_hi, const int tiles_per_image,
                                                                          const long long total_tiles, const int tiles_per_warp) {
@@ -343,11 +351,11 @@ __global__ void __launch_bounds__(kTmaWarps * 32) filter_dense_tma_kernel(const 
     const int nc = g.no - 5;
     const int planes = nc + 1;                                   // objectness + classes: channels 4 .. 4 + nc of an anchor
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // per-warp shared memory: stages [kTmaStages][planes][128] floats | kbuf | idx | mbarriers
-    const size_t stage_bytes = (size_t)planes * kTmaTileCells * sizeof(float);
+    // per-warp shared memory: stages [kTmaStages][planes][128] elements | kbuf | idx | mbarriers
+    const size_t stage_bytes = (size_t)planes * kTmaTileCells * sizeof(T);
     const size_t warp_bytes = ((kTmaStages * stage_bytes + kTmaKbuf * 8 + (size_t)nc * kTmaTileCells * 2 + kTmaStages * 8) + 127) & ~(size_t)127;
     unsigned char *wbase = tma_smem + warp_bytes * warp;
-    float *stages = reinterpret_cast<float *>(wbase);
+    T *stages = reinterpret_cast<T *>(wbase);
     unsigned long long *kbuf = reinterpret_cast<unsigned long long *>(wbase + kTmaStages * stage_bytes);
     unsigned short *idx = reinterpret_cast<unsigned short *>(kbuf + kTmaKbuf);
     unsigned long long *full = reinterpret_cast<unsigned long long *>(wbase + kTmaStages * stage_bytes + kTmaKbuf * 8 + (size_t)nc * kTmaTileCells * 2);
@@ -390,11 +398,11 @@ __global__ void __launch_bounds__(kTmaWarps * 32) filter_dense_tma_kernel(const 
     auto issue = [&](const TileCursor &c, int st) {
         const TmaLevel L = lv[c.l];
         const int cell0 = c.t * kTmaTileCells;
-        const unsigned bytes = (unsigned)min(kTmaTileCells, L.plane - cell0) * 4u;
+        const unsigned bytes = (unsigned)min(kTmaTileCells, L.plane - cell0) * (unsigned)sizeof(T);
         const uint32_t bar = flt_smem_u32(&full[st]);
         if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * (unsigned)planes) : "memory");
         if (lane < planes) {
-            const float *src = L.raw + ((size_t)(c.b * g.na + c.a) * g.no + 4 + lane) * L.plane + cell0;
+            const T *src = static_cast<const T *>(L.raw) + ((size_t)(c.b * g.na + c.a) * g.no + 4 + lane) * L.plane + cell0;
             const uint32_t dst = flt_smem_u32(stages + ((size_t)st * planes + lane) * kTmaTileCells);
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                          "r"(bytes), "r"(bar)
@@ -457,14 +465,14 @@ __global__ void __launch_bounds__(kTmaWarps * 32) filter_dense_tma_kernel(const 
         const TmaLevel L = lv[cons.l];
         const int cell0 = cons.t * kTmaTileCells;
         const int nvalid = min(kTmaTileCells, L.plane - cell0);
-        const float *tile = stages + (size_t)st * planes * kTmaTileCells;          // [planes][128]: row 0 objectness, 1 + c class c
+        const T *tile = stages + (size_t)st * planes * kTmaTileCells;              // [planes][128]: row 0 objectness, 1 + c class c
         const bool in = lane * 4 < nvalid;                      // plane % 4 == 0: the 4 cells are all in or all out
         // ---- per-cell logit bound (identical to filter_dense_kernel) -------------------------------------------------
         float Lb[4];
         bool any = false;
         {
             float4 o4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-            if (in) o4 = *reinterpret_cast<const float4 *>(tile + lane * 4);
+            if (in) o4 = Elem<T>::lds4(tile + lane * 4);
             const float ol[4] = {o4.x, o4.y, o4.z, o4.w};
             const float inv_t = __fdividef(1.0f, t_lo);                                      // +inf when T' == 0
 #pragma unroll
@@ -486,7 +494,7 @@ __global__ void __launch_bounds__(kTmaWarps * 32) filter_dense_tma_kernel(const 
             for (int ci = 0; ci < kDenseChunk; ++ci) {
                 if (ci < nc) {
                     float4 v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-                    if (in) v = *reinterpret_cast<const float4 *>(tile + (size_t)(1 + ci) * kTmaTileCells + lane * 4);
+                    if (in) v = Elem<T>::lds4(tile + (size_t)(1 + ci) * kTmaTileCells + lane * 4);
                     mask |= (v.x > Lb[0] ? 1u : 0u) << (ci * 4 + 0);
                     mask |= (v.y > Lb[1] ? 1u : 0u) << (ci * 4 + 1);
                     mask |= (v.z > Lb[2] ? 1u : 0u) << (ci * 4 + 2);
@@ -516,7 +524,8 @@ __global__ void __launch_bounds__(kTmaWarps * 32) filter_dense_tma_kernel(const 
                     if (e < total) {
                         const unsigned int id = idx[e], bit = id >> 5;
                         const int ci = bit >> 2, cell = (id & 31) * 4 + (bit & 3);      // bit = class * 4 + cell of the lane
-                        const float conf = __fmul_rn(sigmoidf_ref(tile[(1 + ci) * kTmaTileCells + cell]), sigmoidf_ref(tile[cell]));   // general.py:703
+                        const float conf = __fmul_rn(sigmoidf_ref(Elem<T>::cvt(tile[(1 + ci) * kTmaTileCells + cell])),
+                                                     sigmoidf_ref(Elem<T>::cvt(tile[cell])));                             // general.py:703
                         const unsigned int ck = conf_key(conf);
                         emit = conf > f.conf_thres && ck <= cut && class_allowed(f, ci);                      // general.py:710,717
                         key = ((unsigned long long)ck << 32) | (unsigned long long)((row0 + cell) * (unsigned)nc + (unsigned)ci);
@@ -560,6 +569,7 @@ __device__ __forceinline__ unsigned int cut_bin(unsigned int key_hi, unsigned in
     return key_hi <= lo_hi ? 0u : min((key_hi - lo_hi) >> sh, (unsigned)kCutBins - 1u);
 }
 
+template <typename T>
 __global__ void __launch_bounds__(kCutThreads)
 conf_cut_kernel(const HeadGeom g, const FilterOut f, const float obj_logit_lo, unsigned int lo_hi, int sh, unsigned int want,
                 unsigned int *__restrict__ cut_hi, int *__restrict__ cut_dropped) {
@@ -583,8 +593,8 @@ conf_cut_kernel(const HeadGeom g, const FilterOut f, const float obj_logit_lo, u
         const int su = t / nsplit;
         const int cbeg = (t - su * nsplit) * 8;
         const RowGeom rg = row_geom(g, su * kCutStride * 4);          // sampled unit = 4 consecutive rows
-        const float *base = g.raw[rg.l] + ((size_t)(b * g.na + rg.a) * g.no) * rg.plane + rg.cell;
-        const float4 o4 = ldg_stream_f4(base + (size_t)4 * rg.plane);
+        const T *base = static_cast<const T *>(g.raw[rg.l]) + ((size_t)(b * g.na + rg.a) * g.no) * rg.plane + rg.cell;
+        const float4 o4 = Elem<T>::ld4(base + (size_t)4 * rg.plane);
         const float ol[4] = {o4.x, o4.y, o4.z, o4.w};
         float obj[4];
         unsigned int pass = 0;
@@ -600,7 +610,7 @@ conf_cut_kernel(const HeadGeom g, const FilterOut f, const float obj_logit_lo, u
             float4 c4[8];
 #pragma unroll
             for (int ci = 0; ci < 8; ++ci)
-                c4[ci] = c0 + ci < nc ? ldg_stream_f4(base + (size_t)(5 + c0 + ci) * rg.plane) : make_float4(0.f, 0.f, 0.f, 0.f);
+                c4[ci] = c0 + ci < nc ? Elem<T>::ld4(base + (size_t)(5 + c0 + ci) * rg.plane) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int ci = 0; ci < 8; ++ci) {
                 const int c = c0 + ci;
@@ -674,30 +684,32 @@ conf_cut_kernel(const HeadGeom g, const FilterOut f, const float obj_logit_lo, u
 }
 
 // ---- from a decoded prediction (bs, A, no): lane = one row ---------------------------------------
+template <typename T>
 struct ClsFromRow {
-    const float *r;
-    __device__ __forceinline__ float load(int c) const { return __ldg(r + 5 + c); }
+    const T *r;
+    __device__ __forceinline__ float load(int c) const { return Elem<T>::ld1c(r + 5 + c); }
     __device__ __forceinline__ float prob(float raw) const { return raw; }
 };
 
-__global__ void __launch_bounds__(256) filter_z_kernel(const float *__restrict__ z, long long A, int no, const FilterOut f) {
+template <typename T>
+__global__ void __launch_bounds__(256) filter_z_kernel(const T *__restrict__ z, long long A, int no, const FilterOut f) {
     const int b = blockIdx.y;
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = row < A;
-    const float *r = z + ((size_t)b * A + (valid ? row : 0)) * no;
-    const float obj = valid ? __ldg(r + 4) : 0.f;
-    filter_emit(f, (unsigned)row, no - 5, obj, valid, ClsFromRow{r}, f.counts + b, KeySinkGlobal(f.keys + (size_t)b * f.cap, f.cap));
+    const T *r = z + ((size_t)b * A + (valid ? row : 0)) * no;
+    const float obj = valid ? Elem<T>::ld1c(r + 4) : 0.f;
+    filter_emit(f, (unsigned)row, no - 5, obj, valid, ClsFromRow<T>{r}, f.counts + b, KeySinkGlobal(f.keys + (size_t)b * f.cap, f.cap));
 }
 
 }  // namespace dsn
 
 using namespace dsn;
 
-extern "C" __attribute__((visibility("default"))) int dsn_detect_decode(const float *const *raw, const int *ny, const int *nx, const float *stride,
-                                 const float *anchor_grid, int nl, int bs, int na, int no, float *z,
+extern "C" __attribute__((visibility("default"))) int dsn_detect_decode(const void *const *raw, int dtype, const int *ny, const int *nx,
+                                 const float *stride, const float *anchor_grid, int nl, int bs, int na, int no, float *z,
                                  float *const *xperm, void *stream) {
     HeadGeom g;
-    int rc = make_geom(g, raw, ny, nx, stride, anchor_grid, nl, bs, na, no);
+    int rc = make_geom(g, raw, dtype, ny, nx, stride, anchor_grid, nl, bs, na, no);
     if (rc) return rc;
     if (bs == 0 || (!z && !xperm)) return DSN_OK;
     const int cells = no <= 32 ? 128 : 32;
@@ -711,19 +723,21 @@ extern "C" __attribute__((visibility("default"))) int dsn_detect_decode(const fl
     g.tile_off[nl] = tiles;
     const size_t smem = (size_t)2 * cells * no * sizeof(float);
     if (smem > 200 * 1024) return DSN_E_UNSUPPORTED;
-    if (smem > 48 * 1024) {                   // large `no` (e.g. 85): opt in to more dynamic shared memory, once per device
-        static DeviceOnce once;
-        if (int rc2 = raise_dynamic_smem(once, detect_decode_kernel, 200 * 1024)) return rc2;
-    }
-    detect_decode_kernel<<<dim3(tiles, bs), 256, smem, (cudaStream_t)stream>>>(g, z, xp, cells);
+    DSN_DISPATCH_DTYPE(dtype, T, {
+        if (smem > 48 * 1024) {               // large `no` (e.g. 85): opt in to more dynamic shared memory, once per device
+            static DeviceOnce once;           // per element type
+            if (int rc2 = raise_dynamic_smem(once, detect_decode_kernel<T>, 200 * 1024)) return rc2;
+        }
+        detect_decode_kernel<T><<<dim3(tiles, bs), 256, smem, (cudaStream_t)stream>>>(g, z, xp, cells);
+    })
     DSN_CHECK_LAUNCH();
     return DSN_OK;
 }
 
-extern "C" __attribute__((visibility("default"))) int dsn_filter_levels(const float *const *raw, const int *ny, const int *nx, int nl, int bs, int na, int no,
-                                 float conf_thres, int multi_label, const uint64_t *class_mask, uint64_t *keys,
+extern "C" __attribute__((visibility("default"))) int dsn_filter_levels(const void *const *raw, int dtype, const int *ny, const int *nx, int nl, int bs,
+                                 int na, int no, float conf_thres, int multi_label, const uint64_t *class_mask, uint64_t *keys,
                                  int64_t cap, int *counts, void *stream) {
-    return dsn_filter_levels_cut(raw, ny, nx, nl, bs, na, no, conf_thres, multi_label, class_mask, keys, cap, counts, nullptr,
+    return dsn_filter_levels_cut(raw, dtype, ny, nx, nl, bs, na, no, conf_thres, multi_label, class_mask, keys, cap, counts, nullptr,
                                  stream);
 }
 
@@ -741,13 +755,13 @@ static inline void cut_geometry(float conf_thres, unsigned int &lo_hi, int &sh) 
     while ((width >> sh) >= (unsigned)kCutBins) ++sh;
 }
 
-extern "C" __attribute__((visibility("default"))) int dsn_conf_cut_levels(const float *const *raw, const int *ny, const int *nx, int nl,
+extern "C" __attribute__((visibility("default"))) int dsn_conf_cut_levels(const void *const *raw, int dtype, const int *ny, const int *nx, int nl,
                                                                           int bs, int na, int no, float conf_thres, int multi_label,
                                                                           const uint64_t *class_mask, int target,
                                                                           unsigned int *hist_ws, unsigned int *cut_hi,
                                                                           int *cut_dropped, void *stream) {
     HeadGeom g;
-    int rc = make_geom(g, raw, ny, nx, nullptr, nullptr, nl, bs, na, no);
+    int rc = make_geom(g, raw, dtype, ny, nx, nullptr, nullptr, nl, bs, na, no);
     if (rc) return rc;
     (void)hist_ws;                              // reserved (the histogram lives in shared memory)
     if (!cut_hi || !cut_dropped || target < 1 || target > (1 << 28)) return DSN_E_INVALID;
@@ -758,8 +772,8 @@ extern "C" __attribute__((visibility("default"))) int dsn_conf_cut_levels(const 
     if (rc) return rc;
     if (bs == 0) return DSN_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    for (int l = 0; l < nl; ++l)
-        if (g.plane[l] % 4 != 0 || (((uintptr_t)raw[l]) & 15) != 0) return DSN_E_UNSUPPORTED;   // caller: run without a cut
+    // the cut -> filter -> NMS -> redo chain needs planes the 4-element loads and the TMA bulk copies of the redo kernel can walk
+    if (!geom_vec4(g) || !geom_bulk(g)) return DSN_E_UNSUPPORTED;   // caller: run without a cut
     int units = 0;
     for (int l = 0; l < nl; ++l) {
         g.unit_off[l] = units;
@@ -785,26 +799,16 @@ extern "C" __attribute__((visibility("default"))) int dsn_conf_cut_levels(const 
     attr[0].val.clusterDim.z = 1;
     lc.attrs = attr;
     lc.numAttrs = 1;
-    DSN_CUDA(cudaLaunchKernelEx(&lc, conf_cut_kernel, g, f, obj_logit_lower_bound(conf_thres), lo_hi, sh,
-                                (unsigned)kCutFactor * (unsigned)target, cut_hi, cut_dropped));
+    DSN_DISPATCH_DTYPE(dtype, T, {
+        DSN_CUDA(cudaLaunchKernelEx(&lc, conf_cut_kernel<T>, g, f, obj_logit_lower_bound(conf_thres), lo_hi, sh,
+                                    (unsigned)kCutFactor * (unsigned)target, cut_hi, cut_dropped));
+    })
     return DSN_OK;
 }
 
-extern "C" __attribute__((visibility("default"))) int dsn_filter_levels_cut(const float *const *raw, const int *ny, const int *nx, int nl, int bs, int na, int no,
-                                 float conf_thres, int multi_label, const uint64_t *class_mask, uint64_t *keys,
-                                 int64_t cap, int *counts, const unsigned int *cut_hi, void *stream) {
-    HeadGeom g;
-    int rc = make_geom(g, raw, ny, nx, nullptr, nullptr, nl, bs, na, no);
-    if (rc) return rc;
-    FilterOut f;
-    rc = make_filter_out(f, conf_thres, multi_label, no - 5, class_mask, keys, cap, counts);
-    if (rc) return rc;
-    f.cut_hi = cut_hi;
-    if (bs == 0) return DSN_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    DSN_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)bs, st));
-    bool vec = true;
-    for (int l = 0; l < nl; ++l) vec = vec && (g.plane[l] % 4 == 0) && (((uintptr_t)raw[l] & 15) == 0);
+template <typename T>
+static int launch_filter(HeadGeom &g, const FilterOut &f, float conf_thres, int nl, int bs, int na, int no, cudaStream_t st) {
+    const bool vec = geom_vec4(g);
     const int V = vec ? 4 : 1;
     int ctas = 0;
     for (int l = 0; l < nl; ++l) {
@@ -814,26 +818,24 @@ extern "C" __attribute__((visibility("default"))) int dsn_filter_levels_cut(cons
     }
     g.cta_off[nl] = ctas;
     const float lo = obj_logit_lower_bound(conf_thres);
-    if (vec && f.multi_label && no - 5 <= kDenseChunk) {      // few classes: TMA-fed persistent warps
+    if (vec && f.multi_label && no - 5 <= kDenseChunk && geom_bulk(g)) {      // few classes: TMA-fed persistent warps
         const int nc = no - 5;
         int tiles_per_image = 0;
         for (int l = 0; l < nl; ++l) tiles_per_image += na * ((g.plane[l] + kTmaTileCells - 1) / kTmaTileCells);
         const long long total_tiles = (long long)bs * tiles_per_image;
-        const size_t stage_bytes = (size_t)(nc + 1) * kTmaTileCells * sizeof(float);
-        const size_t warp_bytes = ((kTmaStages * stage_bytes + kTmaKbuf * 8 + (size_t)nc * kTmaTileCells * 2 + kTmaStages * 8) + 127) & ~(size_t)127;
-        const size_t smem = warp_bytes * kTmaWarps;
-        static DeviceOnce once;
-        if (int rc2 = raise_dynamic_smem(once, filter_dense_tma_kernel, 200 * 1024)) return rc2;
+        const size_t smem = tma_warp_bytes(nc, (int)sizeof(T)) * kTmaWarps;
+        static DeviceOnce once;               // per element type
+        if (int rc2 = raise_dynamic_smem(once, filter_dense_tma_kernel<T>, 200 * 1024)) return rc2;
         int occ = 0;
-        DSN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, filter_dense_tma_kernel, kTmaWarps * 32, smem));
+        DSN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, filter_dense_tma_kernel<T>, kTmaWarps * 32, smem));
         if (occ < 1) occ = 1;
         // a warp takes a contiguous range of at least kTmaStages + 1 tiles; the grid is what the SMs hold at once
         const long long max_warps = (long long)sm_count_current_device() * occ * kTmaWarps;
         long long tpw = std::max<long long>(kTmaStages + 1, (total_tiles + max_warps - 1) / max_warps);
         const long long warps = (total_tiles + tpw - 1) / tpw;
         const long long grid = (warps + kTmaWarps - 1) / kTmaWarps;
-        filter_dense_tma_kernel<<<(unsigned)grid, kTmaWarps * 32, smem, st>>>(g, f, lo, obj_logit_upper_bound(conf_thres), tiles_per_image,
-                                                                           total_tiles, (int)tpw);
+        filter_dense_tma_kernel<T><<<(unsigned)grid, kTmaWarps * 32, smem, st>>>(g, f, lo, obj_logit_upper_bound(conf_thres), tiles_per_image,
+                                                                              total_tiles, (int)tpw);
         DSN_CHECK_LAUNCH();
         return DSN_OK;
     }
@@ -845,22 +847,40 @@ extern "C" __attribute__((visibility("default"))) int dsn_filter_levels_cut(cons
             ctas += g.ctas_per_plane[l];
         }
         g.cta_off[nl] = ctas;
-        static DeviceOnce once;
-        if (int rc2 = raise_dynamic_smem(once, filter_dense_kernel, (int)sizeof(DenseSmem))) return rc2;
-        filter_dense_kernel<<<dim3(ctas, na, bs), kDenseThreads, sizeof(DenseSmem), st>>>(g, f, lo, obj_logit_upper_bound(conf_thres));
+        static DeviceOnce once;               // per element type
+        if (int rc2 = raise_dynamic_smem(once, filter_dense_kernel<T>, (int)sizeof(DenseSmem))) return rc2;
+        filter_dense_kernel<T><<<dim3(ctas, na, bs), kDenseThreads, sizeof(DenseSmem), st>>>(g, f, lo, obj_logit_upper_bound(conf_thres));
         DSN_CHECK_LAUNCH();
         return DSN_OK;
     }
     dim3 grid(ctas, na, bs);
-    if (vec) filter_levels_kernel<4><<<grid, kFilterThreads, 0, st>>>(g, f, lo);
-    else filter_levels_kernel<1><<<grid, kFilterThreads, 0, st>>>(g, f, lo);
+    if (vec) filter_levels_kernel<T, 4><<<grid, kFilterThreads, 0, st>>>(g, f, lo);
+    else filter_levels_kernel<T, 1><<<grid, kFilterThreads, 0, st>>>(g, f, lo);
     DSN_CHECK_LAUNCH();
     return DSN_OK;
 }
 
-extern "C" __attribute__((visibility("default"))) int dsn_filter_z(const float *z, int bs, int64_t A, int no, float conf_thres, int multi_label,
+extern "C" __attribute__((visibility("default"))) int dsn_filter_levels_cut(const void *const *raw, int dtype, const int *ny, const int *nx, int nl, int bs,
+                                 int na, int no, float conf_thres, int multi_label, const uint64_t *class_mask, uint64_t *keys,
+                                 int64_t cap, int *counts, const unsigned int *cut_hi, void *stream) {
+    HeadGeom g;
+    int rc = make_geom(g, raw, dtype, ny, nx, nullptr, nullptr, nl, bs, na, no);
+    if (rc) return rc;
+    FilterOut f;
+    rc = make_filter_out(f, conf_thres, multi_label, no - 5, class_mask, keys, cap, counts);
+    if (rc) return rc;
+    f.cut_hi = cut_hi;
+    if (bs == 0) return DSN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DSN_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)bs, st));
+    DSN_DISPATCH_DTYPE(dtype, T, { return launch_filter<T>(g, f, conf_thres, nl, bs, na, no, st); })
+    return DSN_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int dsn_filter_z(const void *z, int dtype, int bs, int64_t A, int no, float conf_thres, int multi_label,
                             const uint64_t *class_mask, uint64_t *keys, int64_t cap, int *counts, void *stream) {
-    if (!z || bs < 0 || A < 1 || no < 6) return DSN_E_INVALID;
+    if (!z || bs < 0 || A < 1 || no < 6 || dtype_size(dtype) == 0) return DSN_E_INVALID;
+    if (((uintptr_t)z & (uintptr_t)(dtype_size(dtype) - 1)) != 0) return DSN_E_ALIGN;
     if (bs > 65535 || (unsigned long long)A * (unsigned long long)(no - 5) >= (1ull << 32)) return DSN_E_UNSUPPORTED;
     FilterOut f;
     int rc = make_filter_out(f, conf_thres, multi_label, no - 5, class_mask, keys, cap, counts);
@@ -869,7 +889,7 @@ extern "C" __attribute__((visibility("default"))) int dsn_filter_z(const float *
     cudaStream_t st = (cudaStream_t)stream;
     DSN_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)bs, st));
     dim3 grid((unsigned)((A + 255) / 256), bs);
-    filter_z_kernel<<<grid, 256, 0, st>>>(z, A, no, f);
+    DSN_DISPATCH_DTYPE(dtype, T, { filter_z_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(z), A, no, f); })
     DSN_CHECK_LAUNCH();
     return DSN_OK;
 }

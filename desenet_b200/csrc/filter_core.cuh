@@ -172,10 +172,11 @@ __device__ __forceinline__ void filter_emit(const FilterOut &f, unsigned int row
     }
 }
 
+template <typename T>
 struct ClsFromPlanes {
-    const float *p;        // class-0 plane of this (image, anchor), already offset to the cell
+    const T *p;            // class-0 plane of this (image, anchor), already offset to the cell
     size_t plane;
-    __device__ __forceinline__ float load(int c) const { return ldg_stream_f1(p + (size_t)c * plane); }
+    __device__ __forceinline__ float load(int c) const { return Elem<T>::ld1(p + (size_t)c * plane); }
     __device__ __forceinline__ float prob(float raw) const { return sigmoidf_ref(raw); }
 };
 

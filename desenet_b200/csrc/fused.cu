@@ -32,7 +32,7 @@ constexpr int kMaxPieces = 24;           // bulk copies per round
 
 struct FusedSmem {
     NmsSmem nms;
-    alignas(16) float stage[kStageFloats];
+    alignas(16) float stage[kStageFloats];       // kStageFloats ELEMENTS of the input type (fp16 / bf16 use half of it)
     unsigned int list[kListCap];
     alignas(8) unsigned long long mbar;
     int piece_off[kMaxPieces + 1];       // first stage float of the piece
@@ -74,20 +74,14 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
         : "memory");
 }
 
-struct ClsFromRowPlanes {
-    const float *p;        // class-0 logit of this row
-    size_t plane;
-    __device__ __forceinline__ float load(int c) const { return ldg_stream_f1(p + (size_t)c * plane); }
-    __device__ __forceinline__ float prob(float raw) const { return sigmoidf_ref(raw); }
-};
-
 // key -> global key buffer; while the image has few candidates the key is also stashed in shared memory, and the
 // four box-logit sectors of an emitting row are started towards L2 so that the NMS's box decode hits there
+template <typename T>
 struct KeySinkStash {
     unsigned long long *kout;
     long long cap;
     NmsSmem *nms;
-    const float *box0;     // box-logit 0 of this lane's row
+    const T *box0;         // box-logit 0 of this lane's row
     size_t plane;
     __device__ __forceinline__ void operator()(int slot, unsigned long long key, int /*cls*/) const {
         if (slot < cap) kout[slot] = key;
@@ -98,15 +92,17 @@ struct KeySinkStash {
 };
 
 // raw class logits were loaded by the caller together with the objectness logit (one round trip)
+template <typename T>
 struct ClsPreloaded {
     const float *raw;      // kClsChunk values of the first chunk, already in registers
-    const float *p;        // class-0 logit of this row (further chunks are loaded on demand)
+    const T *p;            // class-0 logit of this row (further chunks are loaded on demand)
     size_t plane;
-    __device__ __forceinline__ float load(int c) const { return c < kClsChunk ? raw[c] : ldg_stream_f1(p + (size_t)c * plane); }
+    __device__ __forceinline__ float load(int c) const { return c < kClsChunk ? raw[c] : Elem<T>::ld1(p + (size_t)c * plane); }
     __device__ __forceinline__ float prob(float v) const { return sigmoidf_ref(v); }
 };
 
 // class pass over the rows listed in shared memory                         general.py:687-718
+template <typename T>
 __device__ __forceinline__ void fused_flush_list(FusedSmem &s, const HeadGeom &g, const FilterOut &f, const NmsParams &p, int b) {
     const int n = (int)s.list_n;
     const int nc = g.no - 5;
@@ -117,33 +113,35 @@ __device__ __forceinline__ void fused_flush_list(FusedSmem &s, const HeadGeom &g
         const unsigned int row = valid ? s.list[i] : 0u;
         const RowGeom rg = row_geom(g, (int)row);
         const int plane = rg.plane;
-        const float *base = g.raw[rg.l] + ((size_t)(b * g.na + rg.a) * g.no) * plane + rg.cell;
+        const T *base = static_cast<const T *>(g.raw[rg.l]) + ((size_t)(b * g.na + rg.a) * g.no) * plane + rg.cell;
         // the list only holds rows whose objectness logit cleared the conservative bound, so nearly all of them pass
         // the exact test: load the objectness logit AND the first chunk of class logits in the same round trip
         float ol = -INFINITY, raw[kClsChunk];
 #pragma unroll
         for (int ci = 0; ci < kClsChunk; ++ci) raw[ci] = 0.f;
         if (valid) {
-            ol = ldg_stream_f1(base + (size_t)4 * plane);
+            ol = Elem<T>::ld1(base + (size_t)4 * plane);
 #pragma unroll
             for (int ci = 0; ci < kClsChunk; ++ci)
-                if (ci < nc) raw[ci] = ldg_stream_f1(base + (size_t)(5 + ci) * plane);
+                if (ci < nc) raw[ci] = Elem<T>::ld1(base + (size_t)(5 + ci) * plane);
         }
         const float obj = valid ? sigmoidf_ref(ol) : 0.f;                         // yolo.py:266
-        KeySinkStash sink{kout, f.cap, &s.nms, base, (size_t)plane};
-        ClsPreloaded cls{raw, base + (size_t)5 * plane, (size_t)plane};
+        KeySinkStash<T> sink{kout, f.cap, &s.nms, base, (size_t)plane};
+        ClsPreloaded<T> cls{raw, base + (size_t)5 * plane, (size_t)plane};
         filter_emit(f, row, nc, obj, valid, cls, &s.ncand, sink);
     }
 }
 
 // append the rows of stage floats [lo, hi) whose logit clears the bound to the shared list
+template <typename T>
 __device__ __forceinline__ void fused_scan_range(FusedSmem &s, int lo, int hi, float obj_logit_lo) {
+    const T *stage = reinterpret_cast<const T *>(s.stage);
     const int lane = threadIdx.x & 31;
     for (int o0 = lo; o0 < hi; o0 += kNmsThreads * 4) {
         const int o = o0 + threadIdx.x * 4;
         unsigned int pass = 0;
         if (o < hi) {
-            const float4 v = *reinterpret_cast<const float4 *>(&s.stage[o]);
+            const float4 v = Elem<T>::lds4(stage + o);
             pass = (v.x >= obj_logit_lo ? 1u : 0u) | (v.y >= obj_logit_lo ? 2u : 0u) | (v.z >= obj_logit_lo ? 4u : 0u) |
                    (v.w >= obj_logit_lo ? 8u : 0u);
         }
@@ -173,6 +171,7 @@ __device__ __forceinline__ void fused_scan_range(FusedSmem &s, int lo, int hi, f
 
 // only_flagged: the on-device redo of the confidence cut (dsn_detect_nms_redo_levels) - only images whose NMS reported
 // det_count == -2 are processed, every other CTA leaves at once.
+template <typename T>
 __global__ void __launch_bounds__(kNmsThreads) detect_fused_kernel(const HeadGeom g, const FilterOut f, const NmsParams p,
                                                                    const float obj_logit_lo, const int only_flagged) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -204,7 +203,7 @@ __global__ void __launch_bounds__(kNmsThreads) detect_fused_kernel(const HeadGeo
                 s.piece_off[np] = used;
                 s.piece_row[np] = g.row_off[l] + a * plane + c;
                 used += take;
-                bytes += (uint32_t)take * 4u;
+                bytes += (uint32_t)take * (uint32_t)sizeof(T);
                 ++np;
                 c += take;
                 if (c == plane) { c = 0; if (++a == g.na) { a = 0; ++l; } }
@@ -216,8 +215,8 @@ __global__ void __launch_bounds__(kNmsThreads) detect_fused_kernel(const HeadGeo
                 mbar_expect_tx(&s.mbar, bytes);
                 for (int i = 0; i < np; ++i) {
                     const int plane = g.plane[pl_[i]];
-                    const float *src = g.raw[pl_[i]] + ((size_t)(b * g.na + pa_[i]) * g.no + 4) * plane + pc_[i];
-                    bulk_g2s(&s.stage[s.piece_off[i]], src, (uint32_t)pn_[i] * 4u, &s.mbar);
+                    const T *src = static_cast<const T *>(g.raw[pl_[i]]) + ((size_t)(b * g.na + pa_[i]) * g.no + 4) * plane + pc_[i];
+                    bulk_g2s(reinterpret_cast<T *>(s.stage) + s.piece_off[i], src, (uint32_t)pn_[i] * (uint32_t)sizeof(T), &s.mbar);
                 }
             }
         }
@@ -230,11 +229,11 @@ __global__ void __launch_bounds__(kNmsThreads) detect_fused_kernel(const HeadGeo
         DSN_LAP(42);   // plan + TMA stage wait
         DSN_MARK(1 + (round < 3 ? round : 3));
         // ---- 1b. scan from shared memory (the list can hold a whole stage, so one pass suffices) --------------------
-        fused_scan_range(s, 0, used, obj_logit_lo);
+        fused_scan_range<T>(s, 0, used, obj_logit_lo);
         __syncthreads();
         DSN_LAP(43);   // scan
         // ---- 2. class pass over the rows of this stage ---------------------------------------------------------------
-        fused_flush_list(s, g, f, p, b);
+        fused_flush_list<T>(s, g, f, p, b);
         __syncthreads();
         DSN_LAP(44);   // class pass
         if (threadIdx.x == 0) s.list_n = 0u;
@@ -252,7 +251,8 @@ __global__ void __launch_bounds__(kNmsThreads) detect_fused_kernel(const HeadGeo
         return;
     }
     // ---- 3. NMS ------------------------------------------------------------------------------------------
-    BoxFromLevels src{g};
+    BoxFromLevels<T> src;
+    src.g = g;
     nms_image(s.nms, p, src, b, p.keys + (size_t)b * p.cap, total, /*stashed_keys=*/total <= kRankSortMax);
 }
 
@@ -261,13 +261,13 @@ __global__ void __launch_bounds__(kNmsThreads) detect_fused_kernel(const HeadGeo
 using namespace dsn;
 
 static int detect_nms_levels_impl(
-    const float *const *raw, const int *ny, const int *nx, const float *stride, const float *anchor_grid, int nl, int bs,
+    const void *const *raw, int dtype, const int *ny, const int *nx, const float *stride, const float *anchor_grid, int nl, int bs,
     int na, int no, float conf_thres, int multi_label, const uint64_t *class_mask, double iou_thres, int agnostic,
     int max_nms, int max_det, float max_wh, uint64_t *keys, int64_t cap, int *counts, float *det, int *det_count,
     void *stream, int only_flagged) {
     if (!stride || !anchor_grid) return DSN_E_INVALID;
     HeadGeom g;
-    int rc = make_geom(g, raw, ny, nx, stride, anchor_grid, nl, bs, na, no);
+    int rc = make_geom(g, raw, dtype, ny, nx, stride, anchor_grid, nl, bs, na, no);
     if (rc) return rc;
     FilterOut f;
     rc = make_filter_out(f, conf_thres, multi_label, no - 5, class_mask, keys, cap, counts);
@@ -279,39 +279,40 @@ static int detect_nms_levels_impl(
     if (bs == 0) return DSN_OK;
     cudaStream_t st = (cudaStream_t)stream;
     // the TMA bulk copies need 16 B aligned, 16 B granular planes; otherwise use the two-kernel path
-    bool vec = true;
-    for (int l = 0; l < nl; ++l) vec = vec && (g.plane[l] % 4 == 0) && (((uintptr_t)raw[l] & 15) == 0);
+    const bool vec = geom_vec4(g) && geom_bulk(g);
     if (!vec) {
         if (only_flagged) return DSN_OK;       // no confidence cut exists for such layouts: nothing can be flagged
-        rc = dsn_filter_levels(raw, ny, nx, nl, bs, na, no, conf_thres, multi_label, class_mask, keys, cap, counts, stream);
+        rc = dsn_filter_levels(raw, dtype, ny, nx, nl, bs, na, no, conf_thres, multi_label, class_mask, keys, cap, counts, stream);
         if (rc) return rc;
-        return dsn_nms_levels(raw, ny, nx, stride, anchor_grid, nl, bs, na, no, keys, cap, counts, conf_thres, iou_thres,
+        return dsn_nms_levels(raw, dtype, ny, nx, stride, anchor_grid, nl, bs, na, no, keys, cap, counts, conf_thres, iou_thres,
                               agnostic, max_nms, max_det, max_wh, nullptr, nullptr, det, det_count, stream);
     }
     const float lo = obj_logit_lower_bound(conf_thres);
     const size_t smem = sizeof(FusedSmem);
-    static DeviceOnce once;
-    rc = raise_dynamic_smem(once, detect_fused_kernel, (int)smem);
-    if (rc) return rc;
-    detect_fused_kernel<<<bs, kNmsThreads, smem, st>>>(g, f, p, lo, only_flagged);
+    DSN_DISPATCH_DTYPE(dtype, T, {
+        static DeviceOnce once;               // per element type
+        rc = raise_dynamic_smem(once, detect_fused_kernel<T>, (int)smem);
+        if (rc) return rc;
+        detect_fused_kernel<T><<<bs, kNmsThreads, smem, st>>>(g, f, p, lo, only_flagged);
+    })
     DSN_CHECK_LAUNCH();
     return DSN_OK;
 }
 
 extern "C" __attribute__((visibility("default"))) int dsn_detect_nms_levels(
-    const float *const *raw, const int *ny, const int *nx, const float *stride, const float *anchor_grid, int nl, int bs,
+    const void *const *raw, int dtype, const int *ny, const int *nx, const float *stride, const float *anchor_grid, int nl, int bs,
     int na, int no, float conf_thres, int multi_label, const uint64_t *class_mask, double iou_thres, int agnostic,
     int max_nms, int max_det, float max_wh, uint64_t *keys, int64_t cap, int *counts, float *det, int *det_count,
     void *stream) {
-    return detect_nms_levels_impl(raw, ny, nx, stride, anchor_grid, nl, bs, na, no, conf_thres, multi_label, class_mask, iou_thres,
+    return detect_nms_levels_impl(raw, dtype, ny, nx, stride, anchor_grid, nl, bs, na, no, conf_thres, multi_label, class_mask, iou_thres,
                                   agnostic, max_nms, max_det, max_wh, keys, cap, counts, det, det_count, stream, 0);
 }
 
 extern "C" __attribute__((visibility("default"))) int dsn_detect_nms_redo_levels(
-    const float *const *raw, const int *ny, const int *nx, const float *stride, const float *anchor_grid, int nl, int bs,
+    const void *const *raw, int dtype, const int *ny, const int *nx, const float *stride, const float *anchor_grid, int nl, int bs,
     int na, int no, float conf_thres, int multi_label, const uint64_t *class_mask, double iou_thres, int agnostic,
     int max_nms, int max_det, float max_wh, uint64_t *keys, int64_t cap, int *counts, float *det, int *det_count,
     void *stream) {
-    return detect_nms_levels_impl(raw, ny, nx, stride, anchor_grid, nl, bs, na, no, conf_thres, multi_label, class_mask, iou_thres,
+    return detect_nms_levels_impl(raw, dtype, ny, nx, stride, anchor_grid, nl, bs, na, no, conf_thres, multi_label, class_mask, iou_thres,
                                   agnostic, max_nms, max_det, max_wh, keys, cap, counts, det, det_count, stream, 1);
 }

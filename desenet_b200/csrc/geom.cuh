@@ -5,7 +5,8 @@
 namespace dsn {
 
 struct HeadGeom {
-    const float *raw[DSN_MAX_LEVELS];   // (bs, na*no, ny, nx) per level
+    const void *raw[DSN_MAX_LEVELS];    // (bs, na*no, ny, nx) per level, elements of type `dtype` (DSN_F32 / DSN_F16 / DSN_BF16)
+    int dtype;
     int ny[DSN_MAX_LEVELS], nx[DSN_MAX_LEVELS], plane[DSN_MAX_LEVELS];
     int row_off[DSN_MAX_LEVELS + 1];    // first row of the level inside z (per image); [nl] = A
     int unit_off[DSN_MAX_LEVELS + 1];   // fused kernel: first work unit (V cells) of the level
@@ -21,17 +22,34 @@ struct XpermPtrs {
     float *p[DSN_MAX_LEVELS];
 };
 
+// planes that 4-element vector loads can walk: plane % 4 == 0 and level pointers aligned to 4 elements
+static inline bool geom_vec4(const HeadGeom &g) {
+    const uintptr_t m = (uintptr_t)(4 * dtype_size(g.dtype) - 1);
+    bool ok = true;
+    for (int l = 0; l < g.nl; ++l) ok = ok && (g.plane[l] % 4 == 0) && (((uintptr_t)g.raw[l] & m) == 0);
+    return ok;
+}
+// ... and that 1-D TMA bulk copies can walk in tiles of 128 cells: 16-byte aligned pointers, rows a multiple of 16 bytes
+static inline bool geom_bulk(const HeadGeom &g) {
+    const int per16 = 16 / dtype_size(g.dtype);
+    bool ok = true;
+    for (int l = 0; l < g.nl; ++l) ok = ok && (g.plane[l] % per16 == 0) && (((uintptr_t)g.raw[l] & 15) == 0);
+    return ok;
+}
+
 // stride / anchor_grid may be NULL for kernels that never decode boxes (the key-only filter).
-static inline int make_geom(HeadGeom &g, const float *const *raw, const int *ny, const int *nx, const float *stride,
+static inline int make_geom(HeadGeom &g, const void *const *raw, int dtype, const int *ny, const int *nx, const float *stride,
                             const float *anchor_grid, int nl, int bs, int na, int no) {
     if (!raw || !ny || !nx || nl < 1 || bs < 0 || na < 1 || no < 6) return DSN_E_INVALID;
+    const int esize = dtype_size(dtype);
+    if (esize == 0) return DSN_E_INVALID;
     if (nl > DSN_MAX_LEVELS || na > DSN_MAX_ANCHORS || bs > 65535) return DSN_E_UNSUPPORTED;
     g = HeadGeom{};
-    g.nl = nl; g.na = na; g.no = no; g.bs = bs;
+    g.nl = nl; g.na = na; g.no = no; g.bs = bs; g.dtype = dtype;
     long long rows = 0;
     for (int l = 0; l < nl; ++l) {
         if (!raw[l] || ny[l] < 1 || nx[l] < 1) return DSN_E_INVALID;
-        if (((uintptr_t)raw[l] & 3) != 0) return DSN_E_ALIGN;
+        if (((uintptr_t)raw[l] & (uintptr_t)(esize - 1)) != 0) return DSN_E_ALIGN;
         g.raw[l] = raw[l];
         g.ny[l] = ny[l]; g.nx[l] = nx[l];
         const long long plane = (long long)ny[l] * nx[l];
@@ -55,7 +73,7 @@ static inline int make_geom(HeadGeom &g, const float *const *raw, const int *ny,
 // Level of a filter CTA from blockIdx.x, with STATIC indices into the by-value kernel parameter (dynamic indexing would
 // make the compiler copy the arrays to local memory) and no integer division: the anchor is blockIdx.y.
 struct TileGeom {
-    const float *raw;
+    const void *raw;
     int plane, row_off, tile;
 };
 __device__ __forceinline__ TileGeom tile_geom(const HeadGeom &g, int x) {

@@ -76,41 +76,46 @@ static int launch_nms(const NmsParams &p, const BoxSrc &src, int bs, cudaStream_
 
 using namespace dsn;
 
-static int nms_levels_impl(const float *const *raw, const int *ny, const int *nx, const float *stride, const float *anchor_grid, int nl,
+static int nms_levels_impl(const void *const *raw, int dtype, const int *ny, const int *nx, const float *stride, const float *anchor_grid, int nl,
                            int bs, int na, int no, const uint64_t *keys, int64_t cap, const int *counts, float conf_thres,
                            double iou_thres, int agnostic, int max_nms, int max_det, float max_wh, const unsigned int *cut_hi,
                            const int *cut_dropped, const float *labels, int max_labels, float *det, int *det_count, void *stream) {
     if (!stride || !anchor_grid) return DSN_E_INVALID;
     if (max_labels < 0 || (max_labels > 0 && !labels)) return DSN_E_INVALID;
-    BoxFromLevels src;
-    int rc = make_geom(src.g, raw, ny, nx, stride, anchor_grid, nl, bs, na, no);
+    HeadGeom g;
+    int rc = make_geom(g, raw, dtype, ny, nx, stride, anchor_grid, nl, bs, na, no);
     if (rc) return rc;
-    if ((unsigned long long)(src.g.A + max_labels) * (unsigned long long)(no - 5) >= (1ull << 32)) return DSN_E_UNSUPPORTED;
-    src.extra = labels;
-    src.extra_rows = max_labels;
+    if ((unsigned long long)(g.A + max_labels) * (unsigned long long)(no - 5) >= (1ull << 32)) return DSN_E_UNSUPPORTED;
     NmsParams p;
     rc = make_nms_params(p, keys, cap, counts, bs, no - 5, conf_thres, iou_thres, agnostic, max_nms, max_det, max_wh, det, det_count);
     if (rc) return rc;
     p.cut_dropped = cut_dropped;
     p.cut_hi = cut_dropped ? cut_hi : nullptr;
-    return launch_nms(p, src, bs, (cudaStream_t)stream);
+    DSN_DISPATCH_DTYPE(dtype, T, {
+        BoxFromLevels<T> src;
+        src.g = g;
+        src.extra = labels;
+        src.extra_rows = max_labels;
+        return launch_nms(p, src, bs, (cudaStream_t)stream);
+    })
+    return DSN_OK;
 }
 
-extern "C" __attribute__((visibility("default"))) int dsn_nms_levels(const float *const *raw, const int *ny, const int *nx, const float *stride,
+extern "C" __attribute__((visibility("default"))) int dsn_nms_levels(const void *const *raw, int dtype, const int *ny, const int *nx, const float *stride,
                               const float *anchor_grid, int nl, int bs, int na, int no, const uint64_t *keys,
                               int64_t cap, const int *counts, float conf_thres, double iou_thres, int agnostic,
                               int max_nms, int max_det, float max_wh, const unsigned int *cut_hi, const int *cut_dropped,
                               float *det, int *det_count, void *stream) {
-    return nms_levels_impl(raw, ny, nx, stride, anchor_grid, nl, bs, na, no, keys, cap, counts, conf_thres, iou_thres, agnostic, max_nms,
+    return nms_levels_impl(raw, dtype, ny, nx, stride, anchor_grid, nl, bs, na, no, keys, cap, counts, conf_thres, iou_thres, agnostic, max_nms,
                            max_det, max_wh, cut_hi, cut_dropped, nullptr, 0, det, det_count, stream);
 }
 
-extern "C" __attribute__((visibility("default"))) int dsn_nms_levels_labels(const float *const *raw, const int *ny, const int *nx, const float *stride,
+extern "C" __attribute__((visibility("default"))) int dsn_nms_levels_labels(const void *const *raw, int dtype, const int *ny, const int *nx, const float *stride,
                               const float *anchor_grid, int nl, int bs, int na, int no, const uint64_t *keys,
                               int64_t cap, const int *counts, float conf_thres, double iou_thres, int agnostic,
                               int max_nms, int max_det, float max_wh, const float *labels, int max_labels, float *det,
                               int *det_count, void *stream) {
-    return nms_levels_impl(raw, ny, nx, stride, anchor_grid, nl, bs, na, no, keys, cap, counts, conf_thres, iou_thres, agnostic, max_nms,
+    return nms_levels_impl(raw, dtype, ny, nx, stride, anchor_grid, nl, bs, na, no, keys, cap, counts, conf_thres, iou_thres, agnostic, max_nms,
                            max_det, max_wh, nullptr, nullptr, labels, max_labels, det, det_count, stream);
 }
 
@@ -131,13 +136,17 @@ extern "C" __attribute__((visibility("default"))) int dsn_append_label_keys(cons
     return DSN_OK;
 }
 
-extern "C" __attribute__((visibility("default"))) int dsn_nms_z(const float *z, int bs, int64_t A, int no, const uint64_t *keys, int64_t cap,
+extern "C" __attribute__((visibility("default"))) int dsn_nms_z(const void *z, int dtype, int bs, int64_t A, int no, const uint64_t *keys, int64_t cap,
                          const int *counts, float conf_thres, double iou_thres, int agnostic, int max_nms, int max_det,
                          float max_wh, float *det, int *det_count, void *stream) {
-    if (!z || A < 1 || no < 6) return DSN_E_INVALID;
+    if (!z || A < 1 || no < 6 || dtype_size(dtype) == 0) return DSN_E_INVALID;
+    if (((uintptr_t)z & (uintptr_t)(dtype_size(dtype) - 1)) != 0) return DSN_E_ALIGN;
     NmsParams p;
     int rc = make_nms_params(p, keys, cap, counts, bs, no - 5, conf_thres, iou_thres, agnostic, max_nms, max_det, max_wh, det, det_count);
     if (rc) return rc;
-    BoxFromZ src{z, A, no};
-    return launch_nms(p, src, bs, (cudaStream_t)stream);
+    DSN_DISPATCH_DTYPE(dtype, T, {
+        BoxFromZ<T> src{static_cast<const T *>(z), A, no};
+        return launch_nms(p, src, bs, (cudaStream_t)stream);
+    })
+    return DSN_OK;
 }

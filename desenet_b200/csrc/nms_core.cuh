@@ -42,18 +42,20 @@ struct RawBox {
     int l, a, cell;        // l < 0: x, y, w, h are already pixels (decoded prediction or an a-priori label row)
 };
 
+template <typename T>
 struct BoxFromZ {
-    const float *z;
+    const T *z;
     long long A;
     int no;
     __device__ __forceinline__ RawBox fetch(int b, unsigned int row) const {
-        const float *r = z + ((size_t)b * A + row) * no;
-        return RawBox{__ldg(r), __ldg(r + 1), __ldg(r + 2), __ldg(r + 3), -1, 0, 0};
+        const T *r = z + ((size_t)b * A + row) * no;
+        return RawBox{Elem<T>::ld1c(r), Elem<T>::ld1c(r + 1), Elem<T>::ld1c(r + 2), Elem<T>::ld1c(r + 3), -1, 0, 0};
     }
     __device__ __forceinline__ float4 finish(const RawBox &q) const { return xywh2xyxy(q.x, q.y, q.w, q.h); }   // general.py:706
     __device__ __forceinline__ float4 operator()(int b, unsigned int row) const { return finish(fetch(b, row)); }
 };
 
+template <typename T>
 struct BoxFromLevels {
     HeadGeom g;
     // optional a-priori label rows appended after the A anchor rows (general.py:690-696): (bs, extra_rows, 5) [cls, x, y, w, h]
@@ -65,9 +67,9 @@ struct BoxFromLevels {
             return RawBox{__ldg(r + 1), __ldg(r + 2), __ldg(r + 3), __ldg(r + 4), -1, 0, 0};       // general.py:692
         }
         const RowGeom rg = row_geom(g, (int)row);
-        const float *base = g.raw[rg.l] + ((size_t)(b * g.na + rg.a) * g.no) * rg.plane + rg.cell;
-        return RawBox{__ldg(base), __ldg(base + rg.plane), __ldg(base + 2 * (size_t)rg.plane), __ldg(base + 3 * (size_t)rg.plane),
-                      rg.l, rg.a, rg.cell};
+        const T *base = static_cast<const T *>(g.raw[rg.l]) + ((size_t)(b * g.na + rg.a) * g.no) * rg.plane + rg.cell;
+        return RawBox{Elem<T>::ld1c(base), Elem<T>::ld1c(base + rg.plane), Elem<T>::ld1c(base + 2 * (size_t)rg.plane),
+                      Elem<T>::ld1c(base + 3 * (size_t)rg.plane), rg.l, rg.a, rg.cell};
     }
     __device__ __forceinline__ float4 finish(const RawBox &q) const {
         if (q.l < 0) return xywh2xyxy(q.x, q.y, q.w, q.h);                                           // general.py:706

@@ -13,7 +13,7 @@
 namespace dsn {
 
 struct SegParams {
-    const float *logits;
+    const void *logits;    // elements of the kernel's template type T (fp32 / fp16 / bf16)
     int bs, C, h, w, H, W;
     const long long *target;
     float *mask_f32;
@@ -143,15 +143,15 @@ struct SrcCols {
     float v[C][3];
 };
 
-template <int C>
-__device__ __forceinline__ SrcCols<C> load_src_row(const float *img, int plane, int row_off, int c0, int c1, int c2) {
+template <int C, typename T>
+__device__ __forceinline__ SrcCols<C> load_src_row(const T *img, int plane, int row_off, int c0, int c1, int c2) {
     SrcCols<C> r;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        const float *pl = img + (size_t)c * plane + row_off;
-        r.v[c][0] = __ldg(pl + c0);
-        r.v[c][1] = __ldg(pl + c1);
-        r.v[c][2] = __ldg(pl + c2);
+        const T *pl = img + (size_t)c * plane + row_off;
+        r.v[c][0] = Elem<T>::ld1c(pl + c0);
+        r.v[c][1] = Elem<T>::ld1c(pl + c1);
+        r.v[c][2] = Elem<T>::ld1c(pl + c2);
     }
     return r;
 }
@@ -164,7 +164,7 @@ __device__ __forceinline__ SrcCols<C> load_src_row(const float *img, int plane, 
 // inner loop is branch-free: two LDS for the row's (l0, l1), C x 4 FMUL+FFMA, the compares, one
 // 16 B streaming store.  Between segments T/B swap roles and the stale one is rebuilt from raw
 // values prefetched one source row ahead.
-template <int C, bool HAS_TGT, int MASK, typename W>
+template <typename TIn, int C, bool HAS_TGT, int MASK, typename W>
 __global__ void __maxnreg__(HAS_TGT ? 96 : 128) seg_fused_rows_kernel(const SegParams p, const int rows_per_cta) {
     extern __shared__ __align__(16) unsigned char seg_smem[];
     float2 *lam = reinterpret_cast<float2 *>(seg_smem);                    // [H]   (l0, l1) of output row Y
@@ -383,7 +383,7 @@ __global__ void __maxnreg__(HAS_TGT ? 96 : 128) seg_fused_rows_kernel(const SegP
             int Y = (int)(r - (long long)b * p.H);
             const int Yend = (int)min((long long)p.H, Y + (r_end - r));        // rows of image b inside this run
             r += Yend - Y;
-            const float *img = p.logits + (size_t)b * C * plane;
+            const TIn *img = static_cast<const TIn *>(p.logits) + (size_t)b * C * plane;
             int y0 = y0_of[Y];
             float T[C][4], B[C][4];
             {
@@ -472,7 +472,7 @@ __device__ __forceinline__ bool hrow_px(const XCoef<PX> &xc, const SrcCols<C> &s
     return fin;
 }
 
-template <int C, int MASK, int PX>
+template <typename TIn, int C, int MASK, int PX>
 __global__ void __launch_bounds__(512) seg_mask_rows_kernel(const SegParams p, const int rows_per_block, const int blocks_per_image,
                                                             const long long nblocks) {
     static_assert(PX == 4 || PX == 8, "a thread owns 4 or 8 pixels of a row");
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(512) seg_mask_rows_kernel(const SegParams p, c
             const int b = (int)(blk / blocks_per_image);
             int Y = (int)(blk - (long long)b * blocks_per_image) * rows_per_block;
             const int Yend = min(p.H, Y + rows_per_block);
-            const float *img = p.logits + (size_t)b * C * plane;
+            const TIn *img = static_cast<const TIn *>(p.logits) + (size_t)b * C * plane;
             int y0 = lerp_coeff(p.sy, Y, p.h).i0;
             float T[C][PX], B[C][PX];
             SrcCols<C> nxt;
@@ -569,16 +569,17 @@ __global__ void __launch_bounds__(512) seg_mask_rows_kernel(const SegParams p, c
 }
 
 // ---- general path: any C, any scale, any mask size, any cm_rows -------------------------------
-__device__ __forceinline__ int pred_bilinear(const float *img, int C, int h, int w, float sy, float sx, int Y, int X) {
+template <typename T>
+__device__ __forceinline__ int pred_bilinear(const T *img, int C, int h, int w, float sy, float sx, int Y, int X) {
     const Lerp ly = lerp_coeff(sy, Y, h);
     const Lerp lx = lerp_coeff(sx, X, w);
     const int y1 = ly.i0 + (ly.i0 < h - 1), x1 = lx.i0 + (lx.i0 < w - 1);
     float best = 0.f;
     int bi = 0;
     for (int c = 0; c < C; ++c) {
-        const float *pl = img + (size_t)c * h * w;
-        const float t = __fmaf_rn(lx.l0, __ldg(pl + ly.i0 * w + lx.i0), __fmul_rn(lx.l1, __ldg(pl + ly.i0 * w + x1)));
-        const float bt = __fmaf_rn(lx.l0, __ldg(pl + y1 * w + lx.i0), __fmul_rn(lx.l1, __ldg(pl + y1 * w + x1)));
+        const T *pl = img + (size_t)c * h * w;
+        const float t = __fmaf_rn(lx.l0, Elem<T>::ld1c(pl + ly.i0 * w + lx.i0), __fmul_rn(lx.l1, Elem<T>::ld1c(pl + ly.i0 * w + x1)));
+        const float bt = __fmaf_rn(lx.l0, Elem<T>::ld1c(pl + y1 * w + lx.i0), __fmul_rn(lx.l1, Elem<T>::ld1c(pl + y1 * w + x1)));
         const float val = __fmaf_rn(ly.l0, t, __fmul_rn(ly.l1, bt));
         if (c == 0) {
             best = val;
@@ -590,11 +591,12 @@ __device__ __forceinline__ int pred_bilinear(const float *img, int C, int h, int
     return bi;
 }
 
-__device__ __forceinline__ int pred_fullres(const float *img, int C, size_t plane, size_t off) {
-    float best = __ldg(img + off);
+template <typename T>
+__device__ __forceinline__ int pred_fullres(const T *img, int C, size_t plane, size_t off) {
+    float best = Elem<T>::ld1c(img + off);
     int bi = 0;
     for (int c = 1; c < C; ++c) {
-        const float val = __ldg(img + (size_t)c * plane + off);
+        const float val = Elem<T>::ld1c(img + (size_t)c * plane + off);
         if (argmax_better(val, best)) {
             best = val;
             bi = c;
@@ -617,14 +619,14 @@ __device__ __forceinline__ void cm_add_match(unsigned int *cm_smem, int bin, boo
     if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&cm_smem[bin], (unsigned int)__popc(peers));
 }
 
-template <bool FULLRES>
+template <typename T, bool FULLRES>
 __global__ void __launch_bounds__(256) seg_general_kernel(const SegParams p) {
     extern __shared__ unsigned int cm_dyn[];
     const int b = blockIdx.y;
     const int nb = p.cm_rows * p.C;
     const size_t plane_lo = (size_t)p.h * p.w;
     const size_t plane_hi = (size_t)p.H * p.W;
-    const float *img = p.logits + (size_t)b * p.C * (FULLRES ? plane_hi : plane_lo);
+    const T *img = static_cast<const T *>(p.logits) + (size_t)b * p.C * (FULLRES ? plane_hi : plane_lo);
     if (p.target) {
         for (int i = threadIdx.x; i < nb; i += blockDim.x) cm_dyn[i] = 0u;
         __syncthreads();
@@ -663,13 +665,13 @@ __global__ void __launch_bounds__(256) seg_general_kernel(const SegParams p) {
 // One thread = 4 consecutive pixels x kQuadsPerThread strided quads; C planes read with 16 B
 // streaming loads (each logit is read exactly once).
 constexpr int kQuadsPerThread = 8;
-template <bool HAS_TGT, bool HAS_MASK>
+template <typename T, bool HAS_TGT, bool HAS_MASK>
 __global__ void __launch_bounds__(256) seg_fullres_vec_kernel(const SegParams p) {
     __shared__ unsigned int cm_smem[DSN_MAX_CM_ROWS * 32];
     const int b = blockIdx.y;
     const size_t plane = (size_t)p.H * p.W;
     const size_t nquads = plane >> 2;
-    const float *img = p.logits + (size_t)b * p.C * plane;
+    const T *img = static_cast<const T *>(p.logits) + (size_t)b * p.C * plane;
     const int nb = p.cm_rows * p.C;
     if (HAS_TGT) {
         for (int i = threadIdx.x; i < nb; i += blockDim.x) cm_smem[i] = 0u;
@@ -683,9 +685,9 @@ __global__ void __launch_bounds__(256) seg_fullres_vec_kernel(const SegParams p)
         const bool valid = q < nquads;
         int pred[4] = {0, 0, 0, 0};
         if (valid) {
-            float4 best = ldg_stream_f4(img + 4 * q);
+            float4 best = Elem<T>::ld4(img + 4 * q);
             for (int c = 1; c < p.C; ++c) {
-                const float4 v = ldg_stream_f4(img + (size_t)c * plane + 4 * q);
+                const float4 v = Elem<T>::ld4(img + (size_t)c * plane + 4 * q);
                 if (argmax_better(v.x, best.x)) { best.x = v.x; pred[0] = c; }
                 if (argmax_better(v.y, best.y)) { best.y = v.y; pred[1] = c; }
                 if (argmax_better(v.z, best.z)) { best.z = v.z; pred[2] = c; }
@@ -723,28 +725,30 @@ __global__ void __launch_bounds__(256) seg_fullres_vec_kernel(const SegParams p)
 }
 
 // ---- plain upsample (strict drop-in for nn.Upsample, yolo.py:183) ------------------------------
-__global__ void __launch_bounds__(256) upsample_bilinear_ac_kernel(const float *__restrict__ in, long long planes, int h, int w,
+template <typename T>
+__global__ void __launch_bounds__(256) upsample_bilinear_ac_kernel(const T *__restrict__ in, long long planes, int h, int w,
                                                                    int H, int W, float sy, float sx, float *__restrict__ out) {
     const size_t total = (size_t)planes * H * W;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int X = (int)(i % W);
         const size_t t = i / W;
         const int Y = (int)(t % H);
-        const float *pl = in + (t / H) * (size_t)h * w;
+        const T *pl = in + (t / H) * (size_t)h * w;
         const Lerp ly = lerp_coeff(sy, Y, h);
         const Lerp lx = lerp_coeff(sx, X, w);
         const int y1 = ly.i0 + (ly.i0 < h - 1), x1 = lx.i0 + (lx.i0 < w - 1);
-        const float tp = __fmaf_rn(lx.l0, __ldg(pl + ly.i0 * w + lx.i0), __fmul_rn(lx.l1, __ldg(pl + ly.i0 * w + x1)));
-        const float bt = __fmaf_rn(lx.l0, __ldg(pl + y1 * w + lx.i0), __fmul_rn(lx.l1, __ldg(pl + y1 * w + x1)));
+        const float tp = __fmaf_rn(lx.l0, Elem<T>::ld1c(pl + ly.i0 * w + lx.i0), __fmul_rn(lx.l1, Elem<T>::ld1c(pl + ly.i0 * w + x1)));
+        const float bt = __fmaf_rn(lx.l0, Elem<T>::ld1c(pl + y1 * w + lx.i0), __fmul_rn(lx.l1, Elem<T>::ld1c(pl + y1 * w + x1)));
         out[i] = __fmaf_rn(ly.l0, tp, __fmul_rn(ly.l1, bt));
     }
 }
 
 static inline float ac_scale(int n_in, int n_out) { return n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.0f; }
 
-static int check_seg_args(const float *logits, int bs, int C, int H, int W, const int64_t *target, float *mask_f32,
+static int check_seg_args(const void *logits, int dtype, int bs, int C, int H, int W, const int64_t *target, float *mask_f32,
                           uint8_t *mask_u8, int mask_h, int mask_w, unsigned long long *cm, int cm_slots, int cm_rows) {
-    if (!logits || bs < 0 || C < 1 || H < 1 || W < 1) return DSN_E_INVALID;
+    if (!logits || bs < 0 || C < 1 || H < 1 || W < 1 || dtype_size(dtype) == 0) return DSN_E_INVALID;
+    if (((uintptr_t)logits & (uintptr_t)(dtype_size(dtype) - 1)) != 0) return DSN_E_ALIGN;
     if ((target != nullptr) != (cm != nullptr)) return DSN_E_INVALID;
     if (target && (cm_slots < 1 || cm_rows < 1)) return DSN_E_INVALID;
     if ((mask_f32 || mask_u8) && (mask_h < 1 || mask_w < 1)) return DSN_E_INVALID;
@@ -753,13 +757,13 @@ static int check_seg_args(const float *logits, int bs, int C, int H, int W, cons
     return DSN_OK;
 }
 
-template <bool FULLRES>
+template <typename T, bool FULLRES>
 static int launch_general(const SegParams &p, cudaStream_t st) {
     const size_t px = std::max((size_t)p.H * p.W, (size_t)p.mask_h * p.mask_w);
     int gx = (int)std::min<size_t>((px + 256 * 16 - 1) / (256 * 16), 4096);
     gx = std::max(gx, 1);
     const size_t smem = p.target ? (size_t)p.cm_rows * p.C * sizeof(unsigned int) : 0;
-    seg_general_kernel<FULLRES><<<dim3(gx, p.bs), 256, smem, st>>>(p);
+    seg_general_kernel<T, FULLRES><<<dim3(gx, p.bs), 256, smem, st>>>(p);
     DSN_CHECK_LAUNCH();
     return DSN_OK;
 }
@@ -775,20 +779,20 @@ static inline void rows_grid(const SegParams &p, int ctas_per_sm, long long &gri
 }
 
 // eval mode (target -> confusion matrix, optionally the mask as well)
-template <int C, int M, typename W>
+template <typename T, int C, int M, typename W>
 static int launch_eval_rows_w(const SegParams &p, cudaStream_t st) {
     const int G = p.W / 4;
     const int threads = std::min(512, (G + 31) / 32 * 32);
     const size_t smem = (sizeof(float2) + sizeof(int)) * (size_t)p.H + sizeof(int) * (size_t)(p.h + 1);
     static DeviceOnce once;                   // per template instantiation
-    if (int rc = raise_dynamic_smem(once, seg_fused_rows_kernel<C, true, M, W>, 200 * 1024)) return rc;
+    if (int rc = raise_dynamic_smem(once, seg_fused_rows_kernel<T, C, true, M, W>, 200 * 1024)) return rc;
     int occ = 0;
-    DSN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seg_fused_rows_kernel<C, true, M, W>, threads, smem));
+    DSN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seg_fused_rows_kernel<T, C, true, M, W>, threads, smem));
     if (occ < 1) occ = 1;
     long long grid;
     int rows_per_cta;
     rows_grid(p, occ, grid, rows_per_cta);
-    seg_fused_rows_kernel<C, true, M, W><<<(unsigned)grid, threads, smem, st>>>(p, rows_per_cta);
+    seg_fused_rows_kernel<T, C, true, M, W><<<(unsigned)grid, threads, smem, st>>>(p, rows_per_cta);
     DSN_CHECK_LAUNCH();
     return DSN_OK;
 }
@@ -797,7 +801,7 @@ static int launch_eval_rows_w(const SegParams &p, cudaStream_t st) {
 // (0: one CTA per block)
 constexpr int kMaskCtasPerSm = DSN_SEG_MASK_CTAS_PER_SM;
 constexpr int kMaskRowsPerBlock = DSN_SEG_MASK_RPB;
-template <int C, int M, int PX>
+template <typename T, int C, int M, int PX>
 static int launch_mask_rows(const SegParams &p, cudaStream_t st) {
     const int G = p.W / PX;
     const int threads = std::min(512, (G + 31) / 32 * 32);
@@ -806,44 +810,70 @@ static int launch_mask_rows(const SegParams &p, cudaStream_t st) {
     const long long nblocks = (long long)p.bs * bpi;
     long long grid = kMaskCtasPerSm > 0 ? std::min<long long>(nblocks, (long long)sm_count() * kMaskCtasPerSm) : nblocks;
     grid = std::min<long long>(grid, 0x7fffffffLL);
-    seg_mask_rows_kernel<C, M, PX><<<(unsigned)grid, threads, 0, st>>>(p, rpb, bpi, nblocks);
+    seg_mask_rows_kernel<T, C, M, PX><<<(unsigned)grid, threads, 0, st>>>(p, rpb, bpi, nblocks);
     DSN_CHECK_LAUNCH();
     return DSN_OK;
 }
-template <int C, int M>
+template <typename T, int C, int M>
 static int launch_mask(const SegParams &p, cudaStream_t st) {
+#if DSN_SEG_MASK_PX == 8
     // 8 pixels per thread when they cannot span more than two source intervals (7 * sx < 1) and the rows allow 32-byte groups
-    const bool px8 = DSN_SEG_MASK_PX == 8 && p.W % 8 == 0 && (double)(p.W - 1) > 7.0 * (double)(p.w - 1) + 1e-3 &&
+    const bool px8 = p.W % 8 == 0 && (double)(p.W - 1) > 7.0 * (double)(p.w - 1) + 1e-3 &&
                      ((M & 1) == 0 || (((uintptr_t)p.mask_f32 & 15) == 0)) && ((M & 2) == 0 || (((uintptr_t)p.mask_u8 & 3) == 0));
-    return px8 ? launch_mask_rows<C, M, 8>(p, st) : launch_mask_rows<C, M, 4>(p, st);
+    if (px8) return launch_mask_rows<T, C, M, 8>(p, st);
+#endif
+    return launch_mask_rows<T, C, M, 4>(p, st);
 }
 
-template <int C>
+template <typename T, int C>
 static int launch_tile(const SegParams &p, cudaStream_t st) {
     const bool tgt = p.target != nullptr;
     const int mk = (p.mask_f32 ? 1 : 0) | (p.mask_u8 ? 2 : 0);
     if (tgt) {
         const bool small = p.cm_rows <= 4;      // 8-bit counters of 4 rows fit one 32-bit word
         switch (mk) {
-            case 0: return small ? launch_eval_rows_w<C, 0, unsigned int>(p, st) : launch_eval_rows_w<C, 0, unsigned long long>(p, st);
-            case 1: return small ? launch_eval_rows_w<C, 1, unsigned int>(p, st) : launch_eval_rows_w<C, 1, unsigned long long>(p, st);
-            case 2: return small ? launch_eval_rows_w<C, 2, unsigned int>(p, st) : launch_eval_rows_w<C, 2, unsigned long long>(p, st);
-            default: return small ? launch_eval_rows_w<C, 3, unsigned int>(p, st) : launch_eval_rows_w<C, 3, unsigned long long>(p, st);
+            case 0: return small ? launch_eval_rows_w<T, C, 0, unsigned int>(p, st) : launch_eval_rows_w<T, C, 0, unsigned long long>(p, st);
+            case 1: return small ? launch_eval_rows_w<T, C, 1, unsigned int>(p, st) : launch_eval_rows_w<T, C, 1, unsigned long long>(p, st);
+            case 2: return small ? launch_eval_rows_w<T, C, 2, unsigned int>(p, st) : launch_eval_rows_w<T, C, 2, unsigned long long>(p, st);
+            default: return small ? launch_eval_rows_w<T, C, 3, unsigned int>(p, st) : launch_eval_rows_w<T, C, 3, unsigned long long>(p, st);
         }
     }
-    if (mk == 1) return launch_mask<C, 1>(p, st);
-    if (mk == 2) return launch_mask<C, 2>(p, st);
-    return launch_mask<C, 3>(p, st);
+    if (mk == 1) return launch_mask<T, C, 1>(p, st);
+    if (mk == 2) return launch_mask<T, C, 2>(p, st);
+    return launch_mask<T, C, 3>(p, st);
+}
+
+template <typename T>
+static int seg_fused_dispatch(const SegParams &p, bool fast, cudaStream_t st) {
+    if (!fast) return launch_general<T, false>(p, st);
+    switch (p.C) {
+        case 2: return launch_tile<T, 2>(p, st);
+        case 3: return launch_tile<T, 3>(p, st);
+        default: return launch_tile<T, 4>(p, st);
+    }
+}
+
+template <typename T>
+static int seg_fullres_dispatch(const SegParams &p, bool fast, bool has_mask, cudaStream_t st) {
+    if (!fast) return launch_general<T, true>(p, st);
+    const size_t nquads = (size_t)p.H * p.W / 4;
+    dim3 grid((unsigned)((nquads + 256 * kQuadsPerThread - 1) / (256 * kQuadsPerThread)), p.bs);
+    const bool tgt = p.target != nullptr;
+    if (tgt && has_mask) seg_fullres_vec_kernel<T, true, true><<<grid, 256, 0, st>>>(p);
+    else if (tgt) seg_fullres_vec_kernel<T, true, false><<<grid, 256, 0, st>>>(p);
+    else seg_fullres_vec_kernel<T, false, true><<<grid, 256, 0, st>>>(p);
+    DSN_CHECK_LAUNCH();
+    return DSN_OK;
 }
 
 }  // namespace dsn
 
 using namespace dsn;
 
-extern "C" __attribute__((visibility("default"))) int dsn_seg_fused(const float *logits, int bs, int C, int h, int w, int H, int W, const int64_t *target,
-                             float *mask_f32, uint8_t *mask_u8, int mask_h, int mask_w, unsigned long long *cm,
-                             int cm_slots, int cm_rows, void *stream) {
-    int rc = check_seg_args(logits, bs, C, H, W, target, mask_f32, mask_u8, mask_h, mask_w, cm, cm_slots, cm_rows);
+extern "C" __attribute__((visibility("default"))) int dsn_seg_fused(const void *logits, int dtype, int bs, int C, int h, int w, int H, int W,
+                             const int64_t *target, float *mask_f32, uint8_t *mask_u8, int mask_h, int mask_w,
+                             unsigned long long *cm, int cm_slots, int cm_rows, void *stream) {
+    int rc = check_seg_args(logits, dtype, bs, C, H, W, target, mask_f32, mask_u8, mask_h, mask_w, cm, cm_slots, cm_rows);
     if (rc) return rc;
     if (h < 1 || w < 1) return DSN_E_INVALID;
     const bool has_mask = mask_f32 || mask_u8;
@@ -860,18 +890,14 @@ extern "C" __attribute__((visibility("default"))) int dsn_seg_fused(const float 
     const bool fast = C >= 2 && C <= kMaxPackedC && (W % 4 == 0) && H >= h && H <= 4096 && (W - 1) >= 4 * (w - 1) && h * w < (1 << 24) &&
                       (!has_mask || (mask_h == H && mask_w == W)) && (!target || cm_rows <= DSN_MAX_CM_ROWS) &&
                       (((uintptr_t)mask_f32 & 15) == 0) && (((uintptr_t)mask_u8 & 3) == 0) && (((uintptr_t)target & 15) == 0);
-    if (!fast) return launch_general<false>(p, st);
-    switch (C) {
-        case 2: return launch_tile<2>(p, st);
-        case 3: return launch_tile<3>(p, st);
-        default: return launch_tile<4>(p, st);
-    }
+    DSN_DISPATCH_DTYPE(dtype, T, { return seg_fused_dispatch<T>(p, fast, st); })
+    return DSN_OK;
 }
 
-extern "C" __attribute__((visibility("default"))) int dsn_seg_fullres(const float *logits, int bs, int C, int H, int W, const int64_t *target, float *mask_f32,
-                               uint8_t *mask_u8, int mask_h, int mask_w, unsigned long long *cm, int cm_slots,
+extern "C" __attribute__((visibility("default"))) int dsn_seg_fullres(const void *logits, int dtype, int bs, int C, int H, int W, const int64_t *target,
+                               float *mask_f32, uint8_t *mask_u8, int mask_h, int mask_w, unsigned long long *cm, int cm_slots,
                                int cm_rows, void *stream) {
-    int rc = check_seg_args(logits, bs, C, H, W, target, mask_f32, mask_u8, mask_h, mask_w, cm, cm_slots, cm_rows);
+    int rc = check_seg_args(logits, dtype, bs, C, H, W, target, mask_f32, mask_u8, mask_h, mask_w, cm, cm_slots, cm_rows);
     if (rc) return rc;
     const bool has_mask = mask_f32 || mask_u8;
     if (bs == 0 || (!target && !has_mask)) return DSN_OK;
@@ -885,27 +911,24 @@ extern "C" __attribute__((visibility("default"))) int dsn_seg_fullres(const floa
     p.mx = has_mask ? (float)W / (float)mask_w : 1.f;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t plane = (size_t)H * W;
+    const uintptr_t vmask = (uintptr_t)(4 * dtype_size(dtype) - 1);        // 4-element loads
     const bool fast = (plane % 4 == 0) && (!has_mask || (mask_h == H && mask_w == W)) &&
-                      (!target || cm_rows * C <= DSN_MAX_CM_ROWS * 32) && (((uintptr_t)logits & 15) == 0) &&
+                      (!target || cm_rows * C <= DSN_MAX_CM_ROWS * 32) && (((uintptr_t)logits & vmask) == 0) &&
                       (((uintptr_t)mask_f32 & 15) == 0) && (((uintptr_t)mask_u8 & 3) == 0) && (((uintptr_t)target & 15) == 0);
-    if (!fast) return launch_general<true>(p, st);
-    const size_t nquads = plane / 4;
-    dim3 grid((unsigned)((nquads + 256 * kQuadsPerThread - 1) / (256 * kQuadsPerThread)), bs);
-    const bool tgt = target != nullptr;
-    if (tgt && has_mask) seg_fullres_vec_kernel<true, true><<<grid, 256, 0, st>>>(p);
-    else if (tgt) seg_fullres_vec_kernel<true, false><<<grid, 256, 0, st>>>(p);
-    else seg_fullres_vec_kernel<false, true><<<grid, 256, 0, st>>>(p);
-    DSN_CHECK_LAUNCH();
+    DSN_DISPATCH_DTYPE(dtype, T, { return seg_fullres_dispatch<T>(p, fast, has_mask, st); })
     return DSN_OK;
 }
 
-extern "C" __attribute__((visibility("default"))) int dsn_upsample_bilinear_ac(const float *in, int64_t planes, int h, int w, int H, int W, float *out,
-                                        void *stream) {
-    if (!in || !out || planes < 0 || h < 1 || w < 1 || H < 1 || W < 1) return DSN_E_INVALID;
+extern "C" __attribute__((visibility("default"))) int dsn_upsample_bilinear_ac(const void *in, int dtype, int64_t planes, int h, int w, int H, int W,
+                                        float *out, void *stream) {
+    if (!in || !out || planes < 0 || h < 1 || w < 1 || H < 1 || W < 1 || dtype_size(dtype) == 0) return DSN_E_INVALID;
     if (planes == 0) return DSN_OK;
     const size_t total = (size_t)planes * H * W;
     const int grid = (int)std::min<size_t>((total + 256 * 8 - 1) / (256 * 8), 148 * 32);
-    upsample_bilinear_ac_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, planes, h, w, H, W, ac_scale(h, H), ac_scale(w, W), out);
+    DSN_DISPATCH_DTYPE(dtype, T, {
+        upsample_bilinear_ac_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const T *>(in), planes, h, w, H, W, ac_scale(h, H),
+                                                                             ac_scale(w, W), out);
+    })
     DSN_CHECK_LAUNCH();
     return DSN_OK;
 }

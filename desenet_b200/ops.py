@@ -26,6 +26,24 @@ def _require_cuda(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tens
     return t if t.is_contiguous() else t.contiguous()
 
 
+# element types the kernels load natively (include/desenet_b200.h: DSN_F32 / DSN_F16 / DSN_BF16); they compute in fp32
+DTYPE_CODE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+def _require_cuda_input(t: torch.Tensor, name: str) -> torch.Tensor:
+    """A raw network output: CUDA, fp32 / fp16 / bf16 (other floating types are upcast to fp32), contiguous."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"desenet_b200: {name} must live on a CUDA device (got {t.device}); "
+                           "this package has no CPU path")
+    if t.dtype not in DTYPE_CODE:
+        if not t.is_floating_point():
+            raise TypeError(f"{name} must be a floating-point tensor, got {t.dtype}")
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
 def _stream(device) -> c_void_p:
     return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -100,7 +118,11 @@ class Head:
     def __init__(self, levels: Sequence[torch.Tensor], anchor_grid, stride=None):
         if len(levels) == 0:
             raise ValueError("no detection levels")
-        self.levels: List[torch.Tensor] = [_require_cuda(l, f"levels[{i}]") for i, l in enumerate(levels)]
+        self.levels: List[torch.Tensor] = [_require_cuda_input(l, f"levels[{i}]") for i, l in enumerate(levels)]
+        if any(l.dtype != self.levels[0].dtype for l in self.levels):
+            self.levels = [l.float() for l in self.levels]
+        self.dtype = self.levels[0].dtype
+        self.dtype_code = DTYPE_CODE[self.dtype]
         self.device = self.levels[0].device
         self.nl = len(self.levels)
         self.bs = int(self.levels[0].shape[0])
@@ -139,7 +161,7 @@ def detect_decode(head: Head, want_z: bool = True, want_x: bool = True):
         xs = [torch.empty((head.bs, head.na, ny, nx, head.no), dtype=torch.float32, device=head.device)
               for ny, nx in zip(head.ny, head.nx)] if want_x else None
         c_x = (c_void_p * head.nl)(*[x.data_ptr() for x in xs]) if xs is not None else None
-        rc = lib.dsn_detect_decode(head.c_raw, head.c_ny, head.c_nx, head.c_stride, head.c_anchor, head.nl, head.bs,
+        rc = lib.dsn_detect_decode(head.c_raw, head.dtype_code, head.c_ny, head.c_nx, head.c_stride, head.c_anchor, head.nl, head.bs,
                                    head.na, head.no, _ptr(z), c_x, _stream(head.device))
     _lib.check(rc, "dsn_detect_decode")
     return z, xs
@@ -162,7 +184,7 @@ def conf_cut_levels(head: Head, conf_thres: float, multi_label: bool, classes=No
     with torch.cuda.device(head.device):
         if cut is None:
             cut = ConfCut(head.bs, head.device)
-        rc = lib.dsn_conf_cut_levels(head.c_raw, head.c_ny, head.c_nx, head.nl, head.bs, head.na, head.no, float(conf_thres),
+        rc = lib.dsn_conf_cut_levels(head.c_raw, head.dtype_code, head.c_ny, head.c_nx, head.nl, head.bs, head.na, head.no, float(conf_thres),
                                      int(ml), class_mask(classes, head.nc), int(target), None, _ptr(cut.cut_hi),
                                      _ptr(cut.dropped), _stream(head.device))
     if rc == -2:
@@ -183,7 +205,7 @@ def filter_levels(head: Head, conf_thres: float, multi_label: bool, classes=None
             keys = torch.empty((head.bs, cap), dtype=torch.int64, device=head.device)
         if counts is None:
             counts = torch.empty((head.bs,), dtype=torch.int32, device=head.device)
-        rc = lib.dsn_filter_levels_cut(head.c_raw, head.c_ny, head.c_nx, head.nl, head.bs, head.na, head.no,
+        rc = lib.dsn_filter_levels_cut(head.c_raw, head.dtype_code, head.c_ny, head.c_nx, head.nl, head.bs, head.na, head.no,
                                        float(conf_thres), int(ml), class_mask(classes, head.nc), _ptr(keys), cap,
                                        _ptr(counts), _ptr(cut.cut_hi if cut else None), _stream(head.device))
     _lib.check(rc, "dsn_filter_levels_cut")
@@ -193,7 +215,7 @@ def filter_levels(head: Head, conf_thres: float, multi_label: bool, classes=None
 def filter_z(z: torch.Tensor, conf_thres: float, multi_label: bool, classes=None, cap: Optional[int] = None):
     """Candidate filter on a decoded prediction (bs, A, no) (general.py:668-718) -> (keys, counts)."""
     lib = _lib.load()
-    z = _require_cuda(z, "prediction")
+    z = _require_cuda_input(z, "prediction")
     bs, A, no = (int(v) for v in z.shape)
     nc = no - 5
     ml = bool(multi_label) and nc > 1
@@ -202,7 +224,7 @@ def filter_z(z: torch.Tensor, conf_thres: float, multi_label: bool, classes=None
     with torch.cuda.device(z.device):
         keys = torch.empty((bs, cap), dtype=torch.int64, device=z.device)
         counts = torch.empty((bs,), dtype=torch.int32, device=z.device)
-        rc = lib.dsn_filter_z(_ptr(z), bs, A, no, float(conf_thres), int(ml), class_mask(classes, nc), _ptr(keys), cap,
+        rc = lib.dsn_filter_z(_ptr(z), DTYPE_CODE[z.dtype], bs, A, no, float(conf_thres), int(ml), class_mask(classes, nc), _ptr(keys), cap,
                               _ptr(counts), _stream(z.device))
     _lib.check(rc, "dsn_filter_z")
     return keys, counts
@@ -247,14 +269,14 @@ def nms_levels(head: Head, keys: torch.Tensor, counts: torch.Tensor, conf_thres:
             det_count = torch.empty((head.bs,), dtype=torch.int32, device=head.device)
         if labels is not None:          # rows >= A are the label rows of ``pad_labels`` (no confidence cut on this path)
             assert cut is None
-            rc = lib.dsn_nms_levels_labels(head.c_raw, head.c_ny, head.c_nx, head.c_stride, head.c_anchor, head.nl, head.bs,
+            rc = lib.dsn_nms_levels_labels(head.c_raw, head.dtype_code, head.c_ny, head.c_nx, head.c_stride, head.c_anchor, head.nl, head.bs,
                                            head.na, head.no, _ptr(keys), int(keys.shape[1]), _ptr(counts), float(conf_thres),
                                            float(iou_thres), int(bool(agnostic)), int(max_nms), int(max_det), float(max_wh),
                                            _ptr(labels[0]), int(labels[0].shape[1]), _ptr(det), _ptr(det_count),
                                            _stream(head.device))
             _lib.check(rc, "dsn_nms_levels_labels")
             return det, det_count
-        rc = lib.dsn_nms_levels(head.c_raw, head.c_ny, head.c_nx, head.c_stride, head.c_anchor, head.nl, head.bs,
+        rc = lib.dsn_nms_levels(head.c_raw, head.dtype_code, head.c_ny, head.c_nx, head.c_stride, head.c_anchor, head.nl, head.bs,
                                 head.na, head.no, _ptr(keys), int(keys.shape[1]), _ptr(counts), float(conf_thres),
                                 float(iou_thres), int(bool(agnostic)), int(max_nms), int(max_det), float(max_wh),
                                 _ptr(cut.cut_hi if cut else None), _ptr(cut.dropped if cut else None), _ptr(det), _ptr(det_count),
@@ -280,7 +302,7 @@ def detect_nms_levels(head: Head, conf_thres: float, iou_thres: float, classes=N
             det = torch.empty((head.bs, max(max_det, 0), 6), dtype=torch.float32, device=head.device)
         if det_count is None:
             det_count = torch.empty((head.bs,), dtype=torch.int32, device=head.device)
-        rc = lib.dsn_detect_nms_levels(head.c_raw, head.c_ny, head.c_nx, head.c_stride, head.c_anchor, head.nl, head.bs,
+        rc = lib.dsn_detect_nms_levels(head.c_raw, head.dtype_code, head.c_ny, head.c_nx, head.c_stride, head.c_anchor, head.nl, head.bs,
                                        head.na, head.no, float(conf_thres), int(ml), class_mask(classes, head.nc),
                                        float(iou_thres), int(bool(agnostic)), int(max_nms), int(max_det), float(max_wh),
                                        _ptr(keys), int(keys.shape[1]), _ptr(counts), _ptr(det), _ptr(det_count),
@@ -297,7 +319,7 @@ def detect_nms_redo_levels(head: Head, conf_thres: float, iou_thres: float, clas
     lib = _lib.load()
     ml = bool(multi_label) and head.nc > 1
     with torch.cuda.device(head.device):
-        rc = lib.dsn_detect_nms_redo_levels(head.c_raw, head.c_ny, head.c_nx, head.c_stride, head.c_anchor, head.nl, head.bs,
+        rc = lib.dsn_detect_nms_redo_levels(head.c_raw, head.dtype_code, head.c_ny, head.c_nx, head.c_stride, head.c_anchor, head.nl, head.bs,
                                             head.na, head.no, float(conf_thres), int(ml), class_mask(classes, head.nc),
                                             float(iou_thres), int(bool(agnostic)), int(max_nms), int(max_det), float(max_wh),
                                             _ptr(keys), int(keys.shape[1]), _ptr(counts), _ptr(det), _ptr(det_count),
@@ -309,12 +331,12 @@ def detect_nms_redo_levels(head: Head, conf_thres: float, iou_thres: float, clas
 def nms_z(z: torch.Tensor, keys: torch.Tensor, counts: torch.Tensor, conf_thres: float, iou_thres: float,
           agnostic: bool, max_det: int, max_nms: int = MAX_NMS, max_wh: float = MAX_WH):
     lib = _lib.load()
-    z = _require_cuda(z, "prediction")
+    z = _require_cuda_input(z, "prediction")
     bs, A, no = (int(v) for v in z.shape)
     with torch.cuda.device(z.device):
         det = torch.empty((bs, max(max_det, 0), 6), dtype=torch.float32, device=z.device)
         det_count = torch.empty((bs,), dtype=torch.int32, device=z.device)
-        rc = lib.dsn_nms_z(_ptr(z), bs, A, no, _ptr(keys), int(keys.shape[1]), _ptr(counts), float(conf_thres),
+        rc = lib.dsn_nms_z(_ptr(z), DTYPE_CODE[z.dtype], bs, A, no, _ptr(keys), int(keys.shape[1]), _ptr(counts), float(conf_thres),
                            float(iou_thres), int(bool(agnostic)), int(max_nms), int(max_det), float(max_wh),
                            _ptr(det), _ptr(det_count), _stream(z.device))
     _lib.check(rc, "dsn_nms_z")
@@ -330,7 +352,7 @@ def cm_rows_for(n_channels: int, nclass: int) -> int:
 def _seg_call(fn_name: str, logits: torch.Tensor, lowres_hw, size, target, mask_dtype, mask_size, cm, cm_rows,
               mask_out=None):
     lib = _lib.load()
-    logits = _require_cuda(logits, "logits")
+    logits = _require_cuda_input(logits, "logits")
     if logits.dim() != 4:
         raise ValueError("logits must be (bs, C, h, w)")
     bs, C = int(logits.shape[0]), int(logits.shape[1])
@@ -369,10 +391,10 @@ def _seg_call(fn_name: str, logits: torch.Tensor, lowres_hw, size, target, mask_
             cm = None
         if fn_name == "dsn_seg_fused":
             h, w = lowres_hw
-            rc = lib.dsn_seg_fused(_ptr(logits), bs, C, h, w, H, W, _ptr(target), _ptr(m32), _ptr(m8), mh, mw, _ptr(cm),
+            rc = lib.dsn_seg_fused(_ptr(logits), DTYPE_CODE[logits.dtype], bs, C, h, w, H, W, _ptr(target), _ptr(m32), _ptr(m8), mh, mw, _ptr(cm),
                                    slots, int(cm_rows), _stream(dev))
         else:
-            rc = lib.dsn_seg_fullres(_ptr(logits), bs, C, H, W, _ptr(target), _ptr(m32), _ptr(m8), mh, mw, _ptr(cm),
+            rc = lib.dsn_seg_fullres(_ptr(logits), DTYPE_CODE[logits.dtype], bs, C, H, W, _ptr(target), _ptr(m32), _ptr(m8), mh, mw, _ptr(cm),
                                      slots, int(cm_rows), _stream(dev))
     _lib.check(rc, fn_name)
     return (m32 if m32 is not None else m8), cm
@@ -397,7 +419,7 @@ def seg_fullres(logits: torch.Tensor, target: Optional[torch.Tensor] = None, mas
 def upsample_bilinear_ac(x: torch.Tensor, size: Tuple[int, int]) -> torch.Tensor:
     """nn.Upsample(bilinear, align_corners=True) (yolo.py:183), bit-identical to ATen's CPU kernel."""
     lib = _lib.load()
-    x = _require_cuda(x, "input")
+    x = _require_cuda_input(x, "input")
     H, W = int(size[0]), int(size[1])
     lead = tuple(int(v) for v in x.shape[:-2])
     planes = 1
@@ -405,7 +427,7 @@ def upsample_bilinear_ac(x: torch.Tensor, size: Tuple[int, int]) -> torch.Tensor
         planes *= v
     with torch.cuda.device(x.device):
         out = torch.empty(lead + (H, W), dtype=torch.float32, device=x.device)
-        rc = lib.dsn_upsample_bilinear_ac(_ptr(x), planes, int(x.shape[-2]), int(x.shape[-1]), H, W, _ptr(out),
+        rc = lib.dsn_upsample_bilinear_ac(_ptr(x), DTYPE_CODE[x.dtype], planes, int(x.shape[-2]), int(x.shape[-1]), H, W, _ptr(out),
                                           _stream(x.device))
     _lib.check(rc, "dsn_upsample_bilinear_ac")
     return out

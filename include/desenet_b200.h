@@ -28,6 +28,12 @@ extern "C" {
 #define DSN_MAX_ANCHORS 16       /* anchors per level (reference: na = 3, yolo.py:245) */
 #define DSN_MAX_CM_ROWS 8        /* confusion-matrix rows handled by the packed-counter path */
 
+/* element type of the raw network outputs (`dtype` arguments): the kernels always compute in fp32; fp16 / bf16 inputs
+ * (the reference's --half, scripts/val.py:144,178-179) are converted as they are loaded */
+#define DSN_F32 0
+#define DSN_F16 1
+#define DSN_BF16 2
+
 /* argument-error codes (negative); positive return values are cudaError_t */
 #define DSN_OK 0
 #define DSN_E_INVALID (-1)       /* null pointer / non-positive size / out-of-range value */
@@ -45,8 +51,8 @@ int dsn_graph_launch_many(void *const *graph_execs, void *const *streams, int n)
 
 /* ------------------------------------------------------------------------------------------
  * Detection head geometry, shared by the calls below.
- *   raw[l]      device pointer, level l conv output, NCHW fp32 (bs, na*no, ny[l], nx[l]);
- *               channel = a*no + o                                  (core/models/yolo.py:258-260)
+ *   raw[l]      device pointer, level l conv output, NCHW (bs, na*no, ny[l], nx[l]), elements of type `dtype`
+ *               (DSN_F32 / DSN_F16 / DSN_BF16); channel = a*no + o  (core/models/yolo.py:258-260)
  *   stride[l]   host, pixels per cell (8,16,32)                      (yolo.py:315)
  *   anchor_grid host, nl*na*2 floats, PIXEL anchors (w,h) = the `anchor_grid` buffer (yolo.py:251)
  *   no = nc + 5; rows of the decoded prediction are ordered level-major, then anchor, gy, gx
@@ -57,7 +63,7 @@ int dsn_graph_launch_many(void *const *graph_execs, void *const *streams, int n)
  * z      (bs, A, no) fp32 or NULL:  sigmoid + grid/anchor xywh decode, levels concatenated.
  * xperm  host array of nl device pointers or NULL: xperm[l] (bs, na, ny, nx, no) = the permuted
  *        raw logits the reference also returns (yolo.py:260). */
-int dsn_detect_decode(const float *const *raw, const int *ny, const int *nx, const float *stride,
+int dsn_detect_decode(const void *const *raw, int dtype, const int *ny, const int *nx, const float *stride,
                       const float *anchor_grid, int nl, int bs, int na, int no,
                       float *z, float *const *xperm, void *stream);
 
@@ -75,7 +81,7 @@ int dsn_detect_decode(const float *const *raw, const int *ny, const int *nx, con
 /* Fused decode + filter straight from the raw head outputs: sigmoid(obj) > conf_thres,
  * conf = obj*cls, multi-label / best-class selection, class filter, warp-aggregated compaction.
  * Replaces yolo.py:259-277 + general.py:668-718 without materialising z. */
-int dsn_filter_levels(const float *const *raw, const int *ny, const int *nx, int nl, int bs, int na,
+int dsn_filter_levels(const void *const *raw, int dtype, const int *ny, const int *nx, int nl, int bs, int na,
                       int no, float conf_thres, int multi_label, const uint64_t *class_mask,
                       uint64_t *keys, int64_t cap, int *counts, void *stream);
 
@@ -94,16 +100,16 @@ int dsn_filter_levels(const float *const *raw, const int *ny, const int *nx, int
  *   target      candidates the NMS is expected to consume at most (e.g. 16*max_det), >= 1
  *   hist_ws     reserved, may be NULL (the histograms live in shared memory)
  *   cut_hi / cut_dropped   device (bs) uint32 / int32 */
-int dsn_conf_cut_levels(const float *const *raw, const int *ny, const int *nx, int nl, int bs, int na, int no,
+int dsn_conf_cut_levels(const void *const *raw, int dtype, const int *ny, const int *nx, int nl, int bs, int na, int no,
                         float conf_thres, int multi_label, const uint64_t *class_mask, int target,
                         unsigned int *hist_ws, unsigned int *cut_hi, int *cut_dropped, void *stream);
-int dsn_filter_levels_cut(const float *const *raw, const int *ny, const int *nx, int nl, int bs, int na,
+int dsn_filter_levels_cut(const void *const *raw, int dtype, const int *ny, const int *nx, int nl, int bs, int na,
                           int no, float conf_thres, int multi_label, const uint64_t *class_mask,
                           uint64_t *keys, int64_t cap, int *counts, const unsigned int *cut_hi, void *stream);
 
 /* Same filter on an already decoded prediction (bs, A, no) — the input of the reference's
  * non_max_suppression(prediction, ...) (general.py:659). */
-int dsn_filter_z(const float *z, int bs, int64_t A, int no, float conf_thres, int multi_label,
+int dsn_filter_z(const void *z, int dtype, int bs, int64_t A, int no, float conf_thres, int multi_label,
                  const uint64_t *class_mask, uint64_t *keys, int64_t cap, int *counts, void *stream);
 
 /* Per-image NMS over the candidate keys: lazy descending-score selection (histogram select +
@@ -122,7 +128,7 @@ int dsn_filter_z(const float *z, int bs, int64_t A, int no, float conf_thres, in
  *              (cut_hi bounds the key range the selection looks at; cut_dropped arms the -2 report)
  * Box source is either the raw levels (dsn_nms_levels: decode on the fly, yolo.py:266-269 +
  * general.py:523-530) or a decoded prediction (dsn_nms_z). */
-int dsn_nms_levels(const float *const *raw, const int *ny, const int *nx, const float *stride,
+int dsn_nms_levels(const void *const *raw, int dtype, const int *ny, const int *nx, const float *stride,
                    const float *anchor_grid, int nl, int bs, int na, int no,
                    const uint64_t *keys, int64_t cap, const int *counts, float conf_thres,
                    double iou_thres, int agnostic, int max_nms, int max_det, float max_wh,
@@ -138,13 +144,13 @@ int dsn_nms_levels(const float *const *raw, const int *ny, const int *nx, const 
 int dsn_append_label_keys(const float *labels, const int *label_count, int bs, int max_labels, int64_t A, int nc,
                           float conf_thres, const uint64_t *class_mask, uint64_t *keys, int64_t cap, int *counts,
                           void *stream);
-int dsn_nms_levels_labels(const float *const *raw, const int *ny, const int *nx, const float *stride,
+int dsn_nms_levels_labels(const void *const *raw, int dtype, const int *ny, const int *nx, const float *stride,
                           const float *anchor_grid, int nl, int bs, int na, int no,
                           const uint64_t *keys, int64_t cap, const int *counts, float conf_thres,
                           double iou_thres, int agnostic, int max_nms, int max_det, float max_wh,
                           const float *labels, int max_labels, float *det, int *det_count, void *stream);
 
-int dsn_nms_z(const float *z, int bs, int64_t A, int no,
+int dsn_nms_z(const void *z, int dtype, int bs, int64_t A, int no,
               const uint64_t *keys, int64_t cap, const int *counts, float conf_thres,
               double iou_thres, int agnostic, int max_nms, int max_det, float max_wh,
               float *det, int *det_count, void *stream);
@@ -153,7 +159,7 @@ int dsn_nms_z(const float *z, int bs, int64_t A, int no,
  * (objectness scan -> shared-memory row list -> class pass -> keys -> lazy NMS).  Same results as the
  * two calls; `keys` (bs, cap) and `counts` (bs) are still written (workspace + candidate counts).
  * Replaces yolo.py:259-277 + general.py:659-750 for callers that hold the raw head outputs. */
-int dsn_detect_nms_levels(const float *const *raw, const int *ny, const int *nx, const float *stride,
+int dsn_detect_nms_levels(const void *const *raw, int dtype, const int *ny, const int *nx, const float *stride,
                           const float *anchor_grid, int nl, int bs, int na, int no,
                           float conf_thres, int multi_label, const uint64_t *class_mask,
                           double iou_thres, int agnostic, int max_nms, int max_det, float max_wh,
@@ -164,7 +170,7 @@ int dsn_detect_nms_levels(const float *const *raw, const int *ny, const int *nx,
  * CTA per flagged image; every other CTA exits at once.  Enqueued right after dsn_nms_levels it makes the
  * cut -> filter -> NMS chain exact without a host round trip (no det_count == -2 ever reaches the caller), so the
  * chain can be captured in a CUDA graph.  keys / counts / det / det_count are the buffers of the preceding calls. */
-int dsn_detect_nms_redo_levels(const float *const *raw, const int *ny, const int *nx, const float *stride,
+int dsn_detect_nms_redo_levels(const void *const *raw, int dtype, const int *ny, const int *nx, const float *stride,
                                const float *anchor_grid, int nl, int bs, int na, int no,
                                float conf_thres, int multi_label, const uint64_t *class_mask,
                                double iou_thres, int agnostic, int max_nms, int max_det, float max_wh,
@@ -180,7 +186,7 @@ int dsn_detect_nms_redo_levels(const float *const *raw, const int *ny, const int
  *      + optional mask write, nearest-resized to (mask_h, mask_w) (plots.py:229)
  *      + optional confusion-matrix accumulation against an int64 target
  *        (closed form of metrics.py:350-388).
- * logits   (bs, C, h, w) fp32 LOW-RES head output (input of the final Upsample)
+ * logits   (bs, C, h, w) LOW-RES head output (input of the final Upsample), elements of type `dtype`
  * H, W     full-resolution size the reference would upsample to (8h, 8w)
  * target   (bs, H, W) int64 or NULL.  Values are wrapped to int32 as metrics.py:359,380 do,
  *          then clamped into [0, cm_rows-1] (negatives -> 0: neither labeled nor a class).
@@ -189,19 +195,19 @@ int dsn_detect_nms_redo_levels(const float *const *raw, const int *ny, const int
  *          image b adds into slot b % cm_slots; the confusion matrix is the sum over slots.
  *          cm[r][p] = #pixels with clamped target r and predicted class p.
  */
-int dsn_seg_fused(const float *logits, int bs, int C, int h, int w, int H, int W,
+int dsn_seg_fused(const void *logits, int dtype, int bs, int C, int h, int w, int H, int W,
                   const int64_t *target, float *mask_f32, uint8_t *mask_u8, int mask_h, int mask_w,
                   unsigned long long *cm, int cm_slots, int cm_rows, void *stream);
 
 /* Same outputs from FULL-RES logits (bs, C, H, W) — the tensor the reference's
  * segoutput_to_target / batch_pix_accuracy / batch_intersection_union receive. */
-int dsn_seg_fullres(const float *logits, int bs, int C, int H, int W,
+int dsn_seg_fullres(const void *logits, int dtype, int bs, int C, int H, int W,
                     const int64_t *target, float *mask_f32, uint8_t *mask_u8, int mask_h, int mask_w,
                     unsigned long long *cm, int cm_slots, int cm_rows, void *stream);
 
 /* nn.Upsample(bilinear, align_corners=True) alone (core/models/yolo.py:183): (planes,h,w) ->
  * (planes,H,W), bit-identical to ATen's CPU kernel (fma(l0,a,l1*b) lerps, horizontal first). */
-int dsn_upsample_bilinear_ac(const float *in, int64_t planes, int h, int w, int H, int W,
+int dsn_upsample_bilinear_ac(const void *in, int dtype, int64_t planes, int h, int w, int H, int W,
                              float *out, void *stream);
 
 /* ------------------------------------------------------------------------------------------

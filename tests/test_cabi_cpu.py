@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/desenet_b200.h but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in desenet_b200/_lib.py"
     assert set(_lib.SIGNATURES) == set(names)
-    assert lib.dsn_version() == 100
+    assert lib.dsn_version() == 200
     assert lib.dsn_error_string(0) == b"ok"
     assert b"invalid" in lib.dsn_error_string(-1)
 
@@ -38,10 +38,12 @@ def test_library_exports_every_declared_symbol():
 def test_argument_errors_do_not_need_a_gpu():
     lib = _lib.load()
     null = ctypes.c_void_p(0)
-    assert lib.dsn_seg_fused(null, 1, 2, 8, 8, 64, 64, null, null, null, 64, 64, null, 0, 4, null) == -1
-    assert lib.dsn_upsample_bilinear_ac(null, 1, 8, 8, 64, 64, null, null) == -1
-    assert lib.dsn_filter_z(null, 1, 10, 11, 0.25, 0, None, null, 10, null, null) == -1
-    assert lib.dsn_nms_z(null, 1, 10, 11, null, 10, null, 0.25, 0.45, 0, 30000, 300, 4096.0, null, null, null) == -1
+    assert lib.dsn_seg_fused(null, 0, 1, 2, 8, 8, 64, 64, null, null, null, 64, 64, null, 0, 4, null) == -1
+    assert lib.dsn_upsample_bilinear_ac(null, 0, 1, 8, 8, 64, 64, null, null) == -1
+    assert lib.dsn_filter_z(null, 0, 1, 10, 11, 0.25, 0, None, null, 10, null, null) == -1
+    assert lib.dsn_nms_z(null, 0, 1, 10, 11, null, 10, null, 0.25, 0.45, 0, 30000, 300, 4096.0, null, null, null) == -1
+    buf = (ctypes.c_float * 64)()
+    assert lib.dsn_upsample_bilinear_ac(buf, 7, 1, 2, 2, 4, 4, buf, null) == -1            # unknown dtype code
 
 
 def test_no_cpu_fallback():

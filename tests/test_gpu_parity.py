@@ -504,3 +504,49 @@ def test_nms_fused_path_with_apriori_labels(dsn):
         want = port.non_max_suppression(z, labels=labels, nms_impl="c", **kw)
         assert_dets_equal(got, [w.numpy() for w in want], str(kw))
         assert (got[0][:, 4] == 1.0).sum() >= 1
+
+
+# ------------------------------------------------------------------------------------------------
+# native fp16 / bf16 inputs (the reference's --half, scripts/val.py:144,178-179): converted as they are loaded, so every
+# result must be BIT-IDENTICAL to the fp32 path on the upcast tensors
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("S,nc,bs", [(640, 6, 3), (160, 6, 2), (96, 6, 2), (64, 80, 2), (320, 80, 2)])
+def test_half_precision_head_outputs_equal_upcast(dsn, dtype, S, nc, bs):
+    levels, _, _ = port.synth_head_outputs(bs, S, nc, seed=S + nc, with_target=False)
+    lo = [l.cuda().to(dtype) for l in levels]
+    up = [l.float() for l in lo]
+    h_lo = dsn.HeadOutputs(lo, port.DEFAULT_ANCHORS, port.DEFAULT_STRIDES)
+    h_up = dsn.HeadOutputs(up, port.DEFAULT_ANCHORS, port.DEFAULT_STRIDES)
+    assert h_lo.head.dtype == dtype and h_lo.dtype == dtype
+    assert torch.equal(h_lo.z, h_up.z) and all(torch.equal(a, b) for a, b in zip(h_lo.x, h_up.x))
+    for kw in (dict(conf_thres=0.25, iou_thres=0.45, max_det=1000), dict(conf_thres=0.001, iou_thres=0.6, multi_label=True, max_det=300),
+               dict(conf_thres=0.05, iou_thres=0.5, classes=[0, 2], agnostic=True)):
+        a = dsn.non_max_suppression(h_lo, **kw)
+        b = dsn.non_max_suppression(h_up, **kw)
+        assert_dets_equal(a, [o.cpu().numpy() for o in b], f"{dtype} {kw}")
+        # decoded prediction in the network's precision, as the reference hands it to non_max_suppression under --half
+        zl = h_up.z.to(dtype)
+        c = dsn.non_max_suppression(zl, **kw)
+        d = dsn.non_max_suppression(zl.float(), **kw)
+        assert_dets_equal(c, [o.cpu().numpy() for o in d], f"strict {dtype} {kw}")
+    assert sum(o.shape[0] for o in b) > 0
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_half_precision_seg_logits_equal_upcast(dsn, dtype):
+    g = torch.Generator().manual_seed(31)
+    for C, h, w, H, W in [(2, 80, 80, 640, 640), (3, 20, 24, 160, 192), (4, 9, 13, 72, 104), (2, 7, 5, 33, 41), (12, 8, 8, 64, 64)]:
+        low = torch.randn(2, C, h, w, generator=g).cuda().to(dtype)
+        tgt = torch.randint(-1, C + 2, (2, H, W), generator=g, dtype=torch.int64).cuda()
+        a, b = dsn.SegLogits(low, size=(H, W)), dsn.SegLogits(low.float(), size=(H, W))
+        assert torch.equal(a.full(), b.full())
+        for size in (None, (H // 2 + 1, W + 3)):
+            assert torch.equal(dsn.segoutput_to_target(a, size), dsn.segoutput_to_target(b, size))
+        assert torch.equal(dsn.seg_confusion_matrix(a, tgt, max(C, 2)).sum(0), dsn.seg_confusion_matrix(b, tgt, max(C, 2)).sum(0))
+        full = b.full()
+        fl = full.to(dtype)
+        assert torch.equal(dsn.segoutput_to_target(fl), dsn.segoutput_to_target(fl.float()))
+        assert torch.equal(dsn.seg_confusion_matrix(fl, tgt, max(C, 2)).sum(0), dsn.seg_confusion_matrix(fl.float(), tgt, max(C, 2)).sum(0))
+        fo = full[:, :, :H - 1, :W - 1].contiguous().to(dtype)          # odd size: general full-res path
+        assert torch.equal(dsn.segoutput_to_target(fo), dsn.segoutput_to_target(fo.float()))
