@@ -433,6 +433,25 @@ def upsample_bilinear_ac(x: torch.Tensor, size: Tuple[int, int]) -> torch.Tensor
     return out
 
 
+def seg_head_conv1x1(features: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """The seg head's last conv, nn.Conv2d(c_hid, n_segcls, 1) + bias (yolo.py:182): (bs, K, h, w) features in the network's
+    precision -> (bs, C, h, w) fp32 low-res logits (what ``seg_fused`` reads)."""
+    lib = _lib.load()
+    features = _require_cuda_input(features, "features")
+    bs, K, h, w = (int(v) for v in features.shape)
+    wt = weight.detach().reshape(int(weight.shape[0]), -1).to(device=features.device, dtype=torch.float32).contiguous()
+    C = int(wt.shape[0])
+    if int(wt.shape[1]) != K:
+        raise ValueError(f"weight must be ({C}, {K}[, 1, 1]), got {tuple(weight.shape)}")
+    bt = bias.detach().to(device=features.device, dtype=torch.float32).contiguous() if bias is not None else None
+    with torch.cuda.device(features.device):
+        out = torch.empty((bs, C, h, w), dtype=torch.float32, device=features.device)
+        rc = lib.dsn_seg_head_conv1x1(_ptr(features), DTYPE_CODE[features.dtype], _ptr(wt), _ptr(bt), bs, K, C, h, w, _ptr(out),
+                                      _stream(features.device))
+    _lib.check(rc, "dsn_seg_head_conv1x1")
+    return out
+
+
 def letterbox_params(img1_shape, img0_shape, ratio_pad=None):
     """(pad_x, pad_y, gain, w0, h0) exactly as scale_coords derives them in Python (general.py:600-605)."""
     if ratio_pad is None:

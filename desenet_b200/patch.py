@@ -148,6 +148,7 @@ class DeferredUpsample(nn.Module):
         self.original = original
         self.fused = fused
         self.training = original.training      # a module built after model.eval() would otherwise start in training mode
+        self.out_dtype_of = None               # head_convs: a parameter whose dtype the strict mode's logits take
         sf = original.scale_factor
         self.scale = int(sf if not isinstance(sf, (tuple, list)) else sf[0])
 
@@ -156,7 +157,30 @@ class DeferredUpsample(nn.Module):
             return self.original(x)
         if self.fused:
             return api.SegLogits(x, scale_factor=self.scale)
-        return api.SegLogits(x, scale_factor=self.scale).full().to(x.dtype)
+        return api.SegLogits(x, scale_factor=self.scale).full().to(x.dtype if self.out_dtype_of is None else self.out_dtype_of.dtype)
+
+
+class FusedHeadConv(nn.Module):
+    """Opt-in replacement (``install(..., head_convs=True)``) for the seg head's last ``nn.Conv2d(c_hid, n_segcls, 1)``
+    (core/models/yolo.py:182): eval + CUDA -> the streaming 1x1 kernel, which reads the features in the network's
+    precision and hands fp32 low-res logits to the deferred Upsample; anything else -> the original module.  SURVEY.md
+    §8f rank 4 — it changes the boundary: the logits are no longer cuDNN's (summation order; under ``--half`` no fp16
+    rounding), so parity with the reference's conv is a tolerance."""
+
+    def __init__(self, original: nn.Conv2d):
+        super().__init__()
+        self.original = original
+        self.training = original.training
+
+    @staticmethod
+    def eligible(m) -> bool:
+        return (isinstance(m, nn.Conv2d) and tuple(m.kernel_size) == (1, 1) and tuple(m.stride) == (1, 1) and tuple(m.padding) == (0, 0)
+                and tuple(m.dilation) == (1, 1) and m.groups == 1 and m.out_channels <= 4 and m.padding_mode == "zeros")
+
+    def forward(self, x):
+        if self.training or not x.is_cuda:
+            return self.original(x)
+        return ops.seg_head_conv1x1(x, self.original.weight, self.original.bias)
 
 
 def _detect_forward_factory(original_forward, fused: bool):
@@ -228,11 +252,14 @@ def _find_originals(modules):
     return orig
 
 
-def install(model: Optional[nn.Module] = None, fused: bool = True, modules: Optional[Iterable[str]] = None) -> Installed:
+def install(model: Optional[nn.Module] = None, fused: bool = True, modules: Optional[Iterable[str]] = None,
+            head_convs: bool = False) -> Installed:
     """Patch every already-imported module that holds one of the reference's hot-path callables (wherever it was
     imported by name — including ``__main__`` when scripts/detect.py or scripts/val.py is the entry script); with
     ``model`` also defer the Detect decode and the seg head's final Upsample of that model instance.
-    ``modules``: restrict the patch to these module names (their current attributes are taken as the originals)."""
+    ``modules``: restrict the patch to these module names (their current attributes are taken as the originals).
+    ``head_convs`` (opt-in, needs ``model``): also run the seg head's last 1x1 convolution in the streaming kernel
+    (``FusedHeadConv``)."""
     h = Installed()
     modules = list(modules) if modules is not None else None
     orig = _find_originals(modules)
@@ -265,6 +292,10 @@ def install(model: Optional[nn.Module] = None, fused: bool = True, modules: Opti
                         idx = len(seq) - 1
                         h._undo.append((_SeqSlot(seq, idx), "module", seq[idx]))
                         seq[idx] = DeferredUpsample(seq[idx], fused)
+                        if head_convs and FusedHeadConv.eligible(seq[idx - 1]):
+                            seq[idx].out_dtype_of = seq[idx - 1].weight       # strict mode returns logits in the model's precision
+                            h._undo.append((_SeqSlot(seq, idx - 1), "module", seq[idx - 1]))
+                            seq[idx - 1] = FusedHeadConv(seq[idx - 1])
     return h
 
 

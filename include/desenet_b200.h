@@ -205,6 +205,15 @@ int dsn_seg_fullres(const void *logits, int dtype, int bs, int C, int H, int W,
                     const int64_t *target, float *mask_f32, uint8_t *mask_u8, int mask_h, int mask_w,
                     unsigned long long *cm, int cm_slots, int cm_rows, void *stream);
 
+/* Producer of the seg tail's input (first slice; opt-in because it changes the boundary): the
+ * seg head's last convolution nn.Conv2d(c_hid, n_segcls, 1) + bias (core/models/yolo.py:182) as a streaming kernel.
+ *   features (bs, K, h, w) NCHW, elements of type `dtype`;  weight (C, K) fp32, bias (C) fp32 or NULL;  C <= 4
+ *   logits   (bs, C, h, w) fp32 = the low-res logits dsn_seg_fused reads
+ * fp32 accumulation in channel order, one FMA per term (cuDNN's summation order and, under --half, its fp16 rounding of the
+ * result differ: parity with the reference's conv is a tolerance, not bit-exactness). */
+int dsn_seg_head_conv1x1(const void *features, int dtype, const float *weight, const float *bias, int bs, int K, int C,
+                         int h, int w, float *logits, void *stream);
+
 /* nn.Upsample(bilinear, align_corners=True) alone (core/models/yolo.py:183): (planes,h,w) ->
  * (planes,H,W), bit-identical to ATen's CPU kernel (fma(l0,a,l1*b) lerps, horizontal first). */
 int dsn_upsample_bilinear_ac(const void *in, int dtype, int64_t planes, int h, int w, int H, int W,

@@ -171,3 +171,40 @@ def test_deferred_outputs_behave_like_tensors(fx):
     want = F.interpolate(torch.from_numpy(fx["seg_full"]), (64, 64), mode="bilinear", align_corners=False)
     assert torch.allclose(small.cpu(), want, atol=1e-5)
     assert np.array_equal(sl.cpu().numpy(), fx["seg_full"])                             # .numpy() on the CPU stand-in
+
+
+def test_head_convs_option_on_cuda(golden):
+    """``install(model, fused=True, head_convs=True)``: the seg head's last 1x1 conv runs in the streaming kernel; the mask
+    is the oracle's argmax of the upsampled logits that kernel produced, and stays within tolerance of the reference's."""
+    import torch.nn as nn
+
+    from desenet_b200 import api, ops, patch
+    from oracle import cport, port
+    g = golden("real_desenet_s128_headconv.npz")
+    fx = golden("real_desenet_s128.npz")
+    ns, names = standin.fake_reference_modules("dsn_fake_gpu_headconv")
+    model = standin.Model(fx)
+    conv = nn.Conv2d(128, 2, 1)
+    with torch.no_grad():
+        conv.weight.copy_(torch.from_numpy(g["weight"]))
+        conv.bias.copy_(torch.from_numpy(g["bias"]))
+    model.seg.out[0] = conv                                        # the head now really ends in Conv2d(c_hid, C, 1) + Upsample
+    model.seg_low = torch.from_numpy(g["feat"]).clone()            # ... and the lookup feeds the conv's input
+    model = model.cuda().eval()
+    model.seg_low = model.seg_low.cuda()
+    img = torch.zeros(2, 3, 128, 128)
+    tgt = torch.from_numpy(fx["target"])
+    with patch.install(model=model, fused=True, modules=names, head_convs=True):
+        assert isinstance(model.seg.out[0], patch.FusedHeadConv)
+        out, seg_out, _ = standin.val_sequence(ns, model, img, tgt)
+        with torch.no_grad():
+            (_, _), s2 = model(img.cuda())
+    assert isinstance(model.seg.out[0], nn.Conv2d)
+    assert isinstance(s2, api.SegLogits) and s2.low.dtype == torch.float32
+    low = ops.seg_head_conv1x1(torch.from_numpy(g["feat"]).cuda(), conv.weight, conv.bias)
+    assert torch.equal(s2.low, low)
+    full = cport.upsample_bilinear_ac(low.cpu().numpy(), 128, 128)
+    assert np.array_equal(seg_out.cpu().numpy(), port.segoutput_to_target_np(full, (128, 128)))
+    ref_full = fx["seg_full"]
+    margin = np.abs(ref_full[:, 1] - ref_full[:, 0])
+    assert ((seg_out.cpu().numpy() == fx["mask"]) | (margin < 1e-4)).all()

@@ -550,3 +550,38 @@ def test_half_precision_seg_logits_equal_upcast(dsn, dtype):
         assert torch.equal(dsn.seg_confusion_matrix(fl, tgt, max(C, 2)).sum(0), dsn.seg_confusion_matrix(fl.float(), tgt, max(C, 2)).sum(0))
         fo = full[:, :, :H - 1, :W - 1].contiguous().to(dtype)          # odd size: general full-res path
         assert torch.equal(dsn.segoutput_to_target(fo), dsn.segoutput_to_target(fo.float()))
+
+
+# ------------------------------------------------------------------------------------------------
+# SURVEY 8f rank 4, first slice: the seg head's last 1x1 convolution as the producer of the fused seg kernels
+# ------------------------------------------------------------------------------------------------
+def test_seg_head_conv1x1_vs_reference_fixture(dsn, golden):
+    """core/models/yolo.py:182 on the real model's tensors: within 1e-5 of the reference's own conv output (summation order
+    differs), and the masks computed from it equal the reference's wherever the class margin exceeds that tolerance."""
+    from desenet_b200 import ops
+    g = golden("real_desenet_s128_headconv.npz")
+    feat, w, b = dev(g["feat"]), dev(g["weight"]), dev(g["bias"])
+    low = ops.seg_head_conv1x1(feat, w, b)
+    want = torch.from_numpy(g["seg_low"])
+    scale = (torch.from_numpy(np.abs(g["weight"])).reshape(2, -1) @ torch.from_numpy(np.abs(g["feat"])).reshape(2, 128, -1)).reshape(want.shape)
+    scale = scale + torch.from_numpy(np.abs(g["bias"])).view(1, 2, 1, 1)                    # sum of |terms| incl. the bias
+    assert ((low.cpu() - want).abs() <= REL_TOL * scale.clamp_min(1e-30)).all()          # relative to the sum of |terms|
+    exact = torch.nn.functional.conv2d(torch.from_numpy(g["feat"]).double(), torch.from_numpy(g["weight"]).double(),
+                                       torch.from_numpy(g["bias"]).double())
+    assert ((low.cpu().double() - exact).abs() <= 1e-6 * scale).all()
+    mask = dsn.segoutput_to_target(dsn.SegLogits(low)).cpu()
+    full = torch.from_numpy(golden("real_desenet_s128.npz")["seg_full"])
+    ref_mask = torch.from_numpy(golden("real_desenet_s128.npz")["mask"])
+    margin = (full[:, 1] - full[:, 0]).abs()
+    assert ((mask == ref_mask) | (margin < 1e-4)).all() and (margin >= 1e-4).float().mean() > 0.9
+    for dt in (torch.float16, torch.bfloat16):                                              # the network's precision in, fp32 out
+        assert torch.equal(ops.seg_head_conv1x1(feat.to(dt), w.to(dt), b.to(dt)), ops.seg_head_conv1x1(feat.to(dt).float(), w.to(dt).float(), b.to(dt).float()))
+    big = torch.randn(4, 128, 80, 80, device="cuda")                                       # DeSeNet-s size, unit-scale features
+    wb, bb = torch.randn(2, 128, 1, 1, device="cuda") * 0.1, torch.randn(2, device="cuda")
+    refb = torch.nn.functional.conv2d(big.double().cpu(), wb.double().cpu(), bb.double().cpu())
+    sb = torch.nn.functional.conv2d(big.abs().double().cpu(), wb.abs().double().cpu(), bb.abs().double().cpu())
+    assert ((ops.seg_head_conv1x1(big, wb, bb).cpu().double() - refb).abs() <= 1e-6 * sb).all()
+    odd = torch.randn(3, 37, 9, 7, device="cuda")                                          # plane % 4 != 0: scalar path
+    w3, b3 = torch.randn(3, 37, 1, 1, device="cuda"), torch.randn(3, device="cuda")
+    ref3 = torch.nn.functional.conv2d(odd.double().cpu(), w3.double().cpu(), b3.double().cpu())
+    assert torch.allclose(ops.seg_head_conv1x1(odd, w3, b3).cpu().double(), ref3, rtol=0, atol=1e-4)
