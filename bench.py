@@ -595,7 +595,8 @@ def run_config(args, cfg_id, rank, world, local_rank, dev, *, primary, host_info
         except Exception:
             pass
         roofline = {
-            "bound": "hbm", "kernel": {"seg": "seg_fused_rows_kernel", "filter": "filter_dense_kernel" if kw["multi_label"] else "filter_levels_kernel"}[dom],
+            "bound": "hbm", "kernel": {"seg": "seg_mask_rows_kernel" if mode == "detect" else "seg_fused_rows_kernel",
+                                       "filter": ("filter_dense_tma_kernel" if nc <= 8 else "filter_dense_kernel") if kw["multi_label"] else "filter_levels_kernel"}[dom],
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "us_per_launch": kern_us[dom],
             "kernels_us": kern_us,

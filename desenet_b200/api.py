@@ -284,7 +284,7 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
             ops.append_label_keys(head, padded, conf_thres, classes, keys, counts)
             det, det_count = ops.nms_levels(head, keys, counts, conf_thres, iou_thres, agnostic, int(max_det), labels=padded)
         else:
-            target = min(ops.MAX_NMS, max(8192, 16 * int(max_det)))
+            target = ops.cut_target_for(max_det)
             cut = None
             if ml and head.A * head.nc >= 8 * target:      # eval setting: sampled confidence cut (exact, see ops.conf_cut_levels)
                 cut = ops.conf_cut_levels(head, conf_thres, ml, classes, target=target)

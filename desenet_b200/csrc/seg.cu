@@ -27,6 +27,9 @@ struct SegParams {
 
 constexpr int kMaxPackedC = 4;      // template instantiations of the fast path
 // build-time tuning switches (no run-time environment knobs in the launchers)
+#ifndef DSN_SEG_EVAL_CTAS_PER_SM
+#define DSN_SEG_EVAL_CTAS_PER_SM 0   // eval-mode seg kernel: cap on the resident CTAs per SM its persistent grid is sized for (0: all that fit)
+#endif
 #ifndef DSN_SEG_MASK_CTAS_PER_SM
 #define DSN_SEG_MASK_CTAS_PER_SM 0   // detect-mode mask kernel: resident CTAs per SM the grid is sized for (0: one CTA per block)
 #endif
@@ -789,6 +792,7 @@ static int launch_eval_rows_w(const SegParams &p, cudaStream_t st) {
     int occ = 0;
     DSN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seg_fused_rows_kernel<T, C, true, M, W>, threads, smem));
     if (occ < 1) occ = 1;
+    if (DSN_SEG_EVAL_CTAS_PER_SM > 0 && occ > DSN_SEG_EVAL_CTAS_PER_SM) occ = DSN_SEG_EVAL_CTAS_PER_SM;
     long long grid;
     int rows_per_cta;
     rows_grid(p, occ, grid, rows_per_cta);

@@ -175,7 +175,14 @@ class ConfCut:
         self.dropped = torch.zeros((bs,), dtype=torch.int32, device=device)
 
 
-def conf_cut_levels(head: Head, conf_thres: float, multi_label: bool, classes=None, target: int = 8192,
+def cut_target_for(max_det: int) -> int:
+    """Candidates the greedy NMS is expected to consume before ``max_det`` survive (it stops there, general.py:735-736):
+    an order of magnitude more than the survivors, at least 4096.  The confidence cut keeps 1.5 x as many; an image that
+    needs more is redone uncut on the device (``detect_nms_redo_levels``), so the choice affects speed only."""
+    return min(MAX_NMS, max(4096, 8 * int(max_det)))
+
+
+def conf_cut_levels(head: Head, conf_thres: float, multi_label: bool, classes=None, target: int = 4096,
                     cut: Optional[ConfCut] = None) -> Optional[ConfCut]:
     """Sampled per-image confidence cut for huge candidate sets (see include/desenet_b200.h).  Returns None when
     the head layout does not allow it (the filter then simply runs without a cut)."""

@@ -55,7 +55,7 @@ class PostProcessor:
         # sampled confidence cut (ops.conf_cut_levels): worth it when an image can emit far more than the max_nms
         # candidates non_max_suppression ever looks at (general.py:728-729), i.e. multi-label at a low threshold
         # candidates the greedy NMS is expected to consume before max_det survive; the cut keeps about twice as many
-        self.cut_target = min(ops.MAX_NMS, max(8192, 16 * int(max_det)))
+        self.cut_target = ops.cut_target_for(max_det)
         self.conf_cut = (self.kw["multi_label"] and cap >= 8 * self.cut_target) if conf_cut is None else bool(conf_cut)
         self.conf_cut = self.conf_cut and not fused_det
         with torch.cuda.device(d):

@@ -9,7 +9,7 @@ import shutil
 import sys
 from collections import OrderedDict
 
-R = sys.argv[1] if len(sys.argv) > 1 else "r1"
+R = sys.argv[1] if len(sys.argv) > 1 else "r2"
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 O = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
@@ -40,7 +40,7 @@ if os.path.exists(ll):
     total = sum(v[1] for v in mine.values()) or 1.0
     shutil.copy(ll, os.path.join(P, f"{R}_launches_cfg2.csv"))
     with open(os.path.join(P, f"{R}_launches_cfg2_summary.csv"), "w") as f:
-        f.write(f"# ncu launch list of `bench.py --steps 20 --warmup 5` (cfg 2, bs 64, CUDA-graph replay, 3 batches in flight), {R}\n")
+        f.write(f"# ncu launch list of `bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e --no-secondary` (cfg 2, bs 64, CUDA-graph replay, 3 batches in flight), {R}\n")
         f.write("# per-launch gpu__time_duration.sum (cold-cache, serialised): compare SHARES, not absolutes\n")
         f.write("kernel,launches,mean_ns,share_of_listed_time\n")
         for k, (n, t) in sorted(mine.items(), key=lambda kv: -kv[1][1]):
@@ -57,7 +57,8 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "launch__occupancy_limit_registers",
         "launch__occupancy_limit_shared_mem"]
 summary, traffic = OrderedDict(), OrderedDict()
-for c in (2, 3, 5):
+PROF_BS = {2: 64, 3: 512, 4: 32, 5: 128}       # profiles/measure_round.sh: the bench's own batch sizes
+for c in (2, 3, 4, 5):
     raw = os.path.join(O, f"{R}_ncu_full_cfg{c}_raw.csv")
     if not os.path.exists(raw) or os.path.getsize(raw) == 0:
         continue
@@ -89,15 +90,17 @@ for c in (2, 3, 5):
             def b(m):
                 v = float(r[hdr.index(m)].replace(",", ""))
                 return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[hdr.index(m)], 1)
-            prof_bs = 32 if c == 5 else 64          # profiles/measure_round.sh
-            traffic.setdefault(f"cfg{c}", OrderedDict())[short] = (b("dram__bytes_read.sum") + b("dram__bytes_write.sum")) / prof_bs
+            t = traffic.setdefault(f"cfg{c}", OrderedDict())
+            t[short] = b("dram__bytes_read.sum") + b("dram__bytes_write.sum")
+            t["images_per_launch"] = PROF_BS[c]
+            t["source"] = f"profiles/{R}_ncu_full_cfg{c}_raw.csv (ncu --set full, bs {PROF_BS[c]}, last capture of each kernel)"
         except Exception:
             pass
     summary[f"cfg{c}"] = out
 if summary:
     json.dump(summary, open(os.path.join(P, f"{R}_ncu_full_summary.json"), "w"), indent=1)
-    traffic["note"] = ("PER IMAGE: (dram__bytes_read.sum + dram__bytes_write.sum) / batch of one launch, from ncu --set full "
-                       "(profiles/%s_ncu_full_cfg*_raw.csv; cfg2/cfg3 captured at bs 64, cfg5 at bs 32); bench.py multiplies by its "
-                       "batch.  Writes still dirty in the 126 MB L2 at kernel end are not counted by ncu" % R)
+    traffic["note"] = ("PER LAUNCH: dram__bytes_read.sum + dram__bytes_write.sum of one launch at `images_per_launch`, from ncu "
+                       "--set full; bench.py reports it as roofline.traffic only when its own batch has that size.  Writes still "
+                       "dirty in the 126 MB L2 at kernel end are not counted by ncu")
     json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
 print("profiles/ updated:", sorted(os.listdir(P)))
