@@ -317,14 +317,30 @@ __global__ void __launch_bounds__(kDenseThreads, 3) filter_dense_kernel(const He
 // costs 68 KB of shared memory per CTA and caps the occupancy at 24 warps per SM (cfg 3: 0.46 of the HBM peak).  Here every
 // warp is a small persistent pipeline of its own: it walks a contiguous range of tiles (128 cells x (1 + nc) planes) and
 // keeps kTmaStages tiles in flight with TMA bulk copies (cp.async.bulk global -> shared, one 512-byte row per plane,
-// issued by lanes 0..nc, completion on one mbarrier per stage) - no registers hold data in flight, the tile arrives where
-// the exact pass wants to index it, and nothing is parked.  The arithmetic is the kernel above's: logit-space bound per
-// cell, one compare per (cell, class), warp compaction of the pairs above the bound, exact sigmoid * sigmoid for those,
-// keys staged per warp and written with one atomic per batch.  Warps never synchronise with each other.
-constexpr int kTmaWarps = 4;             // per CTA
-constexpr int kTmaStages = 3;            // tiles in flight per warp
-constexpr int kTmaKbuf = 128;            // keys staged per warp
+// completion on one mbarrier per stage) - no registers hold data in flight, the tile arrives where the later passes index
+// it, and nothing is parked.  What is left is instruction issue, so the tile body is written for instruction count:
+//   * a lane owns 4 cells; per cell the logit-space bound L of the kernel above, +inf for cells that cannot pass at all;
+//   * per (cell, class) ONE subtraction L - logit whose sign bit is shifted into the lane's 24-bit mask (funnel shift):
+//     two instructions per pair, no predicates;
+//   * the pairs above the bound (4-5 % at the eval setting with the confidence cut) are moved, one per lane and round,
+//     into a small PENDING list that survives across tiles, and the exact arithmetic (sigmoid * sigmoid, the strict
+//     compares of general.py:710-711, the cut on the key) runs only on FULL batches of 32 pending pairs;
+//   * keys are staged per warp and leave with one atomic per batch of up to 128.
+// Warps never synchronise with each other.
+#ifndef DSN_TMA_WARPS
+#define DSN_TMA_WARPS 8
+#endif
+#ifndef DSN_TMA_STAGES
+#define DSN_TMA_STAGES 2
+#endif
+#ifndef DSN_FILTER_LDGSTS
+#define DSN_FILTER_LDGSTS 0
+#endif
+constexpr int kTmaWarps = DSN_TMA_WARPS;     // per CTA
+constexpr int kTmaStages = DSN_TMA_STAGES;   // tiles in flight per warp (more stages = fewer resident warps: measured worse)
+constexpr int kTmaKbuf = 128;                // keys staged per warp
 constexpr int kTmaTileCells = 128;
+constexpr int kTmaPend = 64;                 // pending (cell, class) pairs per warp: < 32 between tiles, <= 63 inside one
 
 struct TmaLevel {
     const void *raw;
@@ -337,28 +353,28 @@ struct TileCursor {
     int b, l, a, t;
 };
 
-static inline size_t tma_warp_bytes(int nc, int esize) {
+// per-warp shared memory: stages [kTmaStages][planes][128] elements | kbuf | pending (class logit, obj logit, ref) | mbarriers
+__host__ __device__ inline size_t tma_warp_bytes(int nc, int esize) {
     const size_t stage_bytes = (size_t)(nc + 1) * kTmaTileCells * esize;
-    return ((kTmaStages * stage_bytes + kTmaKbuf * 8 + (size_t)nc * kTmaTileCells * 2 + kTmaStages * 8) + 127) & ~(size_t)127;
+    return ((kTmaStages * stage_bytes + kTmaKbuf * 8 + kTmaPend * 12 + kTmaStages * 8) + 127) & ~(size_t)127;
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kTmaWarps * 32) filter_dense_tma_kernel(const HeadGeom g, const FilterOut f, const float obj_logit_lo,
-                                                                         const float obj_logit_hi, const int tiles_per_image,
+__global__ void __launch_bounds__(kTmaWarps * 32) filter_dense_tma_kernel(const HeadGeom g, const FilterOut f, const int tiles_per_image,
                                                                          const long long total_tiles, const int tiles_per_warp) {
     extern __shared__ __align__(128) unsigned char tma_smem[];
     __shared__ TmaLevel lv[DSN_MAX_LEVELS];
     const int nc = g.no - 5;
     const int planes = nc + 1;                                   // objectness + classes: channels 4 .. 4 + nc of an anchor
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // per-warp shared memory: stages [kTmaStages][planes][128] elements | kbuf | idx | mbarriers
     const size_t stage_bytes = (size_t)planes * kTmaTileCells * sizeof(T);
-    const size_t warp_bytes = ((kTmaStages * stage_bytes + kTmaKbuf * 8 + (size_t)nc * kTmaTileCells * 2 + kTmaStages * 8) + 127) & ~(size_t)127;
-    unsigned char *wbase = tma_smem + warp_bytes * warp;
+    unsigned char *wbase = tma_smem + tma_warp_bytes(nc, (int)sizeof(T)) * warp;
     T *stages = reinterpret_cast<T *>(wbase);
     unsigned long long *kbuf = reinterpret_cast<unsigned long long *>(wbase + kTmaStages * stage_bytes);
-    unsigned short *idx = reinterpret_cast<unsigned short *>(kbuf + kTmaKbuf);
-    unsigned long long *full = reinterpret_cast<unsigned long long *>(wbase + kTmaStages * stage_bytes + kTmaKbuf * 8 + (size_t)nc * kTmaTileCells * 2);
+    float *pend_v = reinterpret_cast<float *>(kbuf + kTmaKbuf);                  // class logit of a pending pair
+    float *pend_o = pend_v + kTmaPend;                                           // its objectness logit
+    unsigned int *pend_r = reinterpret_cast<unsigned int *>(pend_o + kTmaPend);  // row * nc + class (low half of the key)
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(pend_r + kTmaPend);
 #pragma unroll
     for (int i = 0; i < DSN_MAX_LEVELS; ++i)
         if ((int)threadIdx.x == i && i < g.nl)
@@ -394,31 +410,59 @@ __global__ void __launch_bounds__(kTmaWarps * 32) filter_dense_tma_kernel(const 
         cons.t = r - cons.a * lv[cons.l].tiles;
     }
     TileCursor prod = cons;
-    // lanes 0 .. nc each copy one 512-byte row of the tile (lane 0: objectness); lane 0 posts the byte count with its arrival
+    // lane 0 posts the byte count and issues one bulk copy per plane (512-byte rows; row 0: objectness)
     auto issue = [&](const TileCursor &c, int st) {
-        const TmaLevel L = lv[c.l];
-        const int cell0 = c.t * kTmaTileCells;
-        const unsigned bytes = (unsigned)min(kTmaTileCells, L.plane - cell0) * (unsigned)sizeof(T);
-        const uint32_t bar = flt_smem_u32(&full[st]);
-        if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * (unsigned)planes) : "memory");
-        if (lane < planes) {
-            const T *src = static_cast<const T *>(L.raw) + ((size_t)(c.b * g.na + c.a) * g.no + 4 + lane) * L.plane + cell0;
-            const uint32_t dst = flt_smem_u32(stages + ((size_t)st * planes + lane) * kTmaTileCells);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                         "r"(bytes), "r"(bar)
-                         : "memory");
+        if (lane == 0) {
+            const TmaLevel L = lv[c.l];
+            const int cell0 = c.t * kTmaTileCells;
+            const unsigned bytes = (unsigned)min(kTmaTileCells, L.plane - cell0) * (unsigned)sizeof(T);
+            const uint32_t bar = flt_smem_u32(&full[st]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * (unsigned)planes) : "memory");
+            const T *src = static_cast<const T *>(L.raw) + ((size_t)(c.b * g.na + c.a) * g.no + 4) * L.plane + cell0;
+            uint32_t dst = flt_smem_u32(stages + (size_t)st * planes * kTmaTileCells);
+            for (int pl = 0; pl < planes; ++pl) {
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                             "r"(bytes), "r"(bar)
+                             : "memory");
+                src += L.plane;
+                dst += kTmaTileCells * (unsigned)sizeof(T);
+            }
         }
     };
+#if DSN_FILTER_LDGSTS
+    // measurement variant: the same ring fed by per-lane 16-byte cp.async (LDGSTS) instead of bulk copies
+    auto issue_ldgsts = [&](const TileCursor &c, int st) {
+        const TmaLevel L = lv[c.l];
+        const int cell0 = c.t * kTmaTileCells;
+        constexpr int kVec = 16 / (int)sizeof(T);
+        const int ncell = min(kTmaTileCells, L.plane - cell0);
+        if (lane * kVec < ncell) {
+            const T *src = static_cast<const T *>(L.raw) + ((size_t)(c.b * g.na + c.a) * g.no + 4) * L.plane + cell0 + lane * kVec;
+            uint32_t dst = flt_smem_u32(stages + (size_t)st * planes * kTmaTileCells + lane * kVec);
+            for (int pl = 0; pl < planes; ++pl) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                src += L.plane;
+                dst += kTmaTileCells * (unsigned)sizeof(T);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#define DSN_ISSUE issue_ldgsts
+#else
+#define DSN_ISSUE issue
+#endif
     const int prefill = min(kTmaStages, my_tiles);
     for (int i = 0; i < prefill; ++i) {
-        issue(prod, i);
+        DSN_ISSUE(prod, i);
         advance(prod);
     }
     int issued = prefill;
 
     const unsigned int cap = f.cap > 0x7fffffffLL ? 0x7fffffffu : (unsigned)f.cap;
+    const unsigned int lt = (1u << lane) - 1u;
     int nk = 0;                                         // keys waiting in the warp's kbuf (warp-uniform)
-    int kb = cons.b;                                    // image the staged keys belong to
+    int np = 0;                                         // pending pairs (warp-uniform)
+    int kb = cons.b;                                    // image the staged keys and the pending pairs belong to
     unsigned long long *kout = f.keys + (size_t)kb * f.cap;
     auto flush = [&]() {                                // ONE atomic on the image's counter, coalesced 8-byte stores
         unsigned int base = 0;
@@ -435,19 +479,51 @@ __global__ void __launch_bounds__(kTmaWarps * 32) filter_dense_tma_kernel(const 
         __syncwarp();
         nk = 0;
     };
-    unsigned int cut = f.cut_hi ? f.cut_hi[kb] : 0xFFFFFFFFu;
-    float t_lo = fmaxf(f.conf_thres, __uint_as_float(~cut)) * 0.999f;      // see filter_dense_kernel
+    unsigned int cut;
+    float inv_t;
+    auto image_consts = [&]() {
+        cut = f.cut_hi ? f.cut_hi[kb] : 0xFFFFFFFFu;
+        const float t_lo = fmaxf(f.conf_thres, __uint_as_float(~cut)) * 0.999f;      // see filter_dense_kernel
+        inv_t = __fdividef(1.0f, t_lo);                                              // +inf when T' == 0
+    };
+    image_consts();
+    // exact arithmetic for the newest `n` (<= 32) pending pairs, one per lane                          general.py:703,710,717
+    auto exact_batch = [&](int n) {
+        if (nk > kTmaKbuf - 32) flush();
+        const int e = np - n + lane;
+        bool emit = false;
+        unsigned long long key = 0ull;
+        if (lane < n) {
+            const unsigned int ref = pend_r[e];
+            const float conf = __fmul_rn(sigmoidf_ref(pend_v[e]), sigmoidf_ref(pend_o[e]));
+            const unsigned int ck = conf_key(conf);
+            emit = conf > f.conf_thres && ck <= cut;
+            if (f.use_cmask) emit = emit && class_allowed(f, (int)(ref % (unsigned)nc));
+            key = ((unsigned long long)ck << 32) | (unsigned long long)ref;
+        }
+        const unsigned int bal = __ballot_sync(0xffffffffu, emit);
+        if (emit) kbuf[nk + __popc(bal & lt)] = key;
+        nk += __popc(bal);
+        np -= n;
+        __syncwarp();                                    // the pending slots are rewritten by the next insertion round
+    };
 
     for (int it = 0; it < my_tiles; ++it) {
         const int st = it % kTmaStages;
         const unsigned parity = (unsigned)(it / kTmaStages) & 1u;
         if (cons.b != kb) {                              // next image: its keys go to another buffer, its cut differs
+            if (np > 0) exact_batch(np);
             if (nk > 0) flush();
             kb = cons.b;
             kout = f.keys + (size_t)kb * f.cap;
-            cut = f.cut_hi ? f.cut_hi[kb] : 0xFFFFFFFFu;
-            t_lo = fmaxf(f.conf_thres, __uint_as_float(~cut)) * 0.999f;
+            image_consts();
         }
+#if DSN_FILTER_LDGSTS
+        static_assert(kTmaStages == 2, "the cp.async variant waits with immediates for a two-stage ring");
+        if (issued > it + 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+#else
         {
             const uint32_t bar = flt_smem_u32(&full[st]);
             asm volatile(
@@ -462,89 +538,65 @@ __global__ void __launch_bounds__(kTmaWarps * 32) filter_dense_tma_kernel(const 
                 "r"(parity)
                 : "memory");
         }
+#endif
         const TmaLevel L = lv[cons.l];
         const int cell0 = cons.t * kTmaTileCells;
-        const int nvalid = min(kTmaTileCells, L.plane - cell0);
         const T *tile = stages + (size_t)st * planes * kTmaTileCells;              // [planes][128]: row 0 objectness, 1 + c class c
-        const bool in = lane * 4 < nvalid;                      // plane % 4 == 0: the 4 cells are all in or all out
-        // ---- per-cell logit bound (identical to filter_dense_kernel) -------------------------------------------------
+        const bool in = lane * 4 < min(kTmaTileCells, L.plane - cell0);           // plane % 4 == 0: the 4 cells are all in or all out
+        // ---- per-cell logit bound: sigmoid(cls) * sigmoid(obj) > T' needs cls > L = -ln(1 / (T' * sigmoid(obj)) - 1) ---------
+        const float4 o4 = Elem<T>::lds4(tile + lane * 4);
+        const float ol[4] = {o4.x, o4.y, o4.z, o4.w};
         float Lb[4];
-        bool any = false;
-        {
-            float4 o4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-            if (in) o4 = Elem<T>::lds4(tile + lane * 4);
-            const float ol[4] = {o4.x, o4.y, o4.z, o4.w};
-            const float inv_t = __fdividef(1.0f, t_lo);                                      // +inf when T' == 0
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                Lb[k] = INFINITY;
-                bool pass = ol[k] >= obj_logit_hi;
-                if (!pass && ol[k] >= obj_logit_lo) pass = sigmoidf_ref(ol[k]) > f.conf_thres;   // yolo.py:266, general.py:668
-                if (pass) {
-                    const float q = __fdividef(inv_t, 1.0f + __expf(-ol[k])) - 1.0f;
-                    if (q > 0.f) Lb[k] = -__logf(q) - 4e-3f;                                 // q == +inf -> -inf: everything passes
-                }
-                any = any || Lb[k] < INFINITY;
+        for (int k = 0; k < 4; ++k) {
+            const float q = __fdividef(inv_t, 1.0f + __expf(-ol[k])) - 1.0f;      // NaN objectness -> NaN -> +inf below
+            Lb[k] = q > 0.f ? -__logf(q) - 4e-3f : INFINITY;                      // q == +inf (T' == 0) -> -inf: everything passes
+        }
+        // ---- logit-space test: the sign of L - logit, shifted into the mask (pair p = class * 4 + cell -> bit 4 * nc - 1 - p) -
+        unsigned int mask = 0;
+#pragma unroll
+        for (int ci = 0; ci < kDenseChunk; ++ci) {
+            if (ci < nc) {
+                const float4 v = Elem<T>::lds4(tile + (size_t)(1 + ci) * kTmaTileCells + lane * 4);
+                mask = __funnelshift_l(__float_as_uint(Lb[0] - v.x), mask, 1);
+                mask = __funnelshift_l(__float_as_uint(Lb[1] - v.y), mask, 1);
+                mask = __funnelshift_l(__float_as_uint(Lb[2] - v.z), mask, 1);
+                mask = __funnelshift_l(__float_as_uint(Lb[3] - v.w), mask, 1);
             }
         }
-        if (__any_sync(0xffffffffu, any)) {
-            // ---- logit-space test, one compare per (cell, class) ------------------------------------------------------
-            unsigned int mask = 0;
-#pragma unroll
-            for (int ci = 0; ci < kDenseChunk; ++ci) {
-                if (ci < nc) {
-                    float4 v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-                    if (in) v = Elem<T>::lds4(tile + (size_t)(1 + ci) * kTmaTileCells + lane * 4);
-                    mask |= (v.x > Lb[0] ? 1u : 0u) << (ci * 4 + 0);
-                    mask |= (v.y > Lb[1] ? 1u : 0u) << (ci * 4 + 1);
-                    mask |= (v.z > Lb[2] ? 1u : 0u) << (ci * 4 + 2);
-                    mask |= (v.w > Lb[3] ? 1u : 0u) << (ci * 4 + 3);
-                }
+        if (!in) mask = 0;                               // cells beyond the plane: the stage holds stale bytes there
+        // ---- pairs above the bound -> pending list, one per lane and round; full batches of 32 go through the exact pass ---
+        const unsigned int row0 = (unsigned)(L.row_off + cons.a * L.plane + cell0) + (unsigned)lane * 4u;
+        const int top = 4 * nc - 1;
+        while (__any_sync(0xffffffffu, mask != 0)) {
+            const bool have = mask != 0;
+            const unsigned int bal = __ballot_sync(0xffffffffu, have);
+            if (have) {
+                const int pos = 31 - __clz(mask);        // highest set bit = lowest pair index
+                mask &= ~(1u << pos);
+                const int pr = top - pos, ci = pr >> 2, k = pr & 3;
+                const int slot = np + __popc(bal & lt);
+                pend_v[slot] = Elem<T>::cvt(tile[(1 + ci) * kTmaTileCells + lane * 4 + k]);
+                pend_o[slot] = k == 0 ? ol[0] : (k == 1 ? ol[1] : (k == 2 ? ol[2] : ol[3]));
+                pend_r[slot] = (row0 + (unsigned)k) * (unsigned)nc + (unsigned)ci;
             }
-            if (__any_sync(0xffffffffu, mask != 0)) {
-                const int mine = __popc(mask);
-                int incl = mine;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int up = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += up;
-                }
-                const int total = __shfl_sync(0xffffffffu, incl, 31);
-                int slot = incl - mine;
-                const unsigned int tag = (unsigned)lane;
-                for (unsigned int m = mask; m; m &= m - 1) idx[slot++] = (unsigned short)(((__ffs(m) - 1) << 5) | tag);   // (bit, lane)
-                __syncwarp();
-                // ---- exact arithmetic for the surviving pairs, one per lane ---------------------------------------------
-                const unsigned int row0 = (unsigned)(L.row_off + cons.a * L.plane + cell0);
-                for (int e0 = 0; e0 < total; e0 += 32) {
-                    if (nk > kTmaKbuf - 32) flush();
-                    const int e = e0 + lane;
-                    bool emit = false;
-                    unsigned long long key = 0ull;
-                    if (e < total) {
-                        const unsigned int id = idx[e], bit = id >> 5;
-                        const int ci = bit >> 2, cell = (id & 31) * 4 + (bit & 3);      // bit = class * 4 + cell of the lane
-                        const float conf = __fmul_rn(sigmoidf_ref(Elem<T>::cvt(tile[(1 + ci) * kTmaTileCells + cell])),
-                                                     sigmoidf_ref(Elem<T>::cvt(tile[cell])));                             // general.py:703
-                        const unsigned int ck = conf_key(conf);
-                        emit = conf > f.conf_thres && ck <= cut && class_allowed(f, ci);                      // general.py:710,717
-                        key = ((unsigned long long)ck << 32) | (unsigned long long)((row0 + cell) * (unsigned)nc + (unsigned)ci);
-                    }
-                    const unsigned int bal = __ballot_sync(0xffffffffu, emit);
-                    if (emit) kbuf[nk + __popc(bal & ((1u << lane) - 1u))] = key;
-                    nk += __popc(bal);
-                }
-            }
+            np += __popc(bal);
+            __syncwarp();
+            if (np >= 32) exact_batch(32);
         }
         __syncwarp();                                    // every lane is done with the stage
         if (issued < my_tiles) {                         // refill it with the tile kTmaStages ahead
+#if !DSN_FILTER_LDGSTS
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue(prod, st);
+#endif
+            DSN_ISSUE(prod, st);
             advance(prod);
             ++issued;
         }
         advance(cons);
     }
+#undef DSN_ISSUE
+    if (np > 0) exact_batch(np);
     if (nk > 0) flush();
 }
 
@@ -837,8 +889,7 @@ static int launch_filter(HeadGeom &g, const FilterOut &f, float conf_thres, int 
         long long tpw = std::max<long long>(kTmaStages + 1, (total_tiles + max_warps - 1) / max_warps);
         const long long warps = (total_tiles + tpw - 1) / tpw;
         const long long grid = (warps + kTmaWarps - 1) / kTmaWarps;
-        filter_dense_tma_kernel<T><<<(unsigned)grid, kTmaWarps * 32, smem, st>>>(g, f, lo, obj_logit_upper_bound(conf_thres), tiles_per_image,
-                                                                              total_tiles, (int)tpw);
+        filter_dense_tma_kernel<T><<<(unsigned)grid, kTmaWarps * 32, smem, st>>>(g, f, tiles_per_image, total_tiles, (int)tpw);
         DSN_CHECK_LAUNCH();
         return DSN_OK;
     }

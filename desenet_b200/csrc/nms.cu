@@ -15,7 +15,12 @@
 // and stops at max_det survivors (general.py:735-736), after max_nms candidates
 // (general.py:728-729) or when the keys are exhausted.  Latency-bound, not HBM-bound: it runs next
 // to the streaming kernels on otherwise idle SMs.
-#include "nms_core.cuh"
+#include "nms_launch.cuh"
+
+// the 256-thread instantiation (nms_small.cu)
+int dsn_nms_levels_small(const void *const *raw, int dtype, const int *ny, const int *nx, const float *stride, const float *anchor_grid, int nl,
+                         int bs, int na, int no, const uint64_t *keys, int64_t cap, const int *counts, float conf_thres, double iou_thres,
+                         int agnostic, int max_nms, int max_det, float max_wh, float *det, int *det_count, void *stream);
 
 namespace dsn {
 
@@ -23,24 +28,6 @@ struct FilterClassMask {
     unsigned long long m[4];
     int use;
 };
-
-template <class BoxSrc>
-__global__ void __launch_bounds__(kNmsThreads, 1024 / kNmsThreads) nms_kernel(const NmsParams p, const BoxSrc src) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    NmsSmem &s = *reinterpret_cast<NmsSmem *>(smem_raw);
-    const int b = blockIdx.x;
-    const int total = p.counts[b];
-    if (total > p.cap) {                     // keys were dropped: the caller must retry with a larger cap
-        if (threadIdx.x == 0) p.det_count[b] = -1;
-        return;
-    }
-    if (total <= 0 || p.max_det <= 0 || p.max_nms <= 0) {
-        const bool starved = total <= 0 && p.max_det > 0 && p.max_nms > 0 && p.cut_dropped && p.cut_dropped[b];
-        if (threadIdx.x == 0) p.det_count[b] = starved ? -2 : 0;
-        return;
-    }
-    nms_image(s, p, src, b, p.keys + (size_t)b * p.cap, total);
-}
 
 // A-priori labels as candidates (general.py:690-696, val.py:228 save_hybrid): label j of image b is prediction row A + j
 // with obj = 1 and a one-hot class, i.e. ONE candidate of confidence 1.0 for its class in both selection modes.
@@ -60,52 +47,20 @@ __global__ void append_label_keys_kernel(const float *__restrict__ labels, const
     }
 }
 
-template <class BoxSrc>
-static int launch_nms(const NmsParams &p, const BoxSrc &src, int bs, cudaStream_t st) {
-    if (bs == 0) return DSN_OK;
-    const size_t smem = sizeof(NmsSmem);
-    static DeviceOnce once;           // per template instantiation
-    const int rc = raise_dynamic_smem(once, nms_kernel<BoxSrc>, (int)smem);
-    if (rc) return rc;
-    nms_kernel<BoxSrc><<<bs, kNmsThreads, smem, st>>>(p, src);
-    DSN_CHECK_LAUNCH();
-    return DSN_OK;
-}
-
 }  // namespace dsn
 
 using namespace dsn;
-
-static int nms_levels_impl(const void *const *raw, int dtype, const int *ny, const int *nx, const float *stride, const float *anchor_grid, int nl,
-                           int bs, int na, int no, const uint64_t *keys, int64_t cap, const int *counts, float conf_thres,
-                           double iou_thres, int agnostic, int max_nms, int max_det, float max_wh, const unsigned int *cut_hi,
-                           const int *cut_dropped, const float *labels, int max_labels, float *det, int *det_count, void *stream) {
-    if (!stride || !anchor_grid) return DSN_E_INVALID;
-    if (max_labels < 0 || (max_labels > 0 && !labels)) return DSN_E_INVALID;
-    HeadGeom g;
-    int rc = make_geom(g, raw, dtype, ny, nx, stride, anchor_grid, nl, bs, na, no);
-    if (rc) return rc;
-    if ((unsigned long long)(g.A + max_labels) * (unsigned long long)(no - 5) >= (1ull << 32)) return DSN_E_UNSUPPORTED;
-    NmsParams p;
-    rc = make_nms_params(p, keys, cap, counts, bs, no - 5, conf_thres, iou_thres, agnostic, max_nms, max_det, max_wh, det, det_count);
-    if (rc) return rc;
-    p.cut_dropped = cut_dropped;
-    p.cut_hi = cut_dropped ? cut_hi : nullptr;
-    DSN_DISPATCH_DTYPE(dtype, T, {
-        BoxFromLevels<T> src;
-        src.g = g;
-        src.extra = labels;
-        src.extra_rows = max_labels;
-        return launch_nms(p, src, bs, (cudaStream_t)stream);
-    })
-    return DSN_OK;
-}
 
 extern "C" __attribute__((visibility("default"))) int dsn_nms_levels(const void *const *raw, int dtype, const int *ny, const int *nx, const float *stride,
                               const float *anchor_grid, int nl, int bs, int na, int no, const uint64_t *keys,
                               int64_t cap, const int *counts, float conf_thres, double iou_thres, int agnostic,
                               int max_nms, int max_det, float max_wh, const unsigned int *cut_hi, const int *cut_dropped,
                               float *det, int *det_count, void *stream) {
+    // No confidence cut = the detect setting (a few hundred candidates per image): 256-thread CTAs, which find room next to
+    // the streaming kernels of the other batches in flight (see nms_small.cu).  With a cut: thousands of candidates, 512.
+    if (!cut_dropped)
+        return dsn_nms_levels_small(raw, dtype, ny, nx, stride, anchor_grid, nl, bs, na, no, keys, cap, counts, conf_thres, iou_thres, agnostic,
+                                    max_nms, max_det, max_wh, det, det_count, stream);
     return nms_levels_impl(raw, dtype, ny, nx, stride, anchor_grid, nl, bs, na, no, keys, cap, counts, conf_thres, iou_thres, agnostic, max_nms,
                            max_det, max_wh, cut_hi, cut_dropped, nullptr, 0, det, det_count, stream);
 }
@@ -139,14 +94,5 @@ extern "C" __attribute__((visibility("default"))) int dsn_append_label_keys(cons
 extern "C" __attribute__((visibility("default"))) int dsn_nms_z(const void *z, int dtype, int bs, int64_t A, int no, const uint64_t *keys, int64_t cap,
                          const int *counts, float conf_thres, double iou_thres, int agnostic, int max_nms, int max_det,
                          float max_wh, float *det, int *det_count, void *stream) {
-    if (!z || A < 1 || no < 6 || dtype_size(dtype) == 0) return DSN_E_INVALID;
-    if (((uintptr_t)z & (uintptr_t)(dtype_size(dtype) - 1)) != 0) return DSN_E_ALIGN;
-    NmsParams p;
-    int rc = make_nms_params(p, keys, cap, counts, bs, no - 5, conf_thres, iou_thres, agnostic, max_nms, max_det, max_wh, det, det_count);
-    if (rc) return rc;
-    DSN_DISPATCH_DTYPE(dtype, T, {
-        BoxFromZ<T> src{static_cast<const T *>(z), A, no};
-        return launch_nms(p, src, bs, (cudaStream_t)stream);
-    })
-    return DSN_OK;
+    return nms_z_impl(z, dtype, bs, A, no, keys, cap, counts, conf_thres, iou_thres, agnostic, max_nms, max_det, max_wh, det, det_count, stream);
 }

@@ -8,11 +8,18 @@
 #include "common.cuh"
 #include "geom.cuh"
 
-namespace dsn {
-
 #ifndef DSN_NMS_THREADS
 #define DSN_NMS_THREADS 512
 #endif
+// Everything below depends on the CTA size, and the library holds TWO instantiations (nms.cu: 512 threads, nms_small.cu:
+// 256 threads): the inline namespace keeps their symbols apart.
+#ifndef DSN_NMS_NS
+#define DSN_NMS_NS nms_t512
+#endif
+
+namespace dsn {
+inline namespace DSN_NMS_NS {
+
 constexpr int kNmsThreads = DSN_NMS_THREADS;
 constexpr int kChunk = 2048;        // candidates sorted / resolved per round
 constexpr int kBins = 2048;         // histogram bins per refinement level (11 bits)
@@ -112,7 +119,7 @@ constexpr int kRound = 256;          // candidates resolved per bitmask round
 constexpr int kRankSortMax = 256;    // O(m^2) rank sort below, bitonic sort above
 constexpr int kWords = kRound / 64;
 constexpr int kChainClasses = 256;
-constexpr int kChainSplit = 2;       // = kNmsThreads / kRound: threads per candidate in the survivor test
+constexpr int kChainSplit = kNmsThreads / 256;   // = kNmsThreads / kRound: threads per candidate in the survivor test
 
 struct NmsSmem {
     unsigned long long key[kChunk];
@@ -855,4 +862,5 @@ static inline int make_nms_params(NmsParams &p, const uint64_t *keys, int64_t ca
 }
 
 
+}  // inline namespace DSN_NMS_NS
 }  // namespace dsn

@@ -15,7 +15,7 @@ buf=(ctypes.c_ulonglong*64)()
 logbuf=(ctypes.c_ulonglong*2048)()
 use_cut=os.environ.get('NOCUT') is None
 for it in range(5):
-    cut=ops.conf_cut_levels(head,cfg['conf'],cfg['multi_label'],target=8192) if use_cut else None
+    cut=ops.conf_cut_levels(head,cfg['conf'],cfg['multi_label'],target=ops.cut_target_for(cfg['max_det'])) if use_cut else None
     keys,cnt=ops.filter_levels(head,cfg['conf'],cfg['multi_label'],cut=cut)
     torch.cuda.synchronize()
     a=torch.cuda.Event(enable_timing=True); b=torch.cuda.Event(enable_timing=True)

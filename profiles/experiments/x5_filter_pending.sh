@@ -1,0 +1,19 @@
+O=gpurun_out; mkdir -p $O
+timeout 900 python -m pytest tests -m gpu -q -x > $O/x5_pytest.log 2>&1; tail -3 $O/x5_pytest.log
+B="python bench.py --config 3 --steps 50 --warmup 10 --no-cpu-baseline --no-e2e --no-secondary"
+$B > $O/x5_cfg3_base.json 2>$O/x5_base.err
+DSN_VARIANT="s3:-DDSN_TMA_STAGES=3:detect.cu" $B > $O/x5_cfg3_s3.json 2>$O/x5_s3.err
+for f in $O/x5_cfg3_*.json; do python - "$f" <<'PY'
+import json, sys
+try:
+    d = json.load(open(sys.argv[1]))
+    print(sys.argv[1], round(d["value"]), "img/s", round(d["ms_per_step"] * 1e3, 1), "us/step", {k: round(v, 1) for k, v in d["roofline"]["kernels_us"].items()}, d["check"].get("equals_recorded_1gpu_result"))
+except Exception as e:
+    print(sys.argv[1], "failed", e)
+PY
+done
+ncu --set full --clock-control none --import-source on -k regex:'filter_dense_tma' -c 2 -o $O/x5_ncu_filter -f python profiles/prof_kernels.py --config 3 --bs 512 --reps 2 > $O/x5_ncu.log 2>&1
+ncu -i $O/x5_ncu_filter.ncu-rep --page raw --csv > $O/x5_ncu_filter_raw.csv 2>/dev/null
+ncu -i $O/x5_ncu_filter.ncu-rep --page source --csv --launch-skip 1 --launch-count 1 > $O/x5_ncu_filter_src.csv 2>/dev/null; gzip -f $O/x5_ncu_filter_src.csv
+rm -f $O/x5_ncu_filter.ncu-rep
+for f in $O/x5_*.err; do echo $f; tail -n 3 $f; done

@@ -27,6 +27,13 @@ for c in 2 3 4 5; do
   ncu --set full --clock-control none --import-source on -k regex:'filter_|nms_kernel|seg_|conf_cut|detect_fused' -c 10 \
       -o $O/${R}_ncu_full_cfg$c -f python profiles/prof_kernels.py --config $c --bs $bs --reps 2 > $O/${R}_ncu_full_cfg$c.log 2>&1
   ncu -i $O/${R}_ncu_full_cfg$c.ncu-rep --page raw --csv > $O/${R}_ncu_full_cfg${c}_raw.csv 2>/dev/null
-  rm -f $O/${R}_ncu_full_cfg$c.ncu-rep.tmp
+  # source pages (SASS + source line, per-instruction executed / stall samples) of the hot kernels, then drop the
+  # report itself: gpurun only brings back 64 MiB and one report is 30-50 MB
+  for k in seg_mask_rows seg_fused_rows nms_kernel filter_dense_tma filter_dense_kernel filter_levels; do
+    ncu -i $O/${R}_ncu_full_cfg$c.ncu-rep --page source --csv -k regex:$k --launch-skip 0 --launch-count 1 \
+        > $O/${R}_ncu_src_cfg${c}_$k.csv 2>/dev/null
+    [ -s $O/${R}_ncu_src_cfg${c}_$k.csv ] && [ $(wc -l < $O/${R}_ncu_src_cfg${c}_$k.csv) -gt 20 ] && gzip -f $O/${R}_ncu_src_cfg${c}_$k.csv || rm -f $O/${R}_ncu_src_cfg${c}_$k.csv
+  done
+  rm -f $O/${R}_ncu_full_cfg$c.ncu-rep $O/${R}_ncu_full_cfg$c.ncu-rep.tmp
 done
-ls -la $O | grep ${R}_ | head -60
+du -sh $O; ls -la $O | grep ${R}_ | head -80
