@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <type_traits>
 
 #include "common.cuh"
 #include "geom.cuh"
@@ -323,23 +324,24 @@ static __device__ void bitonic_sort_regs(unsigned long long *a, unsigned long lo
                     v[e] = keep_min ? (pv < v[e] ? pv : v[e]) : (pv > v[e] ? pv : v[e]);
                 }
             } else {
-                // static register indices (a run-time e ^ j would put v[] in local memory); all E keys of a thread lie in
-                // the same k-block for k >= 2 * j, so they share the direction
-                const bool up = ((t * E) & k) == 0 || k < E;
+                // static register indices (a run-time e ^ j would put v[] in local memory).  Direction of element
+                // i = t * E + e: ascending iff (i & k) == 0, i.e. (e & k) == 0 while k < E and ((t * E) & k) == 0 from then on
+                const bool up = ((t * E) & k) == 0;
                 auto cx = [&](unsigned long long &x, unsigned long long &y, bool ascending) {
                     if ((x > y) == ascending) { const unsigned long long tmp = x; x = y; y = tmp; }
                 };
-                if constexpr (E == 2) {
-                    cx(v[0], v[1], up);
-                } else if constexpr (E == 4) {
-                    if (j == 1) {
-                        cx(v[0], v[1], k == 2 ? true : up);
-                        cx(v[2], v[3], k == 2 ? false : up);
-                    } else {
-                        cx(v[0], v[2], up);
-                        cx(v[1], v[3], up);
+                auto step = [&](auto jc) {
+                    constexpr int J = decltype(jc)::value;
+                    if constexpr (J < E) {
+#pragma unroll
+                        for (int e = 0; e < E; ++e)
+                            if ((e & J) == 0) cx(v[e], v[e | J], k < E ? (e & k) == 0 : up);
                     }
-                }
+                };
+                if (j == 1) step(std::integral_constant<int, 1>{});
+                else if (j == 2) step(std::integral_constant<int, 2>{});
+                else if (j == 4) step(std::integral_constant<int, 4>{});
+                else step(std::integral_constant<int, 8>{});
             }
         }
     }
@@ -349,9 +351,11 @@ static __device__ void bitonic_sort_regs(unsigned long long *a, unsigned long lo
     __syncthreads();
 }
 static __device__ void bitonic_sort(unsigned long long *a, unsigned long long *scratch, int n_pow2) {
+    static_assert(kChunk <= 8 * kNmsThreads, "a thread sorts at most 8 keys in registers");
     if (n_pow2 <= kNmsThreads) bitonic_sort_regs<1>(a, scratch);          // callers pad to kNmsThreads keys at least
     else if (n_pow2 == 2 * kNmsThreads) bitonic_sort_regs<2>(a, scratch);
-    else bitonic_sort_regs<4>(a, scratch);
+    else if (n_pow2 == 4 * kNmsThreads) bitonic_sort_regs<4>(a, scratch);
+    else bitonic_sort_regs<8>(a, scratch);
 }
 
 // m <= kNmsThreads unique keys.  T = kNmsThreads / pow2ceil(m) (<= 32) adjacent lanes share one key:
