@@ -59,6 +59,7 @@ SIGNATURES = {
     "dsn_compute_ap": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dsn_det_confusion_matrix": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                                          c_float, c_float, c_int, c_void_p, c_void_p]),
+    "dsn_detect_head_conv1x1": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dsn_seg_head_conv1x1": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dsn_peer_alloc": (c_int, [c_int64, POINTER(c_void_p)]),
     "dsn_peer_free": (c_int, [c_void_p]),

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libdesenet_b200.so")
-SOURCES = ["api.cu", "seg.cu", "detect.cu", "nms.cu", "nms_small.cu", "fused.cu", "coords.cu", "match.cu", "stats.cu", "peer.cu", "headconv.cu"]
+SOURCES = ["api.cu", "seg.cu", "detect.cu", "nms.cu", "nms_small.cu", "fused.cu", "coords.cu", "match.cu", "stats.cu", "peer.cu", "headconv.cu", "detconv.cu"]
 HEADERS = ["common.cuh", "geom.cuh", "filter_core.cuh", "nms_core.cuh", "nms_launch.cuh", os.path.join("..", "..", "include", "desenet_b200.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -459,6 +459,54 @@ def seg_head_conv1x1(features: torch.Tensor, weight: torch.Tensor, bias: Optiona
     return out
 
 
+_CONV_PARAM_CACHE = {}
+
+
+def _conv_params(weight: torch.Tensor, bias: Optional[torch.Tensor], dtype, device):
+    """(N, K) weight in ``dtype`` and fp32 bias on ``device``; converted once per parameter version."""
+    key = (weight.data_ptr(), weight._version, bias.data_ptr() if bias is not None else 0, bias._version if bias is not None else 0,
+           dtype, str(device))
+    hit = _CONV_PARAM_CACHE.get(id(weight))
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
+    wt = weight.detach().reshape(int(weight.shape[0]), -1).to(device=device, dtype=dtype).contiguous()
+    bt = bias.detach().to(device=device, dtype=torch.float32).contiguous() if bias is not None else None
+    if len(_CONV_PARAM_CACHE) > 64:
+        _CONV_PARAM_CACHE.clear()
+    _CONV_PARAM_CACHE[id(weight)] = (key, wt, bt)
+    return wt, bt
+
+
+def detect_head_conv1x1_supported(features: torch.Tensor, n_out: int) -> bool:
+    """Whether ``detect_head_conv1x1`` takes this level (see include/desenet_b200.h: dsn_detect_head_conv1x1)."""
+    if not features.is_cuda or features.dim() != 4 or features.dtype not in DTYPE_CODE or n_out > 256:
+        return False
+    K, plane = int(features.shape[1]), int(features.shape[2]) * int(features.shape[3])
+    if features.dtype == torch.float32:
+        return 12 * K * 4 <= 48 * 1024
+    n_pad = (n_out + 15) // 16 * 16
+    return K % 64 == 0 and plane % 8 == 0 and 3 * 16384 + 1024 + n_pad * K * 2 <= 200 * 1024
+
+
+def detect_head_conv1x1(features: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """One Detect output conv, nn.Conv2d(ch[i], na*no, 1) + bias (yolo.py:252,258): (bs, K, ny, nx) features ->
+    (bs, na*no, ny, nx) raw level in the features' precision.  fp16 / bf16: tcgen05 tensor cores with fp32 accumulation;
+    fp32: exact FMA chain."""
+    lib = _lib.load()
+    features = _require_cuda_input(features, "features")
+    bs, K, ny, nx = (int(v) for v in features.shape)
+    N = int(weight.shape[0])
+    if int(weight.numel()) != N * K:
+        raise ValueError(f"weight must be ({N}, {K}[, 1, 1]), got {tuple(weight.shape)}")
+    wt, bt = _conv_params(weight, bias, features.dtype, features.device)
+    with torch.cuda.device(features.device):
+        out = torch.empty((bs, N, ny, nx), dtype=features.dtype, device=features.device)
+        rc = lib.dsn_detect_head_conv1x1(_ptr(features), DTYPE_CODE[features.dtype], _ptr(wt), _ptr(bt), bs, K, N, ny, nx, _ptr(out),
+                                         _stream(features.device))
+    _lib.check(rc, "dsn_detect_head_conv1x1")
+    return out
+
+
 def letterbox_params(img1_shape, img0_shape, ratio_pad=None):
     """(pad_x, pad_y, gain, w0, h0) exactly as scale_coords derives them in Python (general.py:600-605)."""
     if ratio_pad is None:

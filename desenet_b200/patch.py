@@ -183,11 +183,24 @@ class FusedHeadConv(nn.Module):
         return ops.seg_head_conv1x1(x, self.original.weight, self.original.bias)
 
 
-def _detect_forward_factory(original_forward, fused: bool):
+def _detect_head_conv(conv: nn.Module, x: torch.Tensor) -> torch.Tensor:
+    """``Detect.m[i](x[i])`` (yolo.py:258) through dsn_detect_head_conv1x1 when the level qualifies (plain 1x1 conv, shapes
+    the kernel takes), else the module itself."""
+    if (isinstance(conv, nn.Conv2d) and tuple(conv.kernel_size) == (1, 1) and tuple(conv.stride) == (1, 1)
+            and tuple(conv.padding) == (0, 0) and tuple(conv.dilation) == (1, 1) and conv.groups == 1
+            and x.dtype == conv.weight.dtype and ops.detect_head_conv1x1_supported(x, conv.out_channels)):
+        return ops.detect_head_conv1x1(x, conv.weight, conv.bias)
+    return conv(x)
+
+
+def _detect_forward_factory(original_forward, fused: bool, head_convs: bool = False):
     def forward(self, x):
         if self.training or not x[0].is_cuda:
             return original_forward(self, x)
-        raw = [self.m[i](x[i]) for i in range(self.nl)]                      # yolo.py:258
+        if head_convs:                                                       # SURVEY 8f rank 4: the convs as producers of the tail
+            raw = [_detect_head_conv(self.m[i], x[i]) for i in range(self.nl)]
+        else:
+            raw = [self.m[i](x[i]) for i in range(self.nl)]                  # yolo.py:258
         # host copy of anchor_grid / stride: once per head (re-read only when a buffer is updated in place)
         ver = (self.anchor_grid.data_ptr(), self.anchor_grid._version, self.stride.data_ptr(), self.stride._version)
         cached = getattr(self, "_dsn_spec", None)
@@ -258,8 +271,9 @@ def install(model: Optional[nn.Module] = None, fused: bool = True, modules: Opti
     imported by name — including ``__main__`` when scripts/detect.py or scripts/val.py is the entry script); with
     ``model`` also defer the Detect decode and the seg head's final Upsample of that model instance.
     ``modules``: restrict the patch to these module names (their current attributes are taken as the originals).
-    ``head_convs`` (opt-in, needs ``model``): also run the seg head's last 1x1 convolution in the streaming kernel
-    (``FusedHeadConv``)."""
+    ``head_convs`` (opt-in, needs ``model``): also run the heads' last 1x1 convolutions in this package's kernels - the seg
+    head's ``nn.Conv2d(c_hid, n_segcls, 1)`` (``FusedHeadConv``, streaming kernel) and the ``Detect.m[i]`` output convs
+    (tcgen05 tensor cores for fp16 / bf16 models, exact fp32 FMA otherwise)."""
     h = Installed()
     modules = list(modules) if modules is not None else None
     orig = _find_originals(modules)
@@ -281,7 +295,7 @@ def install(model: Optional[nn.Module] = None, fused: bool = True, modules: Opti
         for m in model.modules():
             cls = type(m)
             if cls.__name__ == "Detect" and hasattr(m, "anchor_grid") and hasattr(m, "m") and cls not in patched_classes:
-                h._set(cls, "forward", _detect_forward_factory(cls.forward, fused))
+                h._set(cls, "forward", _detect_forward_factory(cls.forward, fused, head_convs))
                 patched_classes.add(cls)
             if cls.__name__.startswith("SegMask"):
                 # every seg head of the reference ends in nn.Sequential(..., nn.Conv2d(c, n_segcls, k), nn.Upsample(x8,

@@ -214,6 +214,18 @@ int dsn_seg_fullres(const void *logits, int dtype, int bs, int C, int H, int W,
 int dsn_seg_head_conv1x1(const void *features, int dtype, const float *weight, const float *bias, int bs, int K, int C,
                          int h, int w, float *logits, void *stream);
 
+/* Producer of the detection tail's input (opt-in because it changes the boundary): one
+ * Detect output convolution nn.Conv2d(ch[i], na * no, 1) + bias (core/models/yolo.py:252, applied at :258).
+ *   features (bs, K, ny, nx) NCHW, elements of type `dtype`;  weight (N, K) row-major, elements of type `dtype`;
+ *   bias (N) fp32 or NULL;  out (bs, N, ny, nx) NCHW, elements of type `dtype` = raw level i of dsn_filter_levels / dsn_nms_levels
+ * DSN_F16 / DSN_BF16: tcgen05 tensor cores, fp32 accumulation in TMEM, result rounded to `dtype` (what the reference's
+ * cuDNN convolution does under --half); needs K % 64 == 0, (ny * nx) % 8 == 0, N <= 256 and N_pad * K * 2 + 50 176 bytes of
+ * shared memory <= 200 KB (DSN_E_UNSUPPORTED otherwise: keep the framework's convolution for that level).
+ * DSN_F32: exact fp32 FMA chain in channel order on the CUDA cores (TF32 would break the 1e-5 box tolerance).
+ * Parity with the reference's convolution is a tolerance (summation order), not bit-exactness. */
+int dsn_detect_head_conv1x1(const void *features, int dtype, const void *weight, const float *bias, int bs, int K, int N,
+                            int ny, int nx, void *out, void *stream);
+
 /* nn.Upsample(bilinear, align_corners=True) alone (core/models/yolo.py:183): (planes,h,w) ->
  * (planes,H,W), bit-identical to ATen's CPU kernel (fma(l0,a,l1*b) lerps, horizontal first). */
 int dsn_upsample_bilinear_ac(const void *in, int dtype, int64_t planes, int h, int w, int H, int W,

@@ -208,3 +208,52 @@ def test_head_convs_option_on_cuda(golden):
     ref_full = fx["seg_full"]
     margin = np.abs(ref_full[:, 1] - ref_full[:, 0])
     assert ((seg_out.cpu().numpy() == fx["mask"]) | (margin < 1e-4)).all()
+
+
+@pytest.mark.parametrize("half", [True, False])
+def test_head_convs_detect_convs_on_cuda(golden, half):
+    """``install(model, fused=True, head_convs=True)`` with REAL ``Detect.m[i] = nn.Conv2d(ch, na*no, 1)`` (yolo.py:252,258):
+    the patched forward produces the raw levels with dsn_detect_head_conv1x1 (tcgen05 under --half, exact fp32 FMA otherwise);
+    they stay within the output type's rounding of the framework's own convolution, and the detections of the val.py call
+    sequence are the oracle's for exactly those levels."""
+    import torch.nn as nn
+
+    from desenet_b200 import api, patch
+    from oracle import port
+    fx = golden("real_desenet_s128.npz")
+    ns, names = standin.fake_reference_modules(f"dsn_fake_gpu_detconv_{int(half)}")
+    model = standin.Model(fx)
+    g = torch.Generator().manual_seed(11)
+    chans = (128, 256, 512)
+    feats = [torch.randn(2, c, 128 // s, 128 // s, generator=g) for c, s in zip(chans, (8, 16, 32))]
+    for i, c in enumerate(chans):
+        conv = nn.Conv2d(c, 33, 1)
+        with torch.no_grad():
+            conv.weight.copy_(torch.randn(33, c, 1, 1, generator=g) * (2.0 / c ** 0.5))
+            conv.bias.copy_(torch.randn(33, generator=g) - 3.0)
+        model.det.m[i] = conv
+        setattr(model, f"raw{i}", feats[i].clone())                       # the lookup now feeds the convs' inputs
+    model = model.cuda().eval()
+    if half:
+        model = model.half()
+    img = torch.zeros(2, 3, 128, 128)
+    with torch.no_grad():
+        xin = [getattr(model, f"raw{i}")[:2].clone() for i in range(3)]
+        want_raw = [model.det.m[i](xin[i]) for i in range(3)]             # the framework's own convolution
+        if not half:      # cuDNN's fp32 convolution runs in TF32 by default (~1e-3): compare with the exact convolution instead
+            want_raw = [torch.nn.functional.conv2d(xin[i].double().cpu(), model.det.m[i].weight.double().cpu(),
+                                                   model.det.m[i].bias.double().cpu()).float().cuda() for i in range(3)]
+    with patch.install(model=model, fused=True, modules=names, head_convs=True):
+        with torch.no_grad():
+            (ho, _), _ = model(img.cuda().half() if half else img.cuda())
+        assert isinstance(ho, api.HeadOutputs)
+        out, _, _ = standin.val_sequence(ns, model, img, torch.from_numpy(fx["target"]), half=half)
+    tol = 2e-3 if half else 2e-5
+    for got, want in zip(ho.head.levels, want_raw):
+        assert got.dtype == want.dtype and got.shape == want.shape
+        assert torch.allclose(got.float(), want.float(), rtol=tol, atol=tol * 8), (got.float() - want.float()).abs().max()
+    z = ho.z.float().cpu()
+    want_det = port.non_max_suppression(z, 0.001, 0.6, multi_label=True, nms_impl="c")
+    assert sum(d.shape[0] for d in out) > 0
+    for d, w in zip(out, want_det):
+        assert torch.equal(d.float().cpu(), w)

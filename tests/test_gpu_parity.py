@@ -585,3 +585,57 @@ def test_seg_head_conv1x1_vs_reference_fixture(dsn, golden):
     w3, b3 = torch.randn(3, 37, 1, 1, device="cuda"), torch.randn(3, device="cuda")
     ref3 = torch.nn.functional.conv2d(odd.double().cpu(), w3.double().cpu(), b3.double().cpu())
     assert torch.allclose(ops.seg_head_conv1x1(odd, w3, b3).cpu().double(), ref3, rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("bs,K,ny,nx,N", [(2, 128, 20, 20, 33), (3, 256, 40, 40, 33), (1, 512, 80, 80, 33), (2, 64, 16, 24, 255),
+                                          (1, 128, 8, 8, 16)])
+def test_detect_head_conv1x1_tensor_cores(dsn, dt, bs, K, ny, nx, N):
+    """core/models/yolo.py:252,258 under --half: tcgen05 kernel vs the exact (float64) convolution of the SAME fp16 / bf16
+    operands.  fp32 accumulation, then one rounding to the network's precision: |error| <= 1 ulp of the output type at the
+    result plus 1e-5 of the sum of |terms| (accumulation order)."""
+    from desenet_b200 import ops
+    g = torch.Generator().manual_seed(K + N + ny)
+    x = torch.randn(bs, K, ny, nx, generator=g).to(dt)
+    w = (torch.randn(N, K, 1, 1, generator=g) * (1.0 / K ** 0.5)).to(dt)
+    b = torch.randn(N, generator=g).to(dt)
+    assert ops.detect_head_conv1x1_supported(x.cuda(), N)
+    out = ops.detect_head_conv1x1(x.cuda(), w.cuda(), b.cuda())
+    assert out.dtype == dt and tuple(out.shape) == (bs, N, ny, nx)
+    exact = torch.nn.functional.conv2d(x.double(), w.double(), b.double())
+    scale = torch.nn.functional.conv2d(x.abs().double(), w.abs().double(), b.abs().double())
+    ulp = 2.0 ** (-10 if dt == torch.float16 else -7)
+    err = (out.cpu().double() - exact).abs()
+    assert (err <= ulp * exact.abs() + 1e-5 * scale + 1e-30).all(), f"max err {err.max():.3e}"
+    # partial pixel tiles / several tiles per CTA leave no stale rows: a second call on shifted data still agrees
+    x2 = torch.roll(x, 1, 0) * 0.5
+    out2 = ops.detect_head_conv1x1(x2.cuda(), w.cuda(), b.cuda())
+    exact2 = torch.nn.functional.conv2d(x2.double(), w.double(), b.double())
+    assert ((out2.cpu().double() - exact2).abs() <= ulp * exact2.abs() + 1e-5 * scale + 1e-30).all()
+
+
+def test_detect_head_conv1x1_fp32_and_filter_chain(dsn):
+    """fp32 path: exact FMA chain, within 1e-6 of the float64 convolution relative to the sum of |terms|; and the conv as
+    producer of the tail: detections from its output equal the detections from the same tensor handed over directly."""
+    from desenet_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    feats = [torch.randn(2, K, s, s, generator=g) for K, s in ((128, 20), (256, 10), (512, 5))]
+    ws = [torch.randn(33, K, 1, 1, generator=g) * (2.0 / K ** 0.5) for K in (128, 256, 512)]
+    bs_ = [torch.randn(33, generator=g) - 2.0 for _ in range(3)]
+    raws = []
+    for f, w, b in zip(feats, ws, bs_):
+        out = ops.detect_head_conv1x1(f.cuda(), w.cuda(), b.cuda())
+        exact = torch.nn.functional.conv2d(f.double(), w.double(), b.double())
+        scale = torch.nn.functional.conv2d(f.abs().double(), w.abs().double(), b.abs().double())
+        assert ((out.cpu().double() - exact).abs() <= 1e-6 * scale).all()
+        raws.append(out)
+    odd = torch.randn(1, 48, 7, 9, generator=g)                                                # plane % 4 != 0: scalar path
+    w3, b3 = torch.randn(33, 48, 1, 1, generator=g), torch.randn(33, generator=g)
+    ref3 = torch.nn.functional.conv2d(odd.double(), w3.double(), b3.double())
+    assert torch.allclose(ops.detect_head_conv1x1(odd.cuda(), w3.cuda(), b3.cuda()).cpu().double(), ref3, rtol=0, atol=1e-4)
+    ho = dsn.HeadOutputs(raws, port.DEFAULT_ANCHORS, port.DEFAULT_STRIDES)
+    dets = dsn.non_max_suppression(ho, conf_thres=0.05, iou_thres=0.45)
+    want = port.non_max_suppression(ho.z.cpu(), 0.05, 0.45, nms_impl="c")
+    assert sum(d.shape[0] for d in dets) > 0
+    for d, w_ in zip(dets, want):
+        assert torch.equal(d.cpu(), w_)
