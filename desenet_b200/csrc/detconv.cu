@@ -24,7 +24,7 @@
 //
 //   detect_head_conv_f32_kernel: fp32 activations (the reference's default precision).  Exact fp32 arithmetic, one FMA
 //   per term in channel order (what a plain fp32 convolution computes up to summation order); TF32 tensor cores would
-//   break the 1e-5 box tolerance of the north star.  One thread = 4 pixels x 12 outputs, weights in shared memory.
+//   break the 1e-5 box tolerance of the north star.  One thread = 2 pixels x 36 outputs, weights transposed in shared memory.
 #include <algorithm>
 
 #include "common.cuh"
@@ -34,17 +34,19 @@ namespace dsn {
 // ---------------------------------------------------------------------------------------------------------------------
 // fp32: CUDA cores, exact FMA chain
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kConvG = 12;      // outputs per thread (three groups cover the 33 channels of nc = 6)
+constexpr int kConvG = 36;      // outputs per thread: one group covers the 33 channels of nc = 6 (input read once)
 
+// One thread = V pixels x kConvG outputs.  Weights sit transposed in shared memory, sw[k][kConvG], so a k step costs
+// kConvG / 4 LDS.128 (broadcast) for V * kConvG FMAs: FMA-bound, not LDS-bound.
 template <int V>
 __global__ void __launch_bounds__(256) detect_head_conv_f32_kernel(const float *__restrict__ x, const float *__restrict__ weight,
                                                                    const float *__restrict__ bias, int K, int N, long long plane,
                                                                    float *__restrict__ out) {
-    extern __shared__ float sw[];                      // [kConvG][K] of this output group (rows >= N: zero)
+    extern __shared__ __align__(16) float sw[];        // [K][kConvG] of this output group (columns >= N: zero)
     const int n0 = blockIdx.z * kConvG;
     for (int i = threadIdx.x; i < kConvG * K; i += blockDim.x) {
-        const int n = n0 + i / K;
-        sw[i] = n < N ? weight[(size_t)n * K + (i % K)] : 0.f;
+        const int c = i / K, k = i - c * K;            // coalesced read of weight row n0 + c
+        sw[k * kConvG + c] = n0 + c < N ? weight[(size_t)(n0 + c) * K + k] : 0.f;
     }
     __syncthreads();
     const int b = blockIdx.y;
@@ -56,27 +58,33 @@ __global__ void __launch_bounds__(256) detect_head_conv_f32_kernel(const float *
     for (int c = 0; c < kConvG; ++c)
 #pragma unroll
         for (int j = 0; j < V; ++j) acc[c][j] = (bias && n0 + c < N) ? bias[n0 + c] : 0.f;
-#pragma unroll 4
+#pragma unroll 8
     for (int k = 0; k < K; ++k) {
         float v[V];
-        if constexpr (V == 4) {
-            const float4 t = ldg_stream_f4(px + (size_t)k * plane);
-            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        if constexpr (V == 2) {
+            const float2 t = __ldg(reinterpret_cast<const float2 *>(px + (size_t)k * plane));
+            v[0] = t.x; v[1] = t.y;
         } else {
             v[0] = ldg_stream_f1(px + (size_t)k * plane);
         }
+        const float4 *wk = reinterpret_cast<const float4 *>(sw + k * kConvG);
 #pragma unroll
-        for (int c = 0; c < kConvG; ++c) {
-            const float wk = sw[c * K + k];
+        for (int c4 = 0; c4 < kConvG / 4; ++c4) {
+            const float4 w4 = wk[c4];
 #pragma unroll
-            for (int j = 0; j < V; ++j) acc[c][j] = __fmaf_rn(wk, v[j], acc[c][j]);
+            for (int j = 0; j < V; ++j) {
+                acc[c4 * 4 + 0][j] = __fmaf_rn(w4.x, v[j], acc[c4 * 4 + 0][j]);
+                acc[c4 * 4 + 1][j] = __fmaf_rn(w4.y, v[j], acc[c4 * 4 + 1][j]);
+                acc[c4 * 4 + 2][j] = __fmaf_rn(w4.z, v[j], acc[c4 * 4 + 2][j]);
+                acc[c4 * 4 + 3][j] = __fmaf_rn(w4.w, v[j], acc[c4 * 4 + 3][j]);
+            }
         }
     }
 #pragma unroll
     for (int c = 0; c < kConvG; ++c) {
         if (n0 + c < N) {
             float *po = out + ((size_t)b * N + n0 + c) * plane + u * V;
-            if constexpr (V == 4) *reinterpret_cast<float4 *>(po) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+            if constexpr (V == 2) *reinterpret_cast<float2 *>(po) = make_float2(acc[c][0], acc[c][1]);
             else po[0] = acc[c][0];
         }
     }
@@ -358,16 +366,20 @@ extern "C" __attribute__((visibility("default"))) int dsn_detect_head_conv1x1(co
     if (dtype == DSN_F32) {
         if ((((uintptr_t)features | (uintptr_t)weight | (uintptr_t)out) & 3) != 0) return DSN_E_ALIGN;
         const size_t smem = (size_t)kConvG * K * sizeof(float);
-        if (smem > 48 * 1024) return DSN_E_UNSUPPORTED;
-        const bool vec = plane % 4 == 0 && (((uintptr_t)features | (uintptr_t)out) & 15) == 0;
-        const long long units = vec ? plane / 4 : plane;
+        if (smem > 160 * 1024) return DSN_E_UNSUPPORTED;
+        const bool vec = plane % 2 == 0 && (((uintptr_t)features | (uintptr_t)out) & 7) == 0;
+        const long long units = vec ? plane / 2 : plane;
         dim3 grid((unsigned)((units + 255) / 256), bs, (N + kConvG - 1) / kConvG);
-        if (vec)
-            detect_head_conv_f32_kernel<4><<<grid, 256, smem, st>>>(static_cast<const float *>(features), static_cast<const float *>(weight), bias, K,
+        static DeviceOnce once2, once1;
+        if (vec) {
+            if (int rc = raise_dynamic_smem(once2, detect_head_conv_f32_kernel<2>, 160 * 1024)) return rc;
+            detect_head_conv_f32_kernel<2><<<grid, 256, smem, st>>>(static_cast<const float *>(features), static_cast<const float *>(weight), bias, K,
                                                                     N, plane, static_cast<float *>(out));
-        else
+        } else {
+            if (int rc = raise_dynamic_smem(once1, detect_head_conv_f32_kernel<1>, 160 * 1024)) return rc;
             detect_head_conv_f32_kernel<1><<<grid, 256, smem, st>>>(static_cast<const float *>(features), static_cast<const float *>(weight), bias, K,
                                                                     N, plane, static_cast<float *>(out));
+        }
         DSN_CHECK_LAUNCH();
         return DSN_OK;
     }

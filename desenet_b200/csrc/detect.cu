@@ -333,9 +333,6 @@ __global__ void __launch_bounds__(kDenseThreads, 3) filter_dense_kernel(const He
 #ifndef DSN_TMA_STAGES
 #define DSN_TMA_STAGES 2
 #endif
-#ifndef DSN_FILTER_LDGSTS
-#define DSN_FILTER_LDGSTS 0
-#endif
 constexpr int kTmaWarps = DSN_TMA_WARPS;     // per CTA
 constexpr int kTmaStages = DSN_TMA_STAGES;   // tiles in flight per warp (more stages = fewer resident warps: measured worse)
 constexpr int kTmaKbuf = 128;                // keys staged per warp
@@ -429,31 +426,9 @@ __global__ void __launch_bounds__(kTmaWarps * 32) filter_dense_tma_kernel(const 
             }
         }
     };
-#if DSN_FILTER_LDGSTS
-    // measurement variant: the same ring fed by per-lane 16-byte cp.async (LDGSTS) instead of bulk copies
-    auto issue_ldgsts = [&](const TileCursor &c, int st) {
-        const TmaLevel L = lv[c.l];
-        const int cell0 = c.t * kTmaTileCells;
-        constexpr int kVec = 16 / (int)sizeof(T);
-        const int ncell = min(kTmaTileCells, L.plane - cell0);
-        if (lane * kVec < ncell) {
-            const T *src = static_cast<const T *>(L.raw) + ((size_t)(c.b * g.na + c.a) * g.no + 4) * L.plane + cell0 + lane * kVec;
-            uint32_t dst = flt_smem_u32(stages + (size_t)st * planes * kTmaTileCells + lane * kVec);
-            for (int pl = 0; pl < planes; ++pl) {
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-                src += L.plane;
-                dst += kTmaTileCells * (unsigned)sizeof(T);
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-#define DSN_ISSUE issue_ldgsts
-#else
-#define DSN_ISSUE issue
-#endif
     const int prefill = min(kTmaStages, my_tiles);
     for (int i = 0; i < prefill; ++i) {
-        DSN_ISSUE(prod, i);
+        issue(prod, i);
         advance(prod);
     }
     int issued = prefill;
@@ -518,12 +493,6 @@ __global__ void __launch_bounds__(kTmaWarps * 32) filter_dense_tma_kernel(const 
             kout = f.keys + (size_t)kb * f.cap;
             image_consts();
         }
-#if DSN_FILTER_LDGSTS
-        static_assert(kTmaStages == 2, "the cp.async variant waits with immediates for a two-stage ring");
-        if (issued > it + 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
-        else asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
-#else
         {
             const uint32_t bar = flt_smem_u32(&full[st]);
             asm volatile(
@@ -538,7 +507,6 @@ __global__ void __launch_bounds__(kTmaWarps * 32) filter_dense_tma_kernel(const 
                 "r"(parity)
                 : "memory");
         }
-#endif
         const TmaLevel L = lv[cons.l];
         const int cell0 = cons.t * kTmaTileCells;
         const T *tile = stages + (size_t)st * planes * kTmaTileCells;              // [planes][128]: row 0 objectness, 1 + c class c
@@ -586,16 +554,13 @@ __global__ void __launch_bounds__(kTmaWarps * 32) filter_dense_tma_kernel(const 
         }
         __syncwarp();                                    // every lane is done with the stage
         if (issued < my_tiles) {                         // refill it with the tile kTmaStages ahead
-#if !DSN_FILTER_LDGSTS
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#endif
-            DSN_ISSUE(prod, st);
+            issue(prod, st);
             advance(prod);
             ++issued;
         }
         advance(cons);
     }
-#undef DSN_ISSUE
     if (np > 0) exact_batch(np);
     if (nk > 0) flush();
 }

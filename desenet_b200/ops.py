@@ -483,7 +483,7 @@ def detect_head_conv1x1_supported(features: torch.Tensor, n_out: int) -> bool:
         return False
     K, plane = int(features.shape[1]), int(features.shape[2]) * int(features.shape[3])
     if features.dtype == torch.float32:
-        return 12 * K * 4 <= 48 * 1024
+        return 36 * K * 4 <= 160 * 1024
     n_pad = (n_out + 15) // 16 * 16
     return K % 64 == 0 and plane % 8 == 0 and 3 * 16384 + 1024 + n_pad * K * 2 <= 200 * 1024
 

@@ -188,7 +188,10 @@ def _detect_head_conv(conv: nn.Module, x: torch.Tensor) -> torch.Tensor:
     the kernel takes), else the module itself."""
     if (isinstance(conv, nn.Conv2d) and tuple(conv.kernel_size) == (1, 1) and tuple(conv.stride) == (1, 1)
             and tuple(conv.padding) == (0, 0) and tuple(conv.dilation) == (1, 1) and conv.groups == 1
-            and x.dtype == conv.weight.dtype and ops.detect_head_conv1x1_supported(x, conv.out_channels)):
+            and x.dtype == conv.weight.dtype and ops.detect_head_conv1x1_supported(x, conv.out_channels)
+            # fp32: the kernel is an exact FMA chain; it stands in for the framework's convolution only when that one is
+            # exact fp32 as well (cuDNN's default for fp32 convolutions is TF32, a different precision class and faster)
+            and (x.dtype != torch.float32 or not torch.backends.cudnn.allow_tf32)):
         return ops.detect_head_conv1x1(x, conv.weight, conv.bias)
     return conv(x)
 

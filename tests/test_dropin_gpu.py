@@ -243,11 +243,16 @@ def test_head_convs_detect_convs_on_cuda(golden, half):
         if not half:      # cuDNN's fp32 convolution runs in TF32 by default (~1e-3): compare with the exact convolution instead
             want_raw = [torch.nn.functional.conv2d(xin[i].double().cpu(), model.det.m[i].weight.double().cpu(),
                                                    model.det.m[i].bias.double().cpu()).float().cuda() for i in range(3)]
-    with patch.install(model=model, fused=True, modules=names, head_convs=True):
-        with torch.no_grad():
-            (ho, _), _ = model(img.cuda().half() if half else img.cuda())
-        assert isinstance(ho, api.HeadOutputs)
-        out, _, _ = standin.val_sequence(ns, model, img, torch.from_numpy(fx["target"]), half=half)
+    tf32_was = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False            # fp32 case: the exact kernel stands in for an exact fp32 convolution only
+    try:
+        with patch.install(model=model, fused=True, modules=names, head_convs=True):
+            with torch.no_grad():
+                (ho, _), _ = model(img.cuda().half() if half else img.cuda())
+            assert isinstance(ho, api.HeadOutputs)
+            out, _, _ = standin.val_sequence(ns, model, img, torch.from_numpy(fx["target"]), half=half)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32_was
     tol = 2e-3 if half else 2e-5
     for got, want in zip(ho.head.levels, want_raw):
         assert got.dtype == want.dtype and got.shape == want.shape
