@@ -27,6 +27,9 @@ SIGNATURES = {
     "dsn_nms_levels": (c_int, [_FLOATPP, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_float), POINTER(c_float), c_int, c_int,
                                c_int, c_int, c_void_p, c_int64, c_void_p, c_float, c_double, c_int, c_int, c_int, c_float,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dsn_nms_levels_cta": (c_int, [_FLOATPP, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_float), POINTER(c_float), c_int, c_int,
+                                   c_int, c_int, c_void_p, c_int64, c_void_p, c_float, c_double, c_int, c_int, c_int, c_float,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "dsn_append_label_keys": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_float, POINTER(c_uint64), c_void_p, c_int64,
                                       c_void_p, c_void_p]),
     "dsn_nms_levels_labels": (c_int, [_FLOATPP, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_float), POINTER(c_float), c_int, c_int,

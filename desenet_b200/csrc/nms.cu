@@ -51,18 +51,30 @@ __global__ void append_label_keys_kernel(const float *__restrict__ labels, const
 
 using namespace dsn;
 
+extern "C" __attribute__((visibility("default"))) int dsn_nms_levels_cta(const void *const *raw, int dtype, const int *ny, const int *nx,
+                              const float *stride, const float *anchor_grid, int nl, int bs, int na, int no, const uint64_t *keys,
+                              int64_t cap, const int *counts, float conf_thres, double iou_thres, int agnostic,
+                              int max_nms, int max_det, float max_wh, const unsigned int *cut_hi, const int *cut_dropped,
+                              float *det, int *det_count, int cta_threads, void *stream) {
+    if (cta_threads != 0 && cta_threads != 256 && cta_threads != 512) return DSN_E_INVALID;
+    // Default rule: no confidence cut = the detect setting (a few hundred candidates per image, the seg mask kernel of another
+    // batch running next to it): 256-thread CTAs, which find room between that kernel's short-lived CTAs (see nms_small.cu).
+    // With a cut: thousands of candidates per image, 512.  The 256-thread instantiation carries no cut plumbing.
+    const bool small = cta_threads == 256 || (cta_threads == 0 && !cut_dropped);
+    if (small && !cut_dropped)
+        return dsn_nms_levels_small(raw, dtype, ny, nx, stride, anchor_grid, nl, bs, na, no, keys, cap, counts, conf_thres, iou_thres, agnostic,
+                                    max_nms, max_det, max_wh, det, det_count, stream);
+    return nms_levels_impl(raw, dtype, ny, nx, stride, anchor_grid, nl, bs, na, no, keys, cap, counts, conf_thres, iou_thres, agnostic, max_nms,
+                           max_det, max_wh, cut_hi, cut_dropped, nullptr, 0, det, det_count, stream);
+}
+
 extern "C" __attribute__((visibility("default"))) int dsn_nms_levels(const void *const *raw, int dtype, const int *ny, const int *nx, const float *stride,
                               const float *anchor_grid, int nl, int bs, int na, int no, const uint64_t *keys,
                               int64_t cap, const int *counts, float conf_thres, double iou_thres, int agnostic,
                               int max_nms, int max_det, float max_wh, const unsigned int *cut_hi, const int *cut_dropped,
                               float *det, int *det_count, void *stream) {
-    // No confidence cut = the detect setting (a few hundred candidates per image): 256-thread CTAs, which find room next to
-    // the streaming kernels of the other batches in flight (see nms_small.cu).  With a cut: thousands of candidates, 512.
-    if (!cut_dropped)
-        return dsn_nms_levels_small(raw, dtype, ny, nx, stride, anchor_grid, nl, bs, na, no, keys, cap, counts, conf_thres, iou_thres, agnostic,
-                                    max_nms, max_det, max_wh, det, det_count, stream);
-    return nms_levels_impl(raw, dtype, ny, nx, stride, anchor_grid, nl, bs, na, no, keys, cap, counts, conf_thres, iou_thres, agnostic, max_nms,
-                           max_det, max_wh, cut_hi, cut_dropped, nullptr, 0, det, det_count, stream);
+    return dsn_nms_levels_cta(raw, dtype, ny, nx, stride, anchor_grid, nl, bs, na, no, keys, cap, counts, conf_thres, iou_thres, agnostic, max_nms,
+                              max_det, max_wh, cut_hi, cut_dropped, det, det_count, 0, stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int dsn_nms_levels_labels(const void *const *raw, int dtype, const int *ny, const int *nx, const float *stride,

@@ -267,7 +267,8 @@ def append_label_keys(head: Head, padded, conf_thres: float, classes, keys: torc
 def nms_levels(head: Head, keys: torch.Tensor, counts: torch.Tensor, conf_thres: float, iou_thres: float,
                agnostic: bool, max_det: int, max_nms: int = MAX_NMS, max_wh: float = MAX_WH,
                det: Optional[torch.Tensor] = None, det_count: Optional[torch.Tensor] = None, cut: Optional[ConfCut] = None,
-               labels=None):
+               labels=None, cta_threads: int = 0):
+    """``cta_threads``: 0 = the library's rule (256-thread CTAs without a confidence cut, 512 with one), or 256 / 512."""
     lib = _lib.load()
     with torch.cuda.device(head.device):
         if det is None:
@@ -283,12 +284,12 @@ def nms_levels(head: Head, keys: torch.Tensor, counts: torch.Tensor, conf_thres:
                                            _stream(head.device))
             _lib.check(rc, "dsn_nms_levels_labels")
             return det, det_count
-        rc = lib.dsn_nms_levels(head.c_raw, head.dtype_code, head.c_ny, head.c_nx, head.c_stride, head.c_anchor, head.nl, head.bs,
-                                head.na, head.no, _ptr(keys), int(keys.shape[1]), _ptr(counts), float(conf_thres),
-                                float(iou_thres), int(bool(agnostic)), int(max_nms), int(max_det), float(max_wh),
-                                _ptr(cut.cut_hi if cut else None), _ptr(cut.dropped if cut else None), _ptr(det), _ptr(det_count),
-                                _stream(head.device))
-    _lib.check(rc, "dsn_nms_levels")
+        rc = lib.dsn_nms_levels_cta(head.c_raw, head.dtype_code, head.c_ny, head.c_nx, head.c_stride, head.c_anchor, head.nl, head.bs,
+                                    head.na, head.no, _ptr(keys), int(keys.shape[1]), _ptr(counts), float(conf_thres),
+                                    float(iou_thres), int(bool(agnostic)), int(max_nms), int(max_det), float(max_wh),
+                                    _ptr(cut.cut_hi if cut else None), _ptr(cut.dropped if cut else None), _ptr(det), _ptr(det_count),
+                                    int(cta_threads), _stream(head.device))
+    _lib.check(rc, "dsn_nms_levels_cta")
     return det, det_count
 
 

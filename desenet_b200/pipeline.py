@@ -110,8 +110,11 @@ class PostProcessor:
                                       cut=self.cut)
         ops.filter_levels(head, kw["conf_thres"], kw["multi_label"], kw["classes"], cap=int(self.keys.shape[1]),
                           keys=self.keys, counts=self.counts, cut=cut)
+        # eval mode: the persistent eval seg kernel leaves no room for a second kernel's CTAs on an SM, so the NMS runs
+        # before / after it at full width and the 512-thread CTA (fastest per image) is the right one; in detect mode the
+        # library's rule applies (256 threads between the short-lived CTAs of the mask kernel)
         ops.nms_levels(head, self.keys, self.counts, kw["conf_thres"], kw["iou_thres"], kw["agnostic"], kw["max_det"],
-                       det=self.det, det_count=self.det_count, cut=cut)
+                       det=self.det, det_count=self.det_count, cut=cut, cta_threads=512 if self.mode == "eval" else 0)
         if cut is not None:
             # images the sampled cut starved (det_count == -2) are redone uncut on the device, inside the same enqueue /
             # graph: a negative count never reaches a consumer (HostPipeline, DetEvaluator, graph replay)

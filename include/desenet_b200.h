@@ -133,6 +133,15 @@ int dsn_nms_levels(const void *const *raw, int dtype, const int *ny, const int *
                    const uint64_t *keys, int64_t cap, const int *counts, float conf_thres,
                    double iou_thres, int agnostic, int max_nms, int max_det, float max_wh,
                    const unsigned int *cut_hi, const int *cut_dropped, float *det, int *det_count, void *stream);
+/* Same, with the CTA size chosen by the caller: cta_threads = 512 (fastest per image), 256 (16 K registers per image: finds
+ * room next to the short-lived CTAs of a concurrent streaming kernel) or 0 = dsn_nms_levels' own rule (256 when no
+ * confidence cut is given, 512 otherwise).  Results are identical. */
+int dsn_nms_levels_cta(const void *const *raw, int dtype, const int *ny, const int *nx, const float *stride,
+                       const float *anchor_grid, int nl, int bs, int na, int no,
+                       const uint64_t *keys, int64_t cap, const int *counts, float conf_thres,
+                       double iou_thres, int agnostic, int max_nms, int max_det, float max_wh,
+                       const unsigned int *cut_hi, const int *cut_dropped, float *det, int *det_count, int cta_threads,
+                       void *stream);
 
 /* A-priori labels on the raw-level path (general.py:690-696; scripts/val.py:228 passes them with save_hybrid): label j
  * of image b acts as prediction row A + j with obj = 1 and a one-hot class, i.e. one candidate of confidence 1.0.

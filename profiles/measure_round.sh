@@ -36,4 +36,13 @@ for c in 2 3 4 5; do
   done
   rm -f $O/${R}_ncu_full_cfg$c.ncu-rep $O/${R}_ncu_full_cfg$c.ncu-rep.tmp
 done
+# Detect head convs (tcgen05 kernel vs the framework's cuDNN convolution): correctness + timing, then one capture per level
+timeout 300 python profiles/experiments/check_detconv.py > $O/${R}_detconv.log 2>&1; tail -12 $O/${R}_detconv.log
+timeout 120 python profiles/experiments/prof_detconv.py > /dev/null 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:'detect_head_conv_umma' -c 6 -o $O/${R}_ncu_full_detconv -f \
+    python profiles/experiments/prof_detconv.py > $O/${R}_ncu_full_detconv.log 2>&1
+ncu -i $O/${R}_ncu_full_detconv.ncu-rep --page raw --csv > $O/${R}_ncu_full_detconv_raw.csv 2>/dev/null
+ncu -i $O/${R}_ncu_full_detconv.ncu-rep --page source --csv --launch-skip 1 --launch-count 1 > $O/${R}_ncu_src_detconv_umma.csv 2>/dev/null
+gzip -f $O/${R}_ncu_src_detconv_umma.csv
+rm -f $O/${R}_ncu_full_detconv.ncu-rep
 du -sh $O; ls -la $O | grep ${R}_ | head -80

@@ -36,7 +36,7 @@ if os.path.exists(ll):
         a = agg.setdefault(k, [0, 0.0])
         a[0] += 1
         a[1] += ns
-    mine = {k: v for k, v in agg.items() if "dsn::" in k}
+    mine = {k: v for k, v in agg.items() if "dsn::" in k or "nms_t" in k}       # ncu prints the inline-namespace NMS kernels without the outer dsn::
     total = sum(v[1] for v in mine.values()) or 1.0
     shutil.copy(ll, os.path.join(P, f"{R}_launches_cfg2.csv"))
     with open(os.path.join(P, f"{R}_launches_cfg2_summary.csv"), "w") as f:
@@ -97,6 +97,29 @@ for c in (2, 3, 4, 5):
         except Exception:
             pass
     summary[f"cfg{c}"] = out
+# ---- Detect head conv (tcgen05): timing log + --set full capture of the three levels ------------------------------------
+for name in (f"{R}_detconv.log",):
+    if os.path.exists(os.path.join(O, name)):
+        shutil.copy(os.path.join(O, name), os.path.join(P, name))
+raw = os.path.join(O, f"{R}_ncu_full_detconv_raw.csv")
+if os.path.exists(raw) and os.path.getsize(raw) > 0:
+    rows = list(csv.reader(open(raw, errors="replace")))
+    hdr, units = rows[0], rows[1]
+    shutil.copy(raw, os.path.join(P, f"{R}_ncu_full_detconv_raw.csv"))
+    out = []
+    for r in rows[2:]:
+        if len(r) > hdr.index("Kernel Name"):
+            e = OrderedDict(kernel=r[hdr.index("Kernel Name")])
+            for w in WANT + ["sm__inst_executed_pipe_tensor.sum"]:
+                if w in hdr:
+                    e[w] = r[hdr.index(w)] + " " + units[hdr.index(w)]
+            out.append(e)
+    summary["detconv_fp16_bs64_levels_80_40_20"] = out
+# ---- source pages kept as evidence (gzip, small) --------------------------------------------------------------------------
+for name in os.listdir(O):
+    if name.startswith(f"{R}_ncu_src_") and name.endswith(".csv.gz") and os.path.getsize(os.path.join(O, name)) < 400 * 1024:
+        os.makedirs(os.path.join(P, "src_pages"), exist_ok=True)
+        shutil.copy(os.path.join(O, name), os.path.join(P, "src_pages", name))
 if summary:
     json.dump(summary, open(os.path.join(P, f"{R}_ncu_full_summary.json"), "w"), indent=1)
     traffic["note"] = ("PER LAUNCH: dram__bytes_read.sum + dram__bytes_write.sum of one launch at `images_per_launch`, from ncu "
