@@ -11,6 +11,7 @@
 #include <cstring>
 
 #include <cooperative_groups.h>
+#include <cuda.h>            // CUtensorMap (types only: the encoder is reached through cudaGetDriverEntryPoint)
 
 #include "common.cuh"
 #include "filter_core.cuh"
@@ -333,6 +334,9 @@ __global__ void __launch_bounds__(kDenseThreads, 3) filter_dense_kernel(const He
 #ifndef DSN_TMA_STAGES
 #define DSN_TMA_STAGES 2
 #endif
+#ifndef DSN_FILTER_TENSORMAP
+#define DSN_FILTER_TENSORMAP 1      // one 3-D tensor-map copy per tile instead of 1 + nc bulk copies
+#endif
 constexpr int kTmaWarps = DSN_TMA_WARPS;     // per CTA
 constexpr int kTmaStages = DSN_TMA_STAGES;   // tiles in flight per warp (more stages = fewer resident warps: measured worse)
 constexpr int kTmaKbuf = 128;                // keys staged per warp
@@ -350,15 +354,24 @@ struct TileCursor {
     int b, l, a, t;
 };
 
+// One 3-D tensor map per level over the raw head output (cells, channels, images): a tile = ONE
+// cp.async.bulk.tensor.3d with box (128 cells, 1 + nc channels, 1 image) starting at (cell0, a * no + 4, b) - the same
+// bytes in the same shared-memory order as the per-plane bulk copies, for one issued instruction instead of 1 + nc
+// (each a 10-instruction uniform-register sequence).  Cells beyond the plane are zero-filled and counted.
+struct FilterTensorMaps {
+    CUtensorMap m[DSN_MAX_LEVELS];
+};
+
 // per-warp shared memory: stages [kTmaStages][planes][128] elements | kbuf | pending (class logit, obj logit, ref) | mbarriers
 __host__ __device__ inline size_t tma_warp_bytes(int nc, int esize) {
     const size_t stage_bytes = (size_t)(nc + 1) * kTmaTileCells * esize;
     return ((kTmaStages * stage_bytes + kTmaKbuf * 8 + kTmaPend * 12 + kTmaStages * 8) + 127) & ~(size_t)127;
 }
 
-template <typename T>
+template <typename T, bool TENSOR>
 __global__ void __launch_bounds__(kTmaWarps * 32) filter_dense_tma_kernel(const HeadGeom g, const FilterOut f, const int tiles_per_image,
-                                                                         const long long total_tiles, const int tiles_per_warp) {
+                                                                         const long long total_tiles, const int tiles_per_warp,
+                                                                         const __grid_constant__ FilterTensorMaps maps) {
     extern __shared__ __align__(128) unsigned char tma_smem[];
     __shared__ TmaLevel lv[DSN_MAX_LEVELS];
     const int nc = g.no - 5;
@@ -409,6 +422,18 @@ __global__ void __launch_bounds__(kTmaWarps * 32) filter_dense_tma_kernel(const 
     TileCursor prod = cons;
     // lane 0 posts the byte count and issues one bulk copy per plane (512-byte rows; row 0: objectness)
     auto issue = [&](const TileCursor &c, int st) {
+        if (TENSOR) {
+            if (lane == 0) {
+                const uint32_t bar = flt_smem_u32(&full[st]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)stage_bytes) : "memory");
+                asm volatile(
+                    "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                        flt_smem_u32(stages + (size_t)st * planes * kTmaTileCells)),
+                    "l"(reinterpret_cast<uint64_t>(&maps.m[c.l])), "r"(c.t * kTmaTileCells), "r"(c.a * g.no + 4), "r"(c.b), "r"(bar)
+                    : "memory");
+            }
+            return;
+        }
         if (lane == 0) {
             const TmaLevel L = lv[c.l];
             const int cell0 = c.t * kTmaTileCells;
@@ -826,6 +851,47 @@ extern "C" __attribute__((visibility("default"))) int dsn_conf_cut_levels(const 
     return DSN_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is not linked)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        (void)cudaGetLastError();
+    }
+    return fn;
+}
+// maps of all levels; false when the encoder is missing or refuses a level (the caller then uses the per-plane bulk copies)
+static bool make_filter_tensor_maps(const HeadGeom &g, int nl, int bs, int na, int no, FilterTensorMaps &maps) {
+#if DSN_FILTER_TENSORMAP
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return false;
+    const int es = dtype_size(g.dtype);
+    const CUtensorMapDataType dt = g.dtype == DSN_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                                       : (g.dtype == DSN_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+    for (int l = 0; l < nl; ++l) {
+        const cuuint64_t dims[3] = {(cuuint64_t)g.plane[l], (cuuint64_t)na * no, (cuuint64_t)bs};
+        const cuuint64_t strides[2] = {(cuuint64_t)g.plane[l] * es, (cuuint64_t)g.plane[l] * es * na * no};
+        const cuuint32_t box[3] = {(cuuint32_t)kTmaTileCells, (cuuint32_t)(no - 4), 1u};
+        const cuuint32_t estr[3] = {1u, 1u, 1u};
+        if (enc(&maps.m[l], dt, 3, const_cast<void *>(g.raw[l]), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    return true;
+#else
+    (void)g; (void)nl; (void)bs; (void)na; (void)no; (void)maps;
+    return false;
+#endif
+}
+
 template <typename T>
 static int launch_filter(HeadGeom &g, const FilterOut &f, float conf_thres, int nl, int bs, int na, int no, cudaStream_t st) {
     const bool vec = geom_vec4(g);
@@ -844,17 +910,24 @@ static int launch_filter(HeadGeom &g, const FilterOut &f, float conf_thres, int 
         for (int l = 0; l < nl; ++l) tiles_per_image += na * ((g.plane[l] + kTmaTileCells - 1) / kTmaTileCells);
         const long long total_tiles = (long long)bs * tiles_per_image;
         const size_t smem = tma_warp_bytes(nc, (int)sizeof(T)) * kTmaWarps;
-        static DeviceOnce once;               // per element type
-        if (int rc2 = raise_dynamic_smem(once, filter_dense_tma_kernel<T>, 200 * 1024)) return rc2;
-        int occ = 0;
-        DSN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, filter_dense_tma_kernel<T>, kTmaWarps * 32, smem));
-        if (occ < 1) occ = 1;
+        FilterTensorMaps maps;                  // a by-value kernel argument (captured with the launch in a CUDA graph)
+        const bool tensor = make_filter_tensor_maps(g, nl, bs, na, no, maps);
+        static DeviceOnce once_t, once_b;       // per element type and form
+        if (int rc2 = tensor ? raise_dynamic_smem(once_t, filter_dense_tma_kernel<T, true>, 200 * 1024)
+                             : raise_dynamic_smem(once_b, filter_dense_tma_kernel<T, false>, 200 * 1024))
+            return rc2;
+        // resident CTAs per SM from the resources themselves (the occupancy API answers for the carveout in force when it is
+        // called, which is not yet this kernel's before its first launch): 227 KB of shared memory, 1 KB reserved per CTA
+        const int occ = std::max(1, std::min((int)((227 * 1024) / (smem + 1024)), 2048 / (kTmaWarps * 32)));
         // a warp takes a contiguous range of at least kTmaStages + 1 tiles; the grid is what the SMs hold at once
         const long long max_warps = (long long)sm_count_current_device() * occ * kTmaWarps;
         long long tpw = std::max<long long>(kTmaStages + 1, (total_tiles + max_warps - 1) / max_warps);
         const long long warps = (total_tiles + tpw - 1) / tpw;
         const long long grid = (warps + kTmaWarps - 1) / kTmaWarps;
-        filter_dense_tma_kernel<T><<<(unsigned)grid, kTmaWarps * 32, smem, st>>>(g, f, tiles_per_image, total_tiles, (int)tpw);
+        if (tensor)
+            filter_dense_tma_kernel<T, true><<<(unsigned)grid, kTmaWarps * 32, smem, st>>>(g, f, tiles_per_image, total_tiles, (int)tpw, maps);
+        else
+            filter_dense_tma_kernel<T, false><<<(unsigned)grid, kTmaWarps * 32, smem, st>>>(g, f, tiles_per_image, total_tiles, (int)tpw, maps);
         DSN_CHECK_LAUNCH();
         return DSN_OK;
     }

@@ -124,6 +124,13 @@ def test_nms_fused_equals_strict_and_oracle(dsn, golden, name):
         det, dc = dsn.ops.nms_levels(ho.head, keys, counts, kw["conf_thres"], kw["iou_thres"], kw.get("agnostic", False),
                                      kw.get("max_det", 300))
         two = [det[i, :int(dc[i])] for i in range(det.shape[0])]
+        # both CTA sizes of the NMS kernel (dsn_nms_levels_cta: 256 / 512 threads) return the same rows
+        for cta in (256, 512):
+            det_c, dc_c = dsn.ops.nms_levels(ho.head, keys, counts, kw["conf_thres"], kw["iou_thres"], kw.get("agnostic", False),
+                                             kw.get("max_det", 300), cta_threads=cta)
+            assert torch.equal(dc_c, dc), f"{name} cta {cta} {kw}"
+            for i in range(det.shape[0]):
+                assert torch.equal(det_c[i, :int(dc[i])], det[i, :int(dc[i])]), f"{name} cta {cta} {kw} image {i}"
         want = port.non_max_suppression(z.cpu(), nms_impl="c", **kw)
         assert_dets_equal(strict, [w.numpy() for w in want], f"{name} strict {kw}")
         assert_dets_equal(fused, [w.numpy() for w in want], f"{name} fused {kw}")
