@@ -341,7 +341,7 @@ constexpr int kTmaWarps = DSN_TMA_WARPS;     // per CTA
 constexpr int kTmaStages = DSN_TMA_STAGES;   // tiles in flight per warp (more stages = fewer resident warps: measured worse)
 constexpr int kTmaKbuf = 128;                // keys staged per warp
 constexpr int kTmaTileCells = 128;
-constexpr int kTmaPend = 64;                 // pending (cell, class) pairs per warp: < 32 between tiles, <= 63 inside one
+constexpr int kTmaPend = 80;                 // pending (cell, class) pairs per warp: < 32 between tiles
 
 struct TmaLevel {
     const void *raw;
@@ -561,21 +561,48 @@ __global__ void __launch_bounds__(kTmaWarps * 32) filter_dense_tma_kernel(const 
         // ---- pairs above the bound -> pending list, one per lane and round; full batches of 32 go through the exact pass ---
         const unsigned int row0 = (unsigned)(L.row_off + cons.a * L.plane + cell0) + (unsigned)lane * 4u;
         const int top = 4 * nc - 1;
-        while (__any_sync(0xffffffffu, mask != 0)) {
-            const bool have = mask != 0;
-            const unsigned int bal = __ballot_sync(0xffffffffu, have);
-            if (have) {
-                const int pos = 31 - __clz(mask);        // highest set bit = lowest pair index
-                mask &= ~(1u << pos);
-                const int pr = top - pos, ci = pr >> 2, k = pr & 3;
-                const int slot = np + __popc(bal & lt);
-                pend_v[slot] = Elem<T>::cvt(tile[(1 + ci) * kTmaTileCells + lane * 4 + k]);
-                pend_o[slot] = k == 0 ? ol[0] : (k == 1 ? ol[1] : (k == 2 ? ol[2] : ol[3]));
-                pend_r[slot] = (row0 + (unsigned)k) * (unsigned)nc + (unsigned)ci;
+        // pending-list entry of the pair at bit `pos` of this lane's mask
+        auto put = [&](int slot, int pos) {
+            const int pr = top - pos, ci = pr >> 2, k = pr & 3;
+            pend_v[slot] = Elem<T>::cvt(tile[(1 + ci) * kTmaTileCells + lane * 4 + k]);
+            pend_o[slot] = k == 0 ? ol[0] : (k == 1 ? ol[1] : (k == 2 ? ol[2] : ol[3]));
+            pend_r[slot] = (row0 + (unsigned)k) * (unsigned)nc + (unsigned)ci;
+        };
+        if (__any_sync(0xffffffffu, mask != 0)) {
+            const int mine = __popc(mask);
+            int incl = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += up;
             }
-            np += __popc(bal);
-            __syncwarp();
-            if (np >= 32) exact_batch(32);
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (np + total <= kTmaPend) {
+                // the usual case (a few dozen pairs): every lane appends all of its pairs at once behind one warp scan
+                int slot = np + incl - mine;
+                for (unsigned int m = mask; m;) {
+                    const int pos = 31 - __clz(m);           // highest set bit = lowest pair index
+                    m &= ~(1u << pos);
+                    put(slot++, pos);
+                }
+                np += total;
+                __syncwarp();
+                while (np >= 32) exact_batch(32);
+            } else {
+                // dense tile: one pair per lane and round, full batches drained as they form (np stays below 64)
+                while (__any_sync(0xffffffffu, mask != 0)) {
+                    const bool have = mask != 0;
+                    const unsigned int bal = __ballot_sync(0xffffffffu, have);
+                    if (have) {
+                        const int pos = 31 - __clz(mask);
+                        mask &= ~(1u << pos);
+                        put(np + __popc(bal & lt), pos);
+                    }
+                    np += __popc(bal);
+                    __syncwarp();
+                    if (np >= 32) exact_batch(32);
+                }
+            }
         }
         __syncwarp();                                    // every lane is done with the stage
         if (issued < my_tiles) {                         // refill it with the tile kTmaStages ahead
