@@ -85,7 +85,8 @@ for c in (2, 3, 4, 5):
             if w in hdr:
                 e[w] = r[hdr.index(w)] + " " + units[hdr.index(w)]
         out.append(e)
-        short = "seg" if "seg_" in k else "filter" if "filter_" in k else "nms" if "nms_" in k else "conf_cut" if "conf_cut" in k else k[:20]
+        short = ("redo" if "detect_fused" in k else "seg" if "seg_" in k else "filter" if "filter_" in k else "nms" if "nms_kernel" in k
+                 else "conf_cut" if "conf_cut" in k else k[:20])
         try:
             def b(m):
                 v = float(r[hdr.index(m)].replace(",", ""))
