@@ -1,7 +1,7 @@
 O=gpurun_out; mkdir -p $O
 nvidia-smi -L | head -4
 timeout 600 python -m pytest tests/test_distributed_nccl.py -m gpu -q > $O/x13_nccl_test.log 2>&1; tail -2 $O/x13_nccl_test.log
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 100 --warmup 10 > $O/r2_bench_cfg2_n2.json 2> $O/x13_n2.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 2 --steps 100 --warmup 10 > $O/r2_bench_cfg2_n2.json 2> $O/x13_n2.err
 python - <<'PY'
 import json
 d = json.load(open("gpurun_out/r2_bench_cfg2_n2.json"))
