@@ -262,3 +262,29 @@ def test_head_convs_detect_convs_on_cuda(golden, half):
     assert sum(d.shape[0] for d in out) > 0
     for d, w in zip(out, want_det):
         assert torch.equal(d.float().cpu(), w)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_autoshape_postprocess_sequence_on_cuda(fx, fused):
+    """``AutoShape.forward``'s post-network part (core/models/common.py:775-778): NMS with keyword arguments, then
+    ``scale_coords(shape1, y[i][:, :4], shape0[i])`` IN PLACE on a slice view, result discarded - both names are imported
+    by common.py:22-24 and patched by ``install()``.  Expected: the oracle's NMS on the kernel's decoded prediction, rescaled
+    by the oracle's scale_coords."""
+    from desenet_b200 import patch
+    from oracle import port
+    ns, names = standin.fake_reference_modules(f"dsn_fake_gpu_autoshape_{int(fused)}")
+    model = standin.Model(fx).cuda().eval()
+    x = torch.zeros(2, 3, 128, 128).cuda()
+    shape1, shape0 = [128, 128], [(96, 128), (240, 320)]
+    with patch.install(model=model, fused=fused, modules=names):
+        with torch.no_grad():
+            y = model(x, False, False)[0][0]                                           # common.py:773 (the detection half)
+        y = ns.detect.non_max_suppression(y, 0.001, iou_thres=0.45, classes=None, multi_label=False, max_det=1000)  # :775-776
+        for i in range(2):
+            ns.detect.scale_coords(shape1, y[i][:, :4], shape0[i])                     # :777-778, in place
+    want = port.non_max_suppression(_decoded(None, fx), 0.001, 0.45, classes=None, multi_label=False, max_det=1000, nms_impl="c")
+    assert sum(w.shape[0] for w in want) > 0
+    for i in range(2):
+        w = want[i].clone()
+        w[:, :4] = port.scale_coords(shape1, w[:, :4].clone(), shape0[i])[:, :4]
+        assert y[i].is_cuda and _close(y[i].cpu().numpy(), w.numpy()), f"image {i}"
