@@ -564,7 +564,7 @@ def run_config(args, cfg_id, rank, world, local_rank, dev, *, primary, host_info
             q = lpp[0]
             ops.nms_levels(heads[0], q.keys, q.counts, kw["conf_thres"], kw["iou_thres"], kw["agnostic"], kw["max_det"],
                            det=lpp[i % n_fl].det, det_count=lpp[i % n_fl].det_count, cut=q.cut if q.conf_cut else None,
-                           cta_threads=512 if mode == "eval" else 0)          # as PostProcessor._det launches it
+                           cta_threads=pp.nms_cta_threads)                    # as PostProcessor._det launches it
 
         if pp.conf_cut:
             kern_us["conf_cut"] = time_alone(lambda i: ops.conf_cut_levels(heads[i % nbuf], kw["conf_thres"], kw["multi_label"], kw["classes"],

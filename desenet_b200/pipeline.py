@@ -16,7 +16,8 @@ class PostProcessor:
                  iou_thres=0.45, classes=None, agnostic=False, multi_label=False, max_det=300, mode="detect",
                  nclass: Optional[int] = None, mask_dtype=torch.float32, device=None, overlap_streams=True,
                  na: int = 3, fused_det: bool = False, scale_params: Optional[torch.Tensor] = None, round_boxes: bool = False,
-                 conf_cut: Optional[bool] = None, det_out=None, det_count_out=None, gather=None):
+                 conf_cut: Optional[bool] = None, det_out=None, det_count_out=None, gather=None,
+                 nms_cta_threads: Optional[int] = None):
         """``det_out`` / ``det_count_out``: write the detections there instead of into buffers of this object (tensors, or
         ``peer.RawView`` slices of a gather root's buffer); ``gather = (PeerGather, slot)``: after the detection chain of a
         batch, signal the root that this rank's rows of that slot are complete (see ``desenet_b200.peer``)."""
@@ -60,6 +61,13 @@ class PostProcessor:
         self.conf_cut = self.conf_cut and not fused_det
         with torch.cuda.device(d):
             self.cut = ops.ConfCut(bs, d) if self.conf_cut else None
+        # NMS CTA size (ops.nms_levels).  Eval mode: the persistent eval seg kernel leaves no room for a second kernel's CTAs
+        # on an SM, so the NMS runs before / after it at full width and the 512-thread CTA is the right one.  Detect mode:
+        # the library's rule (256 threads between the short-lived CTAs of the mask kernel).  (A 1024-thread instantiation
+        # was measured for small eval batches - NMS alone 39.8 -> 37.2 us at 64 images, step 75.0 -> 79.8 us - and dropped.)
+        if nms_cta_threads is None:
+            nms_cta_threads = 512 if mode == "eval" else 0
+        self.nms_cta_threads = int(nms_cta_threads)
         self._last_head = None
         # cut + filter + NMS + redo (all CTAs of the redo exit at once unless an image was starved) | filter + NMS | fused
         self.kernels_per_step = (1 if fused_det else (4 if self.conf_cut else 2)) + (0 if mode == "det_only" else 1) \
@@ -110,11 +118,8 @@ class PostProcessor:
                                       cut=self.cut)
         ops.filter_levels(head, kw["conf_thres"], kw["multi_label"], kw["classes"], cap=int(self.keys.shape[1]),
                           keys=self.keys, counts=self.counts, cut=cut)
-        # eval mode: the persistent eval seg kernel leaves no room for a second kernel's CTAs on an SM, so the NMS runs
-        # before / after it at full width and the 512-thread CTA (fastest per image) is the right one; in detect mode the
-        # library's rule applies (256 threads between the short-lived CTAs of the mask kernel)
         ops.nms_levels(head, self.keys, self.counts, kw["conf_thres"], kw["iou_thres"], kw["agnostic"], kw["max_det"],
-                       det=self.det, det_count=self.det_count, cut=cut, cta_threads=512 if self.mode == "eval" else 0)
+                       det=self.det, det_count=self.det_count, cut=cut, cta_threads=self.nms_cta_threads)
         if cut is not None:
             # images the sampled cut starved (det_count == -2) are redone uncut on the device, inside the same enqueue /
             # graph: a negative count never reaches a consumer (HostPipeline, DetEvaluator, graph replay)
