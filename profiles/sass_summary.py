@@ -1,7 +1,7 @@
 """Opcode summary of the built library's SASS (run in the build container, no GPU needed):
     python profiles/sass_summary.py > profiles/r2_sass_opcodes.txt
 Per kernel: instruction count and the counts of the mnemonics that evidence the Blackwell-specific paths (UBLKCP = TMA bulk
-copy, SYNCS = mbarrier, FFMA2 / FMUL2 = packed fp32x2 arithmetic, REDUX = warp reduction, MATCH = warp match, UCGABAR =
+copy, UTMALDG = TMA tensor-map copy, SYNCS = mbarrier, FFMA2 / FMUL2 = packed fp32x2 arithmetic, REDUX = warp reduction, MATCH = warp match, UCGABAR =
 cluster barrier, UTCHMMA / LDTM / UTCBAR = tcgen05.mma / tcgen05.ld / tcgen05.commit, LDG/STG widths)."""
 import collections
 import os
@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 LIB = os.path.join(ROOT, "desenet_b200", "lib", "libdesenet_b200.so")
-WATCH = ["UBLKCP", "SYNCS", "FFMA2", "FMUL2", "FADD2", "REDUX", "MATCH", "UCGABAR", "LDG.E.128", "LDG.E.64", "STG.E.128", "STG.E.64", "LDS.128",
+WATCH = ["UBLKCP", "UTMALDG", "SYNCS", "FFMA2", "FMUL2", "FADD2", "REDUX", "MATCH", "UCGABAR", "LDG.E.128", "LDG.E.64", "STG.E.128", "STG.E.64", "LDS.128",
          "STS.128", "UTCHMMA", "LDTM", "UTCBAR", "UTCATOMSWS", "ATOMS", "ATOMG", "RED", "MUFU", "BAR.SYNC", "SHFL", "VOTE", "DMUL", "DFMA", "LDGSTS", "ERRBAR", "MEMBAR"]
 
 
