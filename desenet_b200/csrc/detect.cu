@@ -317,15 +317,17 @@ __global__ void __launch_bounds__(kDenseThreads, 3) filter_dense_kernel(const He
 // a warp loads its tile (one DRAM round trip), works on it with nothing in flight, and leaves; the parked copy of the tile
 // costs 68 KB of shared memory per CTA and caps the occupancy at 24 warps per SM (cfg 3: 0.46 of the HBM peak).  Here every
 // warp is a small persistent pipeline of its own: it walks a contiguous range of tiles (128 cells x (1 + nc) planes) and
-// keeps kTmaStages tiles in flight with TMA bulk copies (cp.async.bulk global -> shared, one 512-byte row per plane,
-// completion on one mbarrier per stage) - no registers hold data in flight, the tile arrives where the later passes index
-// it, and nothing is parked.  What is left is instruction issue, so the tile body is written for instruction count:
+// keeps kTmaStages tiles in flight with TMA - ONE 3-D tensor-map copy per tile (cp.async.bulk.tensor.3d, box = 128 cells x
+// (1 + nc) channels x 1 image; per-plane bulk copies when no tensor map can be encoded), completion on one mbarrier per
+// stage - no registers hold data in flight, the tile arrives where the later passes index it, and nothing is parked.
+// What is left is instruction issue, so the tile body is written for instruction count:
 //   * a lane owns 4 cells; per cell the logit-space bound L of the kernel above, +inf for cells that cannot pass at all;
 //   * per (cell, class) ONE subtraction L - logit whose sign bit is shifted into the lane's 24-bit mask (funnel shift):
 //     two instructions per pair, no predicates;
-//   * the pairs above the bound (4-5 % at the eval setting with the confidence cut) are moved, one per lane and round,
-//     into a small PENDING list that survives across tiles, and the exact arithmetic (sigmoid * sigmoid, the strict
-//     compares of general.py:710-711, the cut on the key) runs only on FULL batches of 32 pending pairs;
+//   * the pairs above the bound (4-5 % at the eval setting with the confidence cut) are appended, behind one warp scan
+//     (one per lane and round for a dense tile), to a small PENDING list that survives across tiles, and the exact
+//     arithmetic (sigmoid * sigmoid, the strict compares of general.py:710-711, the cut on the key) runs only on FULL
+//     batches of 32 pending pairs;
 //   * keys are staged per warp and leave with one atomic per batch of up to 128.
 // Warps never synchronise with each other.
 #ifndef DSN_TMA_WARPS

@@ -10,11 +10,11 @@
 //      reference candidate order = torchvision's stable sort),
 //   3. fetch their boxes (decode on the fly from the raw head planes, or from z), add the class
 //      offset (general.py:732-733),
-//   4. suppress against the survivors so far, resolve the chunk in 64-wide sub-blocks with a
+//   4. suppress against the survivors so far, resolve the chunk in rounds of 256 candidates with a
 //      bitmask + serial scan, append survivors to the output (general.py:745),
 // and stops at max_det survivors (general.py:735-736), after max_nms candidates
-// (general.py:728-729) or when the keys are exhausted.  Latency-bound, not HBM-bound: it runs next
-// to the streaming kernels on otherwise idle SMs.
+// (general.py:728-729) or when the keys are exhausted.  Latency-bound, not HBM-bound.  Two instantiations of the kernel
+// (nms_launch.cuh): 512-thread CTAs here, 256-thread CTAs in nms_small.cu; dsn_nms_levels_cta picks.
 #include "nms_launch.cuh"
 
 // the 256-thread instantiation (nms_small.cu)
