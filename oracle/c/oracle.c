@@ -123,3 +123,20 @@ void orc_confusion_matrix(const int32_t *pred, const int64_t *target, int64_t n,
         cm[(int64_t)r * C + pred[i]] += 1;
     }
 }
+
+/* ---- 1x1 convolution with bias as ONE fused multiply-add per term, in input-channel order, fp32:
+ *      the heads' last convolutions, nn.Conv2d(c_hid, n_segcls, 1) (core/models/yolo.py:182) and Detect.m[i] =
+ *      nn.Conv2d(ch[i], na * no, 1) (core/models/yolo.py:252, applied at :258).  The reference's own convolution (MKL-DNN /
+ *      cuDNN) has an unspecified summation order, so this restatement pins the ORDER the CUDA producers use
+ *      (acc = bias; acc = fma(w[n][k], x[k], acc) for k = 0 .. K-1), which the GPU tests then match bit for bit; its
+ *      distance to the exact (float64) convolution is checked separately.
+ *      x (bs, K, plane), w (N, K), bias (N) or NULL, out (bs, N, plane). ---- */
+void orc_conv1x1_fma(const float *x, const float *w, const float *bias, int64_t bs, int K, int N, int64_t plane, float *out) {
+    for (int64_t b = 0; b < bs; ++b)
+        for (int n = 0; n < N; ++n)
+            for (int64_t p = 0; p < plane; ++p) {
+                float acc = bias ? bias[n] : 0.0f;
+                for (int k = 0; k < K; ++k) acc = fmaf(w[(int64_t)n * K + k], x[(b * K + k) * plane + p], acc);
+                out[(b * N + n) * plane + p] = acc;
+            }
+}

@@ -65,3 +65,16 @@ def confusion_matrix(pred: np.ndarray, target: np.ndarray, C: int, rows: int) ->
     cm = np.zeros((rows, C), np.int64)
     lib().orc_confusion_matrix(_p(p), _p(t), ctypes.c_int64(p.size), C, rows, _p(cm))
     return cm
+
+
+def conv1x1_fma(x: np.ndarray, w: np.ndarray, bias) -> np.ndarray:
+    """yolo.py:182 / :252,258 as one fp32 FMA per term in channel order (see oracle.c: orc_conv1x1_fma)."""
+    x = np.ascontiguousarray(x, np.float32)
+    bs, K = x.shape[:2]
+    plane = int(np.prod(x.shape[2:]))
+    w = np.ascontiguousarray(w, np.float32).reshape(-1, K)
+    N = w.shape[0]
+    b = None if bias is None else np.ascontiguousarray(bias, np.float32).reshape(N)
+    out = np.empty((bs, N) + x.shape[2:], np.float32)
+    lib().orc_conv1x1_fma(_p(x), _p(w), _p(b) if b is not None else None, ctypes.c_int64(bs), K, N, ctypes.c_int64(plane), _p(out))
+    return out

@@ -646,3 +646,23 @@ def test_detect_head_conv1x1_fp32_and_filter_chain(dsn):
     assert sum(d.shape[0] for d in dets) > 0
     for d, w_ in zip(dets, want):
         assert torch.equal(d.cpu(), w_)
+
+
+def test_fp32_head_convs_bit_exact_vs_c_oracle(dsn, golden):
+    """Both fp32 head-conv producers accumulate one FMA per term in channel order from the bias: bit-identical to the C
+    oracle's orc_conv1x1_fma (yolo.py:182 and yolo.py:252,258), for fp32 inputs and for fp16 inputs converted on load."""
+    from desenet_b200 import ops
+    g = golden("real_desenet_s128_headconv.npz")
+    feat, w, b = g["feat"], g["weight"], g["bias"]
+    low = ops.seg_head_conv1x1(dev(feat), dev(w), dev(b))
+    assert np.array_equal(low.cpu().numpy(), cport.conv1x1_fma(feat, w, b))
+    fh = torch.from_numpy(feat).half()
+    low_h = ops.seg_head_conv1x1(fh.cuda(), dev(w), dev(b))
+    assert np.array_equal(low_h.cpu().numpy(), cport.conv1x1_fma(fh.float().numpy(), w, b))
+    rng = np.random.default_rng(5)
+    for bs, K, ny, nx, N in ((2, 128, 20, 20, 33), (1, 64, 7, 9, 33), (1, 256, 10, 10, 80)):
+        x = rng.standard_normal((bs, K, ny, nx), np.float32)
+        wt = (rng.standard_normal((N, K), np.float32) / np.sqrt(K)).astype(np.float32)
+        bias = rng.standard_normal(N, np.float32)
+        out = ops.detect_head_conv1x1(dev(x), dev(wt).view(N, K, 1, 1), dev(bias))
+        assert np.array_equal(out.cpu().numpy(), cport.conv1x1_fma(x, wt, bias)), (bs, K, ny, nx, N)

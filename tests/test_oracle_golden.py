@@ -127,3 +127,24 @@ def test_seg_validation_accumulate():
     batches = [(torch.randn(2, 2, 16, 16, generator=g), torch.randint(0, 2, (2, 16, 16), generator=g)) for _ in range(3)]
     pa, miou = port.seg_validation_accumulate(batches, 2)
     assert 0.3 < pa < 0.7 and 0.2 < miou < 0.5
+
+
+def test_conv1x1_oracle_against_exact_convolution_and_reference_fixture(golden):
+    """oracle.c: orc_conv1x1_fma (the summation order the CUDA head-conv producers use) stays within 1e-6 of the exact
+    float64 convolution relative to the sum of |terms|, and within 1e-5 of the reference's own conv output on the real
+    model's tensors (fixture generated by tests/golden/make_golden_headconv.py from core/models/yolo.py:182)."""
+    import torch
+    from oracle import cport
+    g = golden("real_desenet_s128_headconv.npz")
+    got = cport.conv1x1_fma(g["feat"], g["weight"], g["bias"])
+    exact = torch.nn.functional.conv2d(torch.from_numpy(g["feat"]).double(), torch.from_numpy(g["weight"]).double(),
+                                       torch.from_numpy(g["bias"]).double()).numpy()
+    scale = torch.nn.functional.conv2d(torch.from_numpy(np.abs(g["feat"])).double(), torch.from_numpy(np.abs(g["weight"])).double(),
+                                       torch.from_numpy(np.abs(g["bias"])).double()).numpy()
+    assert (np.abs(got - exact) <= 1e-6 * scale).all()
+    assert (np.abs(got - g["seg_low"]) <= 1e-5 * scale).all()
+    rng = np.random.default_rng(3)
+    x, w, b = rng.standard_normal((2, 37, 5, 7), np.float32), rng.standard_normal((33, 37), np.float32), rng.standard_normal(33, np.float32)
+    ref = torch.nn.functional.conv2d(torch.from_numpy(x).double(), torch.from_numpy(w).double().view(33, 37, 1, 1), torch.from_numpy(b).double()).numpy()
+    assert np.allclose(cport.conv1x1_fma(x, w, b), ref, rtol=0, atol=1e-4)
+    assert np.array_equal(cport.conv1x1_fma(x, w, None), cport.conv1x1_fma(x, w, np.zeros(33, np.float32)))
